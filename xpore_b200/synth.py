@@ -1,0 +1,217 @@
+"""Synthetic ``xpore dataprep`` output of the BASELINE.json shapes.
+
+Two producers share one statistical model:
+
+* :func:`write_dataset` — real ``data.json`` / ``data.index`` per run plus ``config.yml``
+  (format of ``xpore/scripts/dataprep.py:485-495,642-651``), for the CLI, the golden fixtures
+  and the reference runs;
+* :func:`make_batch` — the same model written straight into a CSR :class:`~xpore_b200.batch.Batch`
+  (vectorised; used by ``bench.py`` at 10^6 positions where a text round trip is pointless).
+
+Model: k-mer per position uniform over the 1024 non-``N`` 5-mers; unmodified reads
+~ N(mu_kmer, sigma_kmer); a fraction ``f_mod`` of positions is modifiable, there modified reads
+~ N(mu_kmer +/- U(3,8), 1.3 sigma_kmer) with rate 0.6 in normal conditions and 0.05 in
+"KO-like" ones; values rounded to 2 decimals (``dataprep.py:638``).
+"""
+from __future__ import annotations
+
+import json
+import os
+from collections import OrderedDict
+from dataclasses import dataclass, field
+
+import numpy as np
+import yaml
+
+from .batch import Batch, Layout
+from .kmer_model import KmerModel
+
+
+@dataclass
+class Spec:
+    conditions: dict  # {condition: n_replicates}, config order
+    ko_like: tuple = ("KO",)
+    n_genes: int = 1
+    pos_per_gene: int = 100
+    reads_lo: int = 50
+    reads_hi: int = 200  # per run, inclusive
+    f_mod: float = 0.4
+    seed: int = 0
+    loguniform_total: tuple | None = None  # (lo, hi): total reads/position log-uniform, split evenly
+    method: dict = field(default_factory=dict)
+    criteria: dict | None = None
+
+    def data_info(self, root="."):
+        info = OrderedDict()
+        for c, nrep in self.conditions.items():
+            info[c] = OrderedDict()
+            for r in range(1, nrep + 1):
+                info[c]["%s-rep%d" % (c, r)] = os.path.join(root, "%s_rep%d" % (c, r))
+        return info
+
+
+# The five BASELINE.json configs.
+def config_spec(name: str) -> Spec:
+    if name == "c1":
+        return Spec({"KO": 2, "WT": 2}, n_genes=1, pos_per_gene=100, reads_lo=50, reads_hi=200, f_mod=0.4,
+                    seed=0, method={"prefiltering": {"method": "t-test", "threshold": 0.1}})
+    if name == "c2":
+        return Spec({"KO": 3, "WT": 3}, n_genes=10000, pos_per_gene=100, reads_lo=20, reads_hi=100, f_mod=0.1,
+                    seed=1, method={"prefiltering": {"method": "t-test", "threshold": 0.1}})
+    if name == "c3":
+        return Spec({"KO": 3, "WT": 3}, n_genes=10000, pos_per_gene=100, reads_lo=20, reads_hi=100, f_mod=0.1,
+                    seed=1, method={"pooling": True, "max_iters": 500})
+    if name == "c4":
+        return Spec({"KO": 2, "WT": 2}, n_genes=1000, pos_per_gene=100, f_mod=0.3, seed=2,
+                    loguniform_total=(20, 5000), criteria={"readcount_min": 5, "readcount_max": 5000})
+    if name == "c5":
+        conds = OrderedDict((c, 3) for c in ["A549", "HEK293T", "HEPG2", "K562", "KO", "MCF7"])
+        return Spec(conds, n_genes=20000, pos_per_gene=100, reads_lo=20, reads_hi=60, f_mod=0.1, seed=3,
+                    method={"prefiltering": {"method": "t-test", "threshold": 0.1}})
+    raise KeyError(name)
+
+
+def _counts(spec: Spec, rng, P: int, G: int) -> np.ndarray:
+    if spec.loguniform_total is not None:
+        lo, hi = spec.loguniform_total
+        tot = np.exp(rng.uniform(np.log(lo), np.log(hi), size=P))
+        return np.maximum(1, np.round(tot / G)).astype(np.int64)[:, None].repeat(G, axis=1)
+    return rng.integers(spec.reads_lo, spec.reads_hi + 1, size=(P, G))
+
+
+def _draw(spec: Spec, rng, km: KmerModel, P: int):
+    """Per-position parameters and per-run read counts for P positions."""
+    info = spec.data_info()
+    lay = Layout.from_data_info(info, pooling=False)
+    G = lay.n_groups
+    rows = km.usable_rows()
+    krow = rows[rng.integers(0, len(rows), size=P)]
+    mu, sd = km.mean[krow], km.stdv[krow]
+    is_mod = rng.random(P) < spec.f_mod
+    shift = rng.uniform(3.0, 8.0, size=P) * np.where(rng.random(P) < 0.5, -1.0, 1.0)
+    counts = _counts(spec, rng, P, G)
+    ko = np.array([lay.condition_names[c] in spec.ko_like for c in lay.run_cond])
+    rate = np.where(ko, 0.05, 0.6)[None, :] * is_mod[:, None]  # [P, G]
+    return lay, krow, mu, sd, shift, counts, rate
+
+
+def _reads(rng, mu, sd, shift, rate, n):
+    """n reads of one (position, run)."""
+    mod = rng.random(n) < rate
+    y = rng.normal(mu, sd, size=n)
+    if mod.any():
+        y[mod] = rng.normal(mu + shift, 1.3 * sd, size=int(mod.sum()))
+    return np.round(y, 2)
+
+
+def write_dataset(root: str, spec: Spec, km: KmerModel | None = None, first_pos: int = 100) -> str:
+    """Write ``<root>/<cond>_rep<i>/data.{json,index}`` and ``<root>/config.yml``; returns the
+    config path.  ``out`` in the YAML is ``<root>/out``."""
+    km = km or KmerModel.load()
+    rng = np.random.default_rng(spec.seed)
+    info = spec.data_info(root)
+    P = spec.n_genes * spec.pos_per_gene
+    lay, krow, mu, sd, shift, counts, rate = _draw(spec, rng, km, P)
+    files = []
+    for r, (c, run) in enumerate((c, run) for c, rd in info.items() for run in rd):
+        d = info[c][run]
+        os.makedirs(d, exist_ok=True)
+        files.append((open(os.path.join(d, "data.json"), "w"), open(os.path.join(d, "data.index"), "w")))
+        files[-1][1].write("idx,start,end\n")
+    for gi in range(spec.n_genes):
+        idx = "ENST%011d" % (gi + 1)
+        for r, (fj, fi) in enumerate(files):
+            data = OrderedDict()
+            for j in range(spec.pos_per_gene):
+                p = gi * spec.pos_per_gene + j
+                y = _reads(rng, mu[p], sd[p], shift[p], rate[p, r], int(counts[p, r]))
+                data[str(first_pos + j)] = {km.kmers[krow[p]]: [float(v) for v in y]}
+            start = fj.tell()
+            fj.write("{")
+            fj.write('"%s":' % idx)
+            json.dump(data, fj, separators=(",", ":"))
+            fj.write("}\n")
+            end = fj.tell()
+            fi.write("%s,%d,%d\n" % (idx, start, end))
+    for fj, fi in files:
+        fj.close()
+        fi.close()
+    cfg = {"data": {c: {run.split("-", 1)[1]: d for run, d in rd.items()} for c, rd in info.items()},
+           "out": os.path.join(root, "out")}
+    if spec.method:
+        cfg["method"] = dict(spec.method)
+    if spec.criteria:
+        cfg["criteria"] = dict(spec.criteria)
+    path = os.path.join(root, "config.yml")
+    with open(path, "w") as f:
+        yaml.safe_dump(cfg, f, sort_keys=False)
+    return path
+
+
+def make_batch(spec: Spec, km: KmerModel | None = None, n_positions: int | None = None,
+               chunk: int = 50000, seed_offset: int = 0, keys: bool = False) -> Batch:
+    """The dataset of ``spec`` as a CSR batch, drawn chunk by chunk (vectorised).
+
+    The read-count criteria of the config are applied like ``io.py:51-52,70-80`` so that the
+    batch holds exactly the positions the packer would keep.  ``seed_offset`` decorrelates the
+    shards of different ranks."""
+    km = km or KmerModel.load()
+    rng = np.random.default_rng([spec.seed, seed_offset])
+    pooling = bool(spec.method.get("pooling", False))
+    info = spec.data_info()
+    lay_runs = Layout.from_data_info(info, pooling=False)
+    lay = Layout.from_data_info(info, pooling=pooling)
+    crit = spec.criteria or {"readcount_min": 15, "readcount_max": 1000}
+    lo, hi = crit["readcount_min"], crit["readcount_max"]
+    P_all = n_positions if n_positions is not None else spec.n_genes * spec.pos_per_gene
+    run_cond = np.asarray(lay_runs.run_cond)
+    C = lay.n_conditions
+    ys, glens, kms, kss, krows = [], [], [], [], []
+    for c0 in range(0, P_all, chunk):
+        P = min(chunk, P_all - c0)
+        _, krow, mu, sd, shift, counts, rate = _draw(spec, rng, km, P)
+        if pooling:
+            csum = np.stack([counts[:, run_cond == c].sum(axis=1) for c in range(C)], axis=1)
+            keep = ((csum >= lo) & (csum <= hi)).sum(axis=1) >= 2
+        else:
+            ok = (counts >= lo) & (counts <= hi)
+            counts = np.where(ok, counts, 0)
+            has = np.stack([ok[:, run_cond == c].any(axis=1) for c in range(C)], axis=1)
+            keep = has.sum(axis=1) >= 2
+        krow, mu, sd, shift, counts, rate = (a[keep] for a in (krow, mu, sd, shift, counts, rate))
+        P = len(krow)
+        n_pr = counts.reshape(-1)  # [P*Gruns], run-major within position
+        R = int(n_pr.sum())
+        cell = np.repeat(np.arange(P * counts.shape[1]), n_pr)
+        pos = cell // counts.shape[1]
+        mod = rng.random(R) < rate.reshape(-1)[cell]
+        y = rng.normal(mu[pos], sd[pos])
+        ym = rng.normal(mu[pos] + shift[pos], 1.3 * sd[pos])
+        y = np.round(np.where(mod, ym, y), 2)
+        if pooling:
+            # reads must be contiguous per condition slot (sorted condition order)
+            order = np.argsort(run_cond, kind="stable")
+            if not (order == np.arange(len(order))).all():
+                cell_rank = np.empty_like(order)
+                cell_rank[order] = np.arange(len(order))
+                key = pos * counts.shape[1] + cell_rank[cell % counts.shape[1]]
+                y = y[np.argsort(key, kind="stable")]
+            glen = np.stack([counts[:, run_cond == c].sum(axis=1) for c in range(C)], axis=1)
+        else:
+            glen = counts
+        ys.append(y)
+        glens.append(glen.astype(np.int32))
+        kms.append(mu)
+        kss.append(sd)
+        krows.append(krow)
+    grp_len = np.concatenate(glens)
+    read_off = np.zeros(len(grp_len) + 1, dtype=np.int64)
+    np.cumsum(grp_len.sum(axis=1, dtype=np.int64), out=read_off[1:])
+    b = Batch(lay, np.concatenate(ys), read_off, np.ascontiguousarray(grp_len),
+              np.concatenate(kms), np.concatenate(kss))
+    if keys:
+        krow = np.concatenate(krows)
+        b.ids = ["ENST%011d" % (i // spec.pos_per_gene + 1) for i in range(b.n_positions)]
+        b.positions = [str(100 + i % spec.pos_per_gene) for i in range(b.n_positions)]
+        b.kmers = [km.kmers[k] for k in krow]
+    return b.validate()
