@@ -1,0 +1,139 @@
+/* xpore_b200.h — C ABI of the B200 diffmod hot path (libxpore_b200.so).
+ *
+ * The reference (GoekeLab/xpore) is pure Python and has no FFI; its seam for this path is
+ *   xpore/scripts/diffmod.py:15  execute(idx, data_dict, ...)            one gene
+ *   xpore/diffmod/io.py:21       load_data(...) -> {(idx,pos,kmer): {y,x,r,...}}
+ *   xpore/diffmod/statstest.py:4 StatsTest(data).fit('t-test')           prefilter
+ *   xpore/diffmod/gmm.py:11,93   GMM(method, data, priors, kmer_signal).fit()
+ *   xpore/diffmod/io.py:230      generate_result_table(models, data_info)
+ * i.e. "positions in, table values out".  This library is that seam for a whole batch of
+ * positions at once: plain pointers and sizes, no Python or torch types.  INTEGRATION.md shows
+ * the ctypes stub a maintainer of the reference would add inside execute().
+ *
+ * Conventions
+ *  - Ownership: the caller allocates every buffer; the library never frees caller memory.
+ *  - Errors: every entry point returns 0 on success, a negative XPB200_E* code otherwise;
+ *    xpb200_last_error() (thread-local) describes the failure.  Numerical conditions of single
+ *    positions (ELBO decreased, iteration cap) are reported in `status`, never abort the batch
+ *    (the reference prints and continues, gmm.py:111-115).
+ *  - Threading: calls on different contexts/streams are independent; one batch in flight per
+ *    context.
+ *  - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef XPORE_B200_H
+#define XPORE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XPB200_OK 0
+#define XPB200_EINVAL (-1)   /* bad argument / unsupported shape */
+#define XPB200_ECUDA (-2)    /* CUDA runtime error */
+#define XPB200_ENOMEM (-3)   /* workspace too small / allocation failed */
+
+/* status bits (per position) */
+#define XPB200_SELECTED 1u        /* passed the prefilter gate (diffmod.py:54): position was fitted */
+#define XPB200_CONVERGED 2u       /* gmm.py:120-122 */
+#define XPB200_ELBO_DECREASED 4u  /* gmm.py:110-115 */
+#define XPB200_HIT_MAX 8u         /* ran max_iters-1 sweeps (gmm.py:103) */
+#define XPB200_KEEP_ROW 16u       /* survives the row filter io.py:363-367 */
+#define XPB200_MOD_IS_1 32u       /* modified cluster = component 1 (io.py:277-282) */
+#define XPB200_HIGHER 64u         /* mod_assignment == "higher" (io.py:288) */
+#define XPB200_TTEST_VALID 128u   /* exactly two conditions present (statstest.py:20-21) */
+
+/* A CSR-packed ragged batch of positions (what io.load_data yields for many genes).
+ * Reads of a position are contiguous, and within the position contiguous per group slot, in
+ * slot order.  A group slot is a run (default) or a condition (method.pooling); a slot with
+ * grp_len == 0 is absent at that position (run filtered by readcount, io.py:51-52). */
+typedef struct xpb200_batch {
+    int32_t n_positions;      /* P */
+    int32_t n_groups;         /* G  (1..64) */
+    int32_t n_conditions;     /* C  (1..32) */
+    int32_t max_reads;        /* max over positions of reads per position */
+    int64_t n_reads;          /* R = read_off[P] */
+    const double* y;          /* [R rounded up to even]  event means (data.json values)      */
+    const int64_t* read_off;  /* [P+1]                                                       */
+    const int32_t* grp_len;   /* [P*G]                                                       */
+    const double* kmer_mean;  /* [P] model_kmer.csv model_mean of the position's k-mer       */
+    const double* kmer_std;   /* [P] model_kmer.csv model_stdv                               */
+    const int32_t* grp_cond;  /* [G] condition index (rank among sorted condition names)     */
+} xpb200_batch;
+
+/* method section of the YAML (configurator.py:46-60) + the fixed priors (:62-77). */
+typedef struct xpb200_method {
+    int32_t max_iters;           /* default 500; at most max_iters-1 sweeps are run */
+    int32_t prefilter;           /* 0 = off, 1 = t-test (statstest.py); other methods => NaN => fit all */
+    double stopping_criteria;    /* default 1e-5 */
+    double prefilter_threshold;  /* fit iff isnan(p) || p < threshold (diffmod.py:54) */
+    double dirichlet_conc;       /* 0.001 (configurator.py:72) */
+} xpb200_method;
+
+/* Result arrays, all [P, width] row-major; rows of positions that were not selected are left
+ * untouched except status and pval. */
+typedef struct xpb200_result {
+    uint32_t* status;  /* [P] */
+    int32_t* n_iter;   /* [P] sweeps run (GMM.info['n_iterations']) */
+    double* pval;      /* [P] prefilter p-value (NaN when not applicable / prefilter off) */
+    double* fit;       /* [P, xpb200_fit_width(G)]  mu0 mu1 lam0 lam1 alpha0 alpha1 beta0 beta1 elbo N[g][k] */
+    double* stats;     /* [P, xpb200_stats_width(G,C)] mu_unmod mu_mod s2_unmod s2_mod conf_unmod conf_mod
+                          p_overlap cdf[4] mod_rate[G] coverage[G] pairwise[C(C,2)][diff,pval,z]
+                          one_vs_all[C][diff,pval,z] (only when C > 2) */
+} xpb200_result;
+
+int32_t xpb200_fit_width(int32_t n_groups);
+int32_t xpb200_stats_width(int32_t n_groups, int32_t n_conditions);
+
+/* Bytes of device scratch xpb200_fit_device needs for P positions. */
+size_t xpb200_workspace_bytes(int32_t n_positions);
+
+/* Whole path on DEVICE pointers: prefilter t-test -> worklist -> VB-EM fit -> statistics,
+ * enqueued on `cuda_stream` (a cudaStream_t, may be NULL); does not synchronise.
+ * `n_fitted_dev` (optional, device uint32) receives the number of selected positions. */
+int32_t xpb200_fit_device(const xpb200_batch* batch, const xpb200_method* method, const xpb200_result* result,
+                          void* workspace, size_t workspace_bytes, uint32_t* n_fitted_dev, void* cuda_stream);
+
+/* Same path on HOST pointers (the drop-in call): copies the batch to the device, runs, copies
+ * the results back, synchronises.  `device` is the CUDA ordinal.  Pinned host buffers make the
+ * copies asynchronous; pageable ones work too.  `n_fitted` (optional) gets the selected count. */
+int32_t xpb200_fit_host(int32_t device, const xpb200_batch* batch, const xpb200_method* method,
+                        const xpb200_result* result, uint32_t* n_fitted);
+
+/* Release the cached device buffers of xpb200_fit_host (all devices). */
+void xpb200_release(void);
+
+/* Individual stages on device pointers (used by the tests and the profiler runs). */
+int32_t xpb200_prefilter_device(const xpb200_batch* batch, const xpb200_method* method, uint32_t* status,
+                                double* pval, void* cuda_stream);
+int32_t xpb200_stats_device(const xpb200_batch* batch, const xpb200_method* method, const xpb200_result* result,
+                            const int32_t* worklist, const uint32_t* n_work_dev, void* cuda_stream);
+
+/* Launch geometry the fit kernel would use for this batch (for reporting): */
+typedef struct xpb200_launch_info {
+    int32_t sm_count, ctas_per_sm, warps_per_cta, smem_per_cta, slab_reads, regs_per_thread;
+} xpb200_launch_info;
+int32_t xpb200_fit_launch_info(int32_t device, int32_t n_groups, int32_t max_reads, xpb200_launch_info* out);
+
+/* Kernel launches issued by this library in the calling thread since load (bench.py's gpu_launches). */
+uint64_t xpb200_launch_count(void);
+
+/* FP64 roofline denominator: dependent-free DFMA streams on every SM; returns TFLOP/s
+ * (2 flop per FMA) measured with CUDA events over `repeats` launches. */
+int32_t xpb200_measure_fp64_peak(int32_t device, int32_t repeats, double* tflops);
+
+/* Special functions exactly as the kernels evaluate them, run on the device over n values
+ * (device pointers); for the accuracy tests.  which: 0 psi, 1 lgamma, 2 log, 3 exp,
+ * 4 student_t two-sided p (x = t, aux = df), 5 E-step r1 (x = d), 6 E-step entropy term. */
+int32_t xpb200_eval_special(int32_t which, const double* x, const double* aux, double* out, int64_t n,
+                            void* cuda_stream);
+
+const char* xpb200_last_error(void);
+const char* xpb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XPORE_B200_H */

@@ -36,3 +36,154 @@ def gene_dict(idx, data_info, index, handles):
             else:
                 dd[(cond, run)] = None
     return dd
+
+
+# ---------------------------------------------------------------------------------------------
+# packing a golden case into a CSR batch and comparing result records with the reference
+# ---------------------------------------------------------------------------------------------
+def pack_case(config_path, ids):
+    """(batch, method dict, data_info) for a golden case via the product packer."""
+    from xpore_b200.batch import BatchBuilder, Layout
+    from xpore_b200.kmer_model import KmerModel
+
+    cfg, data_info, method, criteria, index, handles = open_case(config_path)
+    lay = Layout.from_data_info(data_info, method["pooling"])
+    bb = BatchBuilder(lay, KmerModel.load(), criteria["readcount_min"], criteria["readcount_max"])
+    for idx in ids:
+        bb.add_gene(idx, gene_dict(idx, data_info, index, handles))
+    for h in handles.values():
+        h.close()
+    return bb.build(), method, data_info
+
+
+def _num(v):
+    return float(v) if isinstance(v, str) else v
+
+
+def compare_with_golden(batch, res, method, expected, rtol_param=1e-5, rtol_p=1e-4, iters_exact=True):
+    """Assert a FitResult agrees with the reference outputs of a golden case:
+    selection exact; fitted set exact; parameters rel 1e-5; p-values rel 1e-4; rows exact set."""
+    import numpy as np
+
+    from xpore_b200 import fit as xf
+    from xpore_b200.table import get_result_table_header, result_rows
+
+    lay = batch.layout
+    keys = list(zip(batch.ids, batch.positions, batch.kmers))
+    # selection (io.py:21-90)
+    exp_sel = {tuple(s["key"]): s for s in expected["selected"]}
+    assert set(keys) == set(exp_sel)
+    n = np.diff(batch.read_off)
+    for i, k in enumerate(keys):
+        assert n[i] == exp_sel[k]["n_reads"]
+        present = [lay.group_names[g] for g in range(lay.n_groups) if batch.grp_len[i, g] > 0]
+        assert sorted(present) == sorted(exp_sel[k]["group_names"])
+    # fitted set (diffmod.py:52-58)
+    exp_fit = {tuple(p["key"]): p for p in expected["positions"]}
+    got_fit = {keys[i] for i in np.nonzero(res.selected)[0]}
+    assert got_fit == set(exp_fit), (sorted(got_fit ^ set(exp_fit)))
+    assert res.n_fitted == len(exp_fit)
+    iters_diff = 0
+    for i, k in enumerate(keys):
+        if k not in exp_fit:
+            continue
+        e = exp_fit[k]
+        # the reference orders model groups by sorted name; ours are layout slots
+        gmap = [lay.group_names.index(nm) for nm in e["group_names"]]
+        if iters_exact:
+            assert res.n_iter[i] == e["n_iterations"], (k, res.n_iter[i], e["n_iterations"])
+        iters_diff += int(res.n_iter[i] != e["n_iterations"])
+        assert bool(res.status[i] & xf.CONVERGED) == e["converged"], k
+        np.testing.assert_allclose(res.mu[i], [_num(v) for v in e["location"]], rtol=rtol_param, err_msg=str(k))
+        np.testing.assert_allclose(res.lam[i], [_num(v) for v in e["lambda"]], rtol=rtol_param, err_msg=str(k))
+        np.testing.assert_allclose(res.alpha[i], [_num(v) for v in e["alpha"]], rtol=rtol_param, err_msg=str(k))
+        np.testing.assert_allclose(res.beta[i], [_num(v) for v in e["beta"]], rtol=rtol_param, err_msg=str(k))
+        N_ref = np.array([[_num(v) for v in r] for r in e["N"]])
+        np.testing.assert_allclose(res.N[i][gmap], N_ref, rtol=rtol_param, atol=1e-9, err_msg=str(k))
+        if e["prefilter"] is not None:
+            pv = _num(list(e["prefilter"].values())[0])
+            if np.isnan(pv):
+                assert np.isnan(res.pval[i])
+            else:
+                np.testing.assert_allclose(res.pval[i], pv, rtol=rtol_p, err_msg=str(k))
+    # emitted rows (io.py:346-367)
+    pre = method["prefiltering"]
+    pm = pre["method"] if pre else None
+    assert get_result_table_header(lay, pm) == expected["header"]
+    rows = {tuple(r[:3]): r for r in result_rows(batch, res, pm)}
+    exp_rows = {tuple(r[:3]): r for r in expected["rows"]}
+    assert set(rows) == set(exp_rows)
+    hdr = expected["header"]
+    knife = 0
+    for k, r in rows.items():
+        e = exp_rows[k]
+        assert len(r) == len(e)
+        alt = _knife_edge_alternatives(hdr, e, lay)
+        for name, a, b in zip(hdr[3:], r[3:], e[3:]):
+            if b is None or isinstance(a, str):
+                assert a == b, (k, name, a, b)
+                continue
+            b = _num(b)
+            if np.isnan(b):
+                assert np.isnan(a), (k, name)
+                continue
+            tol = rtol_p if (name.startswith("pval") or name == pm) else rtol_param
+            if np.isclose(a, b, rtol=tol, atol=1e-300):
+                continue
+            # z-test columns: the reference's n = round(mean coverage) sits on x.5 and its rounding
+            # direction is sub-ulp noise (see xp_core.cuh cond_summary) - accept the other direction
+            cands = alt.get(name, [])
+            assert any(np.isclose(a, c, rtol=tol, atol=1e-300) for c in cands), (k, name, a, b, cands)
+            knife += 1
+    return iters_diff, knife
+
+
+def _knife_edge_alternatives(hdr, row, lay):
+    """For every z-test triple of a reference row: the values the reference's own formula
+    (stats.py:7-15) gives from the row's mod_rate_*/coverage_* columns when a mean coverage that
+    lies within 1e-6 of x.5 is rounded the other way."""
+    import math
+    from itertools import combinations, product
+
+    import numpy as np
+    import scipy.stats
+
+    col = {h: (None if v is None else _num(v)) for h, v in zip(hdr[3:], row[3:]) if h != "mod_assignment"}
+    names = lay.group_names
+    gc = list(lay.grp_cond)
+    present = [g for g, nm in enumerate(names) if col.get("mod_rate_%s" % nm) is not None]
+
+    def summary(groups):
+        w = np.array([col["mod_rate_%s" % names[g]] for g in groups])
+        c = np.array([col["coverage_%s" % names[g]] for g in groups])
+        m = c.mean()
+        ns = [np.round(m)]
+        if abs(m - math.floor(m) - 0.5) < 1e-6:
+            ns = [math.floor(m), math.ceil(m)]
+        return w.mean(), ns
+
+    def triples(g1, g2):
+        p1, n1s = summary(g1)
+        p2, n2s = summary(g2)
+        out = []
+        for n1, n2 in product(n1s, n2s):
+            se = np.sqrt(p1 * (1 - p1) / n1 + p2 * (1 - p2) / n2)
+            z = (p1 - p2) / se
+            out.append((p1 - p2, scipy.stats.norm.sf(abs(z)) * 2, z))
+        return out
+
+    alt = {}
+    conds = lay.condition_names
+    tests = [("%s_vs_%s" % (conds[a], conds[b]), [g for g in present if gc[g] == a], [g for g in present if gc[g] == b])
+             for a, b in combinations(range(len(conds)), 2)]
+    if len(conds) > 2:
+        tests += [("%s_vs_all" % conds[a], [g for g in present if gc[g] == a], [g for g in present if gc[g] != a])
+                  for a in range(len(conds))]
+    for tag, g1, g2 in tests:
+        if not g1 or not g2:
+            continue
+        tr = triples(g1, g2)
+        alt["diff_mod_rate_" + tag] = [t[0] for t in tr]
+        alt["pval_" + tag] = [t[1] for t in tr]
+        alt["z_score_" + tag] = [t[2] for t in tr]
+    return alt

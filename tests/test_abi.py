@@ -1,0 +1,66 @@
+"""The C-ABI library builds for sm_100a, loads, and exports every symbol include/xpore_b200.h declares.
+No compute calls here (no GPU in the build container)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from xpore_b200 import _lib
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def library():
+    _lib.build()
+    return _lib.lib()
+
+
+def declared_symbols():
+    text = open(os.path.join(REPO, "include", "xpore_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(xpb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(library):
+    syms = declared_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(library, s), s
+    assert sorted(syms) == sorted(_lib.EXPORTS)
+
+
+def test_record_widths(library):
+    from xpore_b200 import fit as xf
+    for G, Cn in [(2, 2), (4, 2), (6, 2), (6, 3), (18, 6)]:
+        assert library.xpb200_fit_width(G) == xf.fit_width(G)
+        assert library.xpb200_stats_width(G, Cn) == xf.stats_width(G, Cn)
+    assert library.xpb200_workspace_bytes(1000) >= 4000
+    assert b"sm_100a" in library.xpb200_version()
+
+
+def test_struct_layouts_match_header():
+    # field order/sizes of the ctypes mirrors (x86-64 / LP64)
+    assert C.sizeof(_lib.XpBatch) == 4 * 4 + 8 + 6 * 8
+    assert C.sizeof(_lib.XpMethod) == 2 * 4 + 3 * 8
+    assert C.sizeof(_lib.XpResult) == 5 * 8
+    assert C.sizeof(_lib.XpLaunchInfo) == 6 * 4
+
+
+def test_argument_validation_without_gpu(library):
+    b = _lib.XpBatch(0, 0, 2, 0, 0, None, None, None, None, None, None)
+    m = _lib.XpMethod(500, 0, 1e-5, float("nan"), 0.001)
+    r = _lib.XpResult(None, None, None, None, None)
+    rc = library.xpb200_fit_device(C.byref(b), C.byref(m), C.byref(r), None, 0, None, None)
+    assert rc == -1 and b"n_groups" in library.xpb200_last_error()
+
+
+def test_no_cpu_fallback_in_product():
+    """The product package must not import the oracle or the emulator."""
+    pkg = os.path.join(REPO, "xpore_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(root, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "xp_emul" not in src, f

@@ -1,0 +1,192 @@
+"""Parity of the CUDA path (through the C ABI) with the reference / the oracle.  Needs a B200."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.special
+import scipy.stats
+
+from xpore_b200 import _lib
+from xpore_b200 import fit as xf
+from xpore_b200.kmer_model import KmerModel
+from xpore_b200.synth import Spec, make_batch
+
+from helpers import compare_with_golden, pack_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    _lib.build()
+    return torch
+
+
+def dev_special(torch, which, x, aux=None):
+    L = _lib.lib()
+    xd = torch.tensor(np.ascontiguousarray(x, dtype=np.float64), device="cuda")
+    ad = torch.tensor(np.ascontiguousarray(aux if aux is not None else np.zeros_like(x), dtype=np.float64), device="cuda")
+    out = torch.empty_like(xd)
+    _lib.check(L.xpb200_eval_special(which, xd.data_ptr(), ad.data_ptr(), out.data_ptr(), xd.numel(), None))
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def test_device_special_functions(torch_cuda):
+    torch = torch_cuda
+    x = np.concatenate([np.geomspace(1e-3, 1e5, 4000), np.linspace(0.001, 30, 3000)])
+    np.testing.assert_allclose(dev_special(torch, 0, x), scipy.special.digamma(x), rtol=2e-13, atol=2e-14)
+    np.testing.assert_allclose(dev_special(torch, 1, x), scipy.special.gammaln(x), rtol=2e-13, atol=2e-14)
+    xl = np.geomspace(1e-300, 1e300, 5000)
+    np.testing.assert_allclose(dev_special(torch, 2, xl), np.log(xl), rtol=4e-16)
+    xe = np.linspace(-700, 700, 20001)
+    np.testing.assert_allclose(dev_special(torch, 3, xe), np.exp(xe), rtol=1e-15)
+    d = np.concatenate([np.linspace(-60, 60, 4001), [-1e4, -600, -500.5, 500.5, 600, 1e4, 0.0]])
+    np.testing.assert_allclose(dev_special(torch, 5, d), scipy.special.expit(np.clip(d, -500, 500)), rtol=2e-15,
+                               atol=1e-300)
+    rm = scipy.special.expit(-np.abs(d))
+    ent = scipy.special.xlogy(rm, rm) + (1 - rm) * np.log1p(-rm)
+    np.testing.assert_allclose(dev_special(torch, 6, d), ent, rtol=1e-12, atol=1e-15)
+    rng = np.random.default_rng(0)
+    t = np.concatenate([rng.normal(0, 3, 4000), rng.normal(0, 30, 500)])
+    df = rng.integers(2, 2000, 4500).astype(np.float64)
+    ref = scipy.stats.t.sf(np.abs(t), df) * 2
+    got = dev_special(torch, 4, t, df)
+    ok = ref > 1e-290
+    np.testing.assert_allclose(got[ok], ref[ok], rtol=5e-12)
+
+
+def test_golden_through_c_abi(torch_cuda, golden_case):
+    """Host buffers -> xpb200_fit_host -> records, against the unmodified reference's outputs:
+    selection and fitted set exact, parameters rel 1e-5, p-values rel 1e-4 (north_star)."""
+    exp = golden_case["expected"]
+    batch, method, _ = pack_case(golden_case["config_path"], exp["ids"])
+    res = xf.fit_batch(batch, xf.Method.from_dict(method))
+    iters_diff, knife = compare_with_golden(batch, res, method, exp, rtol_param=1e-5, rtol_p=1e-4, iters_exact=False)
+    print("%s: positions with a different sweep count: %d of %d; knife-edge z-tests: %d"
+          % (golden_case["name"], iters_diff, res.n_fitted, knife))
+    assert iters_diff == 0
+
+
+def _oracle_fit(batch, p, method):
+    from oracle import xpore_oracle as orc
+    y = batch.y[batch.read_off[p]:batch.read_off[p + 1]]
+    present = np.nonzero(batch.grp_len[p] > 0)[0]
+    X = np.zeros((len(y), len(present)), dtype=bool)
+    o = 0
+    for j, g in enumerate(present):
+        X[o:o + batch.grp_len[p, g], j] = True
+        o += batch.grp_len[p, g]
+    f = orc.fit_position(y, X, batch.kmer_mean[p], batch.kmer_std[p], method.max_iters, method.stopping_criteria,
+                         rng=np.random.RandomState(1))
+    return f, present
+
+
+@pytest.mark.parametrize("shape", ["c2", "c3_pooled", "c5_multicond", "c4_ragged"])
+def test_device_path_vs_oracle(torch_cuda, shape):
+    """Seeded synthetic batches of the BASELINE shapes, device-resident entry point, against the
+    CPU oracle on a sample of positions (the oracle needs ~40 ms per position)."""
+    specs = {
+        "c2": (Spec({"KO": 3, "WT": 3}, reads_lo=20, reads_hi=100, f_mod=0.3, seed=21,
+                    method={"prefiltering": {"method": "t-test", "threshold": 0.1}}), 600, 40),
+        "c3_pooled": (Spec({"KO": 3, "WT": 3}, reads_lo=20, reads_hi=100, f_mod=0.3, seed=22,
+                           method={"pooling": True}), 300, 30),
+        "c5_multicond": (Spec({c: 3 for c in ["A549", "HEK293T", "HEPG2", "K562", "KO", "MCF7"]}, reads_lo=20,
+                              reads_hi=60, f_mod=0.3, seed=23,
+                              method={"prefiltering": {"method": "t-test", "threshold": 0.1}}), 200, 20),
+        "c4_ragged": (Spec({"KO": 2, "WT": 2}, f_mod=0.3, seed=24, loguniform_total=(20, 5000),
+                           criteria={"readcount_min": 5, "readcount_max": 5000}), 300, 24),
+    }
+    spec, P, n_check = specs[shape]
+    torch = torch_cuda
+    batch = make_batch(spec, KmerModel.load(), n_positions=P)
+    method = xf.Method.from_dict(spec.method)
+    db = xf.DeviceBatch(batch)
+    out = xf.fit_device(db, method)
+    torch.cuda.synchronize()
+    res = out.to_host()
+    # the host-buffer entry point must give the same bits
+    res2 = xf.fit_batch(batch, method)
+    assert (res.status == res2.status).all() and (res.n_iter == res2.n_iter).all()
+    sel = res.selected
+    np.testing.assert_array_equal(res.fit[sel], res2.fit[sel])
+    np.testing.assert_array_equal(res.stats[sel], res2.stats[sel])
+    # prefilter: exact selection against scipy on every position
+    from oracle import xpore_oracle as orc
+    if method.prefilter_method:
+        gc = batch.layout.grp_cond
+        for p in range(batch.n_positions):
+            y = batch.y[batch.read_off[p]:batch.read_off[p + 1]]
+            cond = np.repeat(gc, batch.grp_len[p])
+            x, _ = orc.one_hot(cond)
+            pv = orc.prefilter_pvalue(y, x)
+            if np.isnan(pv):
+                assert np.isnan(res.pval[p]) and sel[p]
+            else:
+                np.testing.assert_allclose(res.pval[p], pv, rtol=1e-9)
+                assert sel[p] == bool(pv < method.prefilter_threshold)
+    else:
+        assert sel.all() and np.isnan(res.pval).all()
+    assert res.n_fitted == int(sel.sum())
+    # fitted parameters and statistics against the oracle on a sample
+    rng = np.random.default_rng(5)
+    idx = np.nonzero(sel)[0]
+    idx = rng.choice(idx, size=min(n_check, len(idx)), replace=False)
+    same_iters = 0
+    for p in idx:
+        f, present = _oracle_fit(batch, p, method)
+        same_iters += int(f["n_iterations"] == res.n_iter[p])
+        np.testing.assert_allclose(res.mu[p], f["location"], rtol=1e-5)
+        np.testing.assert_allclose(res.alpha[p], f["alpha"], rtol=1e-5)
+        np.testing.assert_allclose(res.beta[p], f["beta"], rtol=1e-5)
+        np.testing.assert_allclose(res.N[p][present], f["N"], rtol=1e-5, atol=1e-9)
+        assert bool(res.status[p] & xf.CONVERGED) == f["converged"]
+    print("%s: %d/%d sampled positions with the oracle's sweep count" % (shape, same_iters, len(idx)))
+    assert same_iters == len(idx)
+
+
+def test_empty_and_tiny_batches(torch_cuda):
+    spec = Spec({"KO": 2, "WT": 2}, reads_lo=15, reads_hi=16, seed=3)
+    b0 = make_batch(spec, KmerModel.load(), n_positions=0) if False else None
+    b1 = make_batch(spec, KmerModel.load(), n_positions=1)
+    r1 = xf.fit_batch(b1, xf.Method())
+    assert r1.n_fitted == 1 and r1.n_iter[0] >= 2 and np.isfinite(r1.fit[0]).all()
+    # max_iters edge: at most max_iters-1 sweeps (gmm.py:103)
+    r2 = xf.fit_batch(b1, xf.Method(max_iters=3))
+    assert r2.n_iter[0] == 2
+    # empty batch
+    from xpore_b200.batch import Batch
+    e = Batch(b1.layout, np.zeros(0), np.zeros(1, np.int64), np.zeros((0, 4), np.int32), np.zeros(0), np.zeros(0))
+    r0 = xf.fit_batch(e, xf.Method())
+    assert r0.n_fitted == 0 and r0.fit.shape[0] == 0
+
+
+def test_full_size_properties(torch_cuda):
+    """Size-independent properties on a large batch (100k positions, c2 shape): permutation
+    invariance of the result records and determinism across runs."""
+    torch = torch_cuda
+    spec = Spec({"KO": 3, "WT": 3}, reads_lo=20, reads_hi=100, f_mod=0.1, seed=31,
+                method={"prefiltering": {"method": "t-test", "threshold": 0.1}})
+    batch = make_batch(spec, KmerModel.load(), n_positions=100000)
+    method = xf.Method.from_dict(spec.method)
+    res = xf.fit_device(xf.DeviceBatch(batch), method)
+    torch.cuda.synchronize()
+    a = res.to_host()
+    perm = np.random.default_rng(0).permutation(batch.n_positions)
+    shuffled = batch.subset(perm)
+    b = xf.fit_batch(shuffled, method)
+    assert a.n_fitted == b.n_fitted and 0.1 * batch.n_positions < a.n_fitted < 0.5 * batch.n_positions
+    np.testing.assert_array_equal(a.status[perm], b.status)
+    np.testing.assert_array_equal(a.n_iter[perm], b.n_iter)
+    np.testing.assert_array_equal(a.pval[perm], b.pval)
+    sel = b.selected
+    np.testing.assert_array_equal(a.fit[perm][sel], b.fit[sel])
+    np.testing.assert_array_equal(a.stats[perm][sel], b.stats[sel])
+    # sanity of the fitted values
+    assert np.isfinite(b.fit[sel]).all()
+    N = b.N[sel]
+    n_reads = np.diff(shuffled.read_off)[sel]
+    np.testing.assert_allclose(N.sum(axis=(1, 2)), n_reads, rtol=1e-12)
+    assert (b.n_iter[sel] >= 2).all() and (b.n_iter[sel] <= 499).all()

@@ -1,0 +1,380 @@
+// xp_api.cu — C ABI (include/xpore_b200.h) over the kernels in xp_kernels.cuh.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/xpore_b200.h"
+#include "xp_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+thread_local uint64_t g_launches = 0;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(XPB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+constexpr int kFitWarps = 4;
+constexpr size_t kMaxSmemPerCta = 227 * 1024;
+
+struct Workspace {  // carved out of the caller's buffer
+    uint32_t* hist;
+    uint32_t* cursor;
+    uint32_t* n_work;
+    unsigned int* ticket;
+    int32_t* worklist;
+};
+size_t ws_header_bytes() { return (size_t)(2 * xpk::kBuckets + 64) * 4; }
+Workspace carve(void* ws) {
+    Workspace w;
+    uint32_t* u = reinterpret_cast<uint32_t*>(ws);
+    w.hist = u;
+    w.cursor = u + xpk::kBuckets;
+    w.n_work = u + 2 * xpk::kBuckets;
+    w.ticket = u + 2 * xpk::kBuckets + 1;
+    w.worklist = reinterpret_cast<int32_t*>(u + 2 * xpk::kBuckets + 64);
+    return w;
+}
+
+int check_batch(const xpb200_batch* b, const xpb200_method* m) {
+    if (!b || !m) return fail(XPB200_EINVAL, "null batch/method");
+    if (b->n_positions < 0) return fail(XPB200_EINVAL, "n_positions < 0");
+    if (b->n_groups < 1 || b->n_groups > xpk::kMaxGroups) return fail(XPB200_EINVAL, "n_groups must be 1..64");
+    if (b->n_conditions < 1 || b->n_conditions > xpk::kMaxConditions)
+        return fail(XPB200_EINVAL, "n_conditions must be 1..32");
+    if (!(m->dirichlet_conc > 0.0)) return fail(XPB200_EINVAL, "dirichlet_conc must be > 0");
+    return 0;
+}
+
+struct Geometry {
+    int warps, cap, ctas_per_sm, sms;
+    size_t smem;
+};
+
+template <int W>
+int occupancy_for(size_t smem, int* ctas) {
+    CK(cudaFuncSetAttribute(xpk::xp_fit_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, xpk::xp_fit_kernel<W>, W * 32, smem));
+    return 0;
+}
+
+// Slab sized to the batch's longest position; warps per CTA shrink when one slab set no longer
+// fits 227 KB.
+int fit_geometry(int G, int max_reads, Geometry* g) {
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int cap = std::max(32, (max_reads + 1 + 7) & ~7);
+    const size_t per_warp = xpk::fit_warp_smem_bytes(cap, G);
+    int warps = kFitWarps;
+    while (warps > 1 && per_warp * warps > kMaxSmemPerCta) warps >>= 1;
+    if (per_warp * warps > kMaxSmemPerCta)
+        return fail(XPB200_EINVAL, "a position has more reads than one CTA's shared memory holds (max_reads=" +
+                                       std::to_string(max_reads) + ")");
+    g->warps = warps;
+    g->cap = cap;
+    g->smem = per_warp * warps;
+    g->sms = sms;
+    int ctas = 0, rc = 0;
+    if (warps == 4) rc = occupancy_for<4>(g->smem, &ctas);
+    else if (warps == 2) rc = occupancy_for<2>(g->smem, &ctas);
+    else rc = occupancy_for<1>(g->smem, &ctas);
+    if (rc) return rc;
+    if (ctas < 1) return fail(XPB200_ECUDA, "fit kernel does not fit on an SM");
+    g->ctas_per_sm = ctas;
+    return 0;
+}
+
+int launch_prefilter(const xpb200_batch* b, const xpb200_method* m, uint32_t* status, double* pval,
+                     cudaStream_t st) {
+    if (b->n_positions == 0) return 0;
+    xpk::PrefilterArgs a;
+    a.y = b->y; a.read_off = b->read_off; a.grp_len = b->grp_len; a.kmer_mean = b->kmer_mean;
+    a.grp_cond = b->grp_cond; a.P = b->n_positions; a.G = b->n_groups;
+    a.enabled = (m->prefilter == 1);
+    a.threshold = m->prefilter_threshold;
+    a.status = status; a.pval = pval;
+    constexpr int W = 4;
+    const int tiles = (b->n_positions + 31) / 32;
+    xpk::xp_prefilter_kernel<W><<<(tiles + W - 1) / W, W * 32, 0, st>>>(a);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int launch_stats(const xpb200_batch* b, const xpb200_method* m, const xpb200_result* r, const int32_t* worklist,
+                 const uint32_t* n_work, cudaStream_t st) {
+    if (b->n_positions == 0) return 0;
+    xpk::StatsArgs a;
+    a.worklist = worklist; a.n_work = n_work; a.P = b->n_positions; a.G = b->n_groups; a.C = b->n_conditions;
+    a.grp_cond = b->grp_cond; a.grp_len = b->grp_len; a.kmer_mean = b->kmer_mean; a.kmer_std = b->kmer_std;
+    a.conc0 = m->dirichlet_conc; a.fit = r->fit; a.stats = r->stats; a.status = r->status;
+    const int threads = 128;
+    xpk::xp_stats_kernel<<<(b->n_positions + threads - 1) / threads, threads, 0, st>>>(a);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* xpb200_last_error(void) { return g_err.c_str(); }
+const char* xpb200_version(void) { return "xpore_b200 0.1 (sm_100a)"; }
+uint64_t xpb200_launch_count(void) { return g_launches; }
+int32_t xpb200_fit_width(int32_t G) { return xpc::fit_width(G); }
+int32_t xpb200_stats_width(int32_t G, int32_t C) { return xpc::stats_width(G, C); }
+size_t xpb200_workspace_bytes(int32_t P) { return ws_header_bytes() + (size_t)std::max(P, 1) * 4; }
+
+int32_t xpb200_fit_launch_info(int32_t device, int32_t G, int32_t max_reads, xpb200_launch_info* out) {
+    if (!out) return fail(XPB200_EINVAL, "null out");
+    CK(cudaSetDevice(device));
+    Geometry g;
+    if (int rc = fit_geometry(G, max_reads, &g)) return rc;
+    cudaFuncAttributes fa;
+    if (g.warps == 4) CK(cudaFuncGetAttributes(&fa, xpk::xp_fit_kernel<4>));
+    else if (g.warps == 2) CK(cudaFuncGetAttributes(&fa, xpk::xp_fit_kernel<2>));
+    else CK(cudaFuncGetAttributes(&fa, xpk::xp_fit_kernel<1>));
+    out->sm_count = g.sms; out->ctas_per_sm = g.ctas_per_sm; out->warps_per_cta = g.warps;
+    out->smem_per_cta = (int32_t)g.smem; out->slab_reads = g.cap; out->regs_per_thread = fa.numRegs;
+    return 0;
+}
+
+int32_t xpb200_prefilter_device(const xpb200_batch* b, const xpb200_method* m, uint32_t* status, double* pval,
+                                void* stream) {
+    if (int rc = check_batch(b, m)) return rc;
+    return launch_prefilter(b, m, status, pval, (cudaStream_t)stream);
+}
+
+int32_t xpb200_stats_device(const xpb200_batch* b, const xpb200_method* m, const xpb200_result* r,
+                            const int32_t* worklist, const uint32_t* n_work, void* stream) {
+    if (int rc = check_batch(b, m)) return rc;
+    return launch_stats(b, m, r, worklist, n_work, (cudaStream_t)stream);
+}
+
+int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const xpb200_result* r, void* workspace,
+                          size_t workspace_bytes, uint32_t* n_fitted_dev, void* stream) {
+    if (int rc = check_batch(b, m)) return rc;
+    if (!r || !r->status || !r->n_iter || !r->pval || !r->fit || !r->stats)
+        return fail(XPB200_EINVAL, "null result array");
+    const int P = b->n_positions;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P == 0) {
+        if (n_fitted_dev) CK(cudaMemsetAsync(n_fitted_dev, 0, 4, st));
+        return 0;
+    }
+    if (!workspace || workspace_bytes < xpb200_workspace_bytes(P)) return fail(XPB200_ENOMEM, "workspace too small");
+    Workspace ws = carve(workspace);
+    CK(cudaMemsetAsync(workspace, 0, ws_header_bytes(), st));
+
+    // K1 prefilter (or: everything selected, p-value NaN)
+    const uint32_t* sel = nullptr;
+    if (m->prefilter) {
+        if (int rc = launch_prefilter(b, m, r->status, r->pval, st)) return rc;
+        sel = r->status;
+    } else {
+        CK(cudaMemsetAsync(r->status, 0, (size_t)P * 4, st));
+        CK(cudaMemsetAsync(r->pval, 0xFF, (size_t)P * 8, st));  // all-ones = NaN
+    }
+    // worklist, longest positions first
+    xpk::WorklistArgs wa;
+    wa.status = sel; wa.read_off = b->read_off; wa.P = P; wa.hist = ws.hist; wa.cursor = ws.cursor;
+    wa.n_work = ws.n_work; wa.worklist = ws.worklist;
+    const int wthreads = 256;
+    const int wblocks = std::min((P + wthreads - 1) / wthreads, 1184);
+    xpk::xp_worklist_count<<<wblocks, wthreads, 0, st>>>(wa);
+    xpk::xp_worklist_scan<<<1, xpk::kBuckets, 0, st>>>(wa);
+    xpk::xp_worklist_scatter<<<wblocks, wthreads, 0, st>>>(wa);
+    g_launches += 3;
+    CK(cudaGetLastError());
+
+    // K3 fit: persistent CTAs, one warp per position
+    Geometry g;
+    if (int rc = fit_geometry(b->n_groups, b->max_reads, &g)) return rc;
+    xpk::FitArgs fa;
+    fa.y = b->y; fa.read_off = b->read_off; fa.grp_len = b->grp_len; fa.kmer_mean = b->kmer_mean;
+    fa.kmer_std = b->kmer_std; fa.worklist = ws.worklist; fa.n_work = ws.n_work; fa.ticket = ws.ticket;
+    fa.G = b->n_groups; fa.max_iters = m->max_iters; fa.cap = g.cap; fa.stopping = m->stopping_criteria;
+    fa.conc0 = m->dirichlet_conc;
+    fa.lg_prior_w = xpm::xlgamma(2.0 * m->dirichlet_conc) - 2.0 * xpm::xlgamma(m->dirichlet_conc);
+    fa.fit = r->fit; fa.n_iter = r->n_iter; fa.status = r->status;
+    const int max_ctas = g.sms * g.ctas_per_sm;
+    const int need = (P + g.warps - 1) / g.warps;
+    const int grid = std::max(1, std::min(max_ctas, need));
+    if (g.warps == 4) xpk::xp_fit_kernel<4><<<grid, 128, g.smem, st>>>(fa);
+    else if (g.warps == 2) xpk::xp_fit_kernel<2><<<grid, 64, g.smem, st>>>(fa);
+    else xpk::xp_fit_kernel<1><<<grid, 32, g.smem, st>>>(fa);
+    ++g_launches;
+    CK(cudaGetLastError());
+
+    // K4 statistics
+    if (int rc = launch_stats(b, m, r, ws.worklist, ws.n_work, st)) return rc;
+    if (n_fitted_dev) CK(cudaMemcpyAsync(n_fitted_dev, ws.n_work, 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// ---- host-buffer entry point --------------------------------------------------------------
+namespace {
+struct DevCache {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    void* buf = nullptr;
+    size_t cap = 0;
+};
+std::mutex g_cache_mu;
+std::vector<DevCache> g_cache;
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+}  // namespace
+
+int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_method* m, const xpb200_result* r,
+                        uint32_t* n_fitted) {
+    if (int rc = check_batch(b, m)) return rc;
+    if (!r || !r->status || !r->n_iter || !r->pval || !r->fit || !r->stats)
+        return fail(XPB200_EINVAL, "null result array");
+    CK(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    DevCache* dc = nullptr;
+    for (auto& c : g_cache)
+        if (c.device == device) dc = &c;
+    if (!dc) {
+        g_cache.push_back(DevCache());
+        dc = &g_cache.back();
+        dc->device = device;
+        CK(cudaStreamCreateWithFlags(&dc->stream, cudaStreamNonBlocking));
+    }
+    const int P = b->n_positions, G = b->n_groups, C = b->n_conditions;
+    const size_t R2 = (size_t)((b->n_reads + 1) & ~(int64_t)1);
+    const int FW = xpc::fit_width(G), SW = xpc::stats_width(G, C);
+    // device layout
+    size_t o = 0;
+    const size_t o_y = o; o += align_up(R2 * 8);
+    const size_t o_off = o; o += align_up((size_t)(P + 1) * 8);
+    const size_t o_glen = o; o += align_up((size_t)P * G * 4);
+    const size_t o_km = o; o += align_up((size_t)P * 8);
+    const size_t o_ks = o; o += align_up((size_t)P * 8);
+    const size_t o_gc = o; o += align_up((size_t)G * 4);
+    const size_t o_status = o; o += align_up((size_t)P * 4);
+    const size_t o_niter = o; o += align_up((size_t)P * 4);
+    const size_t o_pval = o; o += align_up((size_t)P * 8);
+    const size_t o_fit = o; o += align_up((size_t)P * FW * 8);
+    const size_t o_stats = o; o += align_up((size_t)P * SW * 8);
+    const size_t o_nf = o; o += 256;
+    const size_t o_ws = o; o += align_up(xpb200_workspace_bytes(P));
+    if (o > dc->cap) {
+        if (dc->buf) CK(cudaFree(dc->buf));
+        dc->buf = nullptr;
+        dc->cap = 0;
+        const size_t want = o + o / 8;
+        if (cudaMalloc(&dc->buf, want) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(XPB200_ENOMEM, "cudaMalloc of " + std::to_string(want) + " bytes failed");
+        }
+        dc->cap = want;
+    }
+    char* d = reinterpret_cast<char*>(dc->buf);
+    cudaStream_t st = dc->stream;
+    if (P > 0) {
+        CK(cudaMemcpyAsync(d + o_y, b->y, (size_t)b->n_reads * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d + o_off, b->read_off, (size_t)(P + 1) * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d + o_glen, b->grp_len, (size_t)P * G * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d + o_km, b->kmer_mean, (size_t)P * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d + o_ks, b->kmer_std, (size_t)P * 8, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(d + o_gc, b->grp_cond, (size_t)G * 4, cudaMemcpyHostToDevice, st));
+    xpb200_batch db = *b;
+    db.y = (const double*)(d + o_y); db.read_off = (const int64_t*)(d + o_off);
+    db.grp_len = (const int32_t*)(d + o_glen); db.kmer_mean = (const double*)(d + o_km);
+    db.kmer_std = (const double*)(d + o_ks); db.grp_cond = (const int32_t*)(d + o_gc);
+    xpb200_result dr;
+    dr.status = (uint32_t*)(d + o_status); dr.n_iter = (int32_t*)(d + o_niter); dr.pval = (double*)(d + o_pval);
+    dr.fit = (double*)(d + o_fit); dr.stats = (double*)(d + o_stats);
+    if (P > 0) {
+        CK(cudaMemsetAsync(dr.n_iter, 0, (size_t)P * 4, st));
+        CK(cudaMemsetAsync(dr.fit, 0xFF, (size_t)P * FW * 8, st));
+        CK(cudaMemsetAsync(dr.stats, 0xFF, (size_t)P * SW * 8, st));
+    }
+    if (int rc = xpb200_fit_device(&db, m, &dr, d + o_ws, xpb200_workspace_bytes(P), (uint32_t*)(d + o_nf), st))
+        return rc;
+    if (P > 0) {
+        CK(cudaMemcpyAsync(r->status, dr.status, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(r->n_iter, dr.n_iter, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(r->pval, dr.pval, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(r->fit, dr.fit, (size_t)P * FW * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(r->stats, dr.stats, (size_t)P * SW * 8, cudaMemcpyDeviceToHost, st));
+    }
+    uint32_t nf = 0;
+    CK(cudaMemcpyAsync(&nf, d + o_nf, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_fitted) *n_fitted = nf;
+    return 0;
+}
+
+void xpb200_release(void) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (auto& c : g_cache) {
+        cudaSetDevice(c.device);
+        if (c.buf) cudaFree(c.buf);
+        if (c.stream) cudaStreamDestroy(c.stream);
+    }
+    g_cache.clear();
+}
+
+int32_t xpb200_measure_fp64_peak(int32_t device, int32_t repeats, double* tflops) {
+    if (!tflops || repeats < 1) return fail(XPB200_EINVAL, "bad arguments");
+    CK(cudaSetDevice(device));
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    double* out = nullptr;
+    CK(cudaMalloc(&out, 8));
+    const int iters = 1 << 16, threads = 256, blocks = sms * 8;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    xpk::xp_dfma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0);  // warm-up
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int i = 0; i < repeats; ++i) {
+        CK(cudaEventRecord(e0));
+        xpk::xp_dfma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    g_launches += repeats + 1;
+    CK(cudaGetLastError());
+    const double flops = 2.0 * 8.0 * (double)iters * threads * (double)blocks;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return 0;
+}
+
+int32_t xpb200_eval_special(int32_t which, const double* x, const double* aux, double* out, int64_t n, void* stream) {
+    if (n <= 0) return 0;
+    const int threads = 128;
+    xpk::xp_eval_special_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+        which, x, aux, out, (long long)n);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,635 @@
+// xp_kernels.cuh — sm_100a kernels of the diffmod hot path.
+//
+//   K1  xp_prefilter_kernel   two-sample t-test per position (statstest.py:4-18)  — HBM streaming
+//   W*  xp_worklist_*         selected positions, longest first (replaces the gene queue,
+//                             scripts/diffmod.py:152-175, helper.py:96-116)
+//   K3  xp_fit_kernel         VB-EM of the 2-component mixture (gmm.py:11-127), one warp per
+//                             position, reads resident in shared memory for all sweeps,
+//                             persistent CTAs pulling tickets from a global worklist
+//   K4  xp_stats_kernel       cluster assignment, z-tests, overlap, row filter (io.py:255-367)
+//
+// FP64 throughout (the reference is float64 and its stopping rule rounds an ELBO difference at
+// 1e-8 absolute, gmm.py:110).  No tensor cores: nothing here is a dense contraction.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "xp_core.cuh"
+
+namespace xpk {
+
+using namespace xpc;
+
+constexpr int kMaxGroups = 64;
+constexpr int kMaxConditions = 32;
+constexpr int kBuckets = 512;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(kFull, v, m);
+    return v;
+}
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        const uint64_t o = __shfl_xor_sync(kFull, v, m);
+        v = o < v ? o : v;
+    }
+    return v;
+}
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        const uint64_t o = __shfl_xor_sync(kFull, v, m);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+
+// order-preserving map double -> uint64
+__device__ __forceinline__ uint64_t dkey(double x) {
+    const uint64_t u = d2u(x);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double keyd(uint64_t k) {
+    return u2d((k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k);
+}
+
+// ---- mbarrier + 1-D TMA bulk copy (global -> shared) ----------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "XP_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra XP_DONE_%=;\n"
+        "bra XP_WAIT_%=;\n"
+        "XP_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: prefilter t-test.  One warp per tile of 32 consecutive positions: the warp streams each
+// position's reads (coalesced 8-byte loads), reduces the centred moments of the two present
+// conditions, lane j keeps position j's moments; then all 32 lanes evaluate their Student-t
+// p-value in parallel.
+// ------------------------------------------------------------------------------------------
+struct PrefilterArgs {
+    const double* y;
+    const int64_t* read_off;
+    const int32_t* grp_len;
+    const double* kmer_mean;
+    const int32_t* grp_cond;
+    int P, G;
+    int enabled;       // 1 = t-test, 0 = prefilter configured with an unknown method (NaN => fit all)
+    double threshold;
+    uint32_t* status;  // [P] written: SELECTED | TTEST_VALID
+    double* pval;      // [P]
+};
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) xp_prefilter_kernel(PrefilterArgs a) {
+    __shared__ int s_off[WARPS][kMaxGroups + 1];
+    __shared__ signed char s_side[WARPS][kMaxGroups];  // 0 -> first condition, 1 -> second
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * WARPS + warp;
+    const int p0 = tile * 32;
+    if (p0 >= a.P) return;
+    const int G = a.G;
+    int* goff = s_off[warp];
+    signed char* side = s_side[warp];
+
+    double k_na = 0, k_s1a = 0, k_s2a = 0, k_nb = 0, k_s1b = 0, k_s2b = 0;
+    bool k_valid = false;
+    const int pend = min(32, a.P - p0);
+    for (int j = 0; j < pend; ++j) {
+        const int p = p0 + j;
+        const int64_t off = a.read_off[p];
+        const int n = (int)(a.read_off[p + 1] - off);
+        const double m0 = a.kmer_mean[p];
+        // conditions present at this position
+        unsigned cmask = 0;
+        for (int g = lane; g < G; g += 32) {
+            const int len = a.grp_len[(size_t)p * G + g];
+            goff[g + 1] = len;
+            if (len > 0) cmask |= 1u << a.grp_cond[g];
+        }
+        cmask = __reduce_or_sync(kFull, cmask);
+        const bool valid = a.enabled && (__popc(cmask) == 2);
+        __syncwarp();
+        if (valid) {
+            const int ca = __ffs(cmask) - 1;
+            if (lane == 0) {
+                int acc = 0;
+                goff[0] = 0;
+                for (int g = 0; g < G; ++g) {
+                    acc += goff[g + 1];
+                    goff[g + 1] = acc;
+                }
+            }
+            for (int g = lane; g < G; g += 32) side[g] = (a.grp_cond[g] == ca) ? 0 : 1;
+            __syncwarp();
+            double s1a = 0, s2a = 0, s1b = 0, s2b = 0;
+            int na = 0, nb = 0;
+            int g = 0, gend = goff[1];
+            const double* yp = a.y + off;
+            for (int i = lane; i < n; i += 32) {
+                while (i >= gend) {
+                    ++g;
+                    gend = goff[g + 1];
+                }
+                const double v = __ldg(yp + i) - m0;
+                if (side[g] == 0) {
+                    s1a += v;
+                    s2a = fma(v, v, s2a);
+                    ++na;
+                } else {
+                    s1b += v;
+                    s2b = fma(v, v, s2b);
+                    ++nb;
+                }
+            }
+            s1a = warp_sum(s1a);
+            s2a = warp_sum(s2a);
+            s1b = warp_sum(s1b);
+            s2b = warp_sum(s2b);
+            na = __reduce_add_sync(kFull, na);
+            nb = __reduce_add_sync(kFull, nb);
+            if (lane == j) {
+                k_na = na; k_s1a = s1a; k_s2a = s2a;
+                k_nb = nb; k_s1b = s1b; k_s2b = s2b;
+                k_valid = true;
+            }
+        }
+        __syncwarp();
+    }
+    if (lane < pend) {
+        const int p = p0 + lane;
+        double pv = NAN;
+        uint32_t st = 0;
+        if (k_valid) {
+            double t, df;
+            ttest_from_moments(k_na, k_s1a, k_s2a, k_nb, k_s1b, k_s2b, t, df);
+            pv = student_t_two_sided(t, df);
+            st |= STATUS_TTEST_VALID;
+        }
+        if (pv != pv || pv < a.threshold) st |= STATUS_SELECTED;  // diffmod.py:54
+        a.pval[p] = pv;
+        a.status[p] = st;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Worklist: selected positions ordered by descending read count (semi-log buckets), so the
+// persistent fit kernel starts the longest positions first.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cost_bucket(int n) {  // larger n -> smaller bucket id
+    int cls;
+    if (n < 16) cls = n < 0 ? 0 : n;
+    else {
+        const int e = 31 - __clz(n);
+        cls = 16 + (e - 4) * 16 + ((n >> (e - 4)) & 15);
+    }
+    cls = min(cls, kBuckets - 1);
+    return kBuckets - 1 - cls;
+}
+
+struct WorklistArgs {
+    const uint32_t* status;  // may be null => every position selected
+    const int64_t* read_off;
+    int P;
+    uint32_t* hist;      // [kBuckets] zeroed
+    uint32_t* cursor;    // [kBuckets]
+    uint32_t* n_work;    // [1]
+    int32_t* worklist;   // [P]
+};
+
+__global__ void xp_worklist_count(WorklistArgs a) {
+    __shared__ uint32_t h[kBuckets];
+    for (int i = threadIdx.x; i < kBuckets; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < a.P; p += gridDim.x * blockDim.x) {
+        if (a.status && !(a.status[p] & STATUS_SELECTED)) continue;
+        atomicAdd(&h[cost_bucket((int)(a.read_off[p + 1] - a.read_off[p]))], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kBuckets; i += blockDim.x)
+        if (h[i]) atomicAdd(&a.hist[i], h[i]);
+}
+
+__global__ void xp_worklist_scan(WorklistArgs a) {  // <<<1, kBuckets>>>
+    __shared__ uint32_t s[kBuckets];
+    const int t = threadIdx.x;
+    s[t] = a.hist[t];
+    __syncthreads();
+    for (int d = 1; d < kBuckets; d <<= 1) {
+        const uint32_t v = (t >= d) ? s[t - d] : 0;
+        __syncthreads();
+        s[t] += v;
+        __syncthreads();
+    }
+    a.cursor[t] = s[t] - a.hist[t];  // exclusive start
+    if (t == kBuckets - 1) *a.n_work = s[t];
+}
+
+__global__ void xp_worklist_scatter(WorklistArgs a) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < a.P; p += gridDim.x * blockDim.x) {
+        if (a.status && !(a.status[p] & STATUS_SELECTED)) continue;
+        const int b = cost_bucket((int)(a.read_off[p + 1] - a.read_off[p]));
+        const uint32_t slot = atomicAdd(&a.cursor[b], 1u);
+        a.worklist[slot] = p;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: variational EM.  One warp owns one position at a time.
+//
+// Per-warp shared memory (doubles unless noted):
+//   slab[cap+2]       centred reads y' (TMA bulk copy lands here; +2 for 16-byte alignment slack)
+//   scratch[2G][33]   per-lane partial N_gk of the current sweep (33: bank-conflict-free columns)
+//   Nsm[2G]           N_gk
+//   lw[2G]            E[ln w_gk] = psi(c_gk) - psi(c_g0 + c_g1)        (gmm.py:283-284)
+//   Asm[G]            per-group constant of d_n
+//   psis[G]           psi(2 c0 + n_g): sum_k c_gk = 2 c0 + n_g is constant over sweeps
+//   sc[4]             E[tau_k], E[ln tau_k] published by the lanes that own component k
+//   goff[G+1] (int)   group offsets inside the position
+//   mbar (u64)        TMA completion barrier
+// ------------------------------------------------------------------------------------------
+struct FitArgs {
+    const double* y;
+    const int64_t* read_off;
+    const int32_t* grp_len;
+    const double* kmer_mean;
+    const double* kmer_std;
+    const int32_t* worklist;   // null => identity
+    const uint32_t* n_work;    // device count of worklist entries
+    unsigned int* ticket;      // zeroed before launch
+    int G, max_iters, cap;
+    double stopping, conc0, lg_prior_w;  // lg_prior_w = lgamma(2 c0) - 2 lgamma(c0)
+    double* fit;
+    int32_t* n_iter;
+    uint32_t* status;
+};
+
+__host__ __device__ inline size_t fit_warp_smem_bytes(int cap, int G) {
+    size_t doubles = (size_t)(cap + 2) + 66 * (size_t)G + 2 * G + 2 * G + G + G + 4;
+    size_t bytes = doubles * 8 + (size_t)((G + 2) & ~1) * 4 + 8;
+    return (bytes + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ int warp_count_le(const double* yv, int n, uint64_t K, int lane) {
+    int c = 0;
+    for (int i = lane; i < n; i += 32) c += (dkey(yv[i]) <= K) ? 1 : 0;
+    return __reduce_add_sync(kFull, c);
+}
+
+// order statistics sorted[r] and sorted[min(r+1, n-1)] by bisection on the key space
+__device__ void warp_select2(const double* yv, int n, int r, uint64_t kmin, uint64_t kmax, int lane, double& a,
+                             double& b) {
+    uint64_t lo = kmin, hi = kmax;
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if (warp_count_le(yv, n, mid, lane) >= r + 1) hi = mid;
+        else lo = mid + 1;
+    }
+    a = keyd(lo);
+    b = a;
+    if (r + 1 < n && warp_count_le(yv, n, lo, lane) < r + 2) {
+        uint64_t mn = ~0ull;
+        for (int i = lane; i < n; i += 32) {
+            const uint64_t k = dkey(yv[i]);
+            if (k > lo && k < mn) mn = k;
+        }
+        b = keyd(warp_min_u64(mn));
+    }
+}
+
+__device__ double warp_percentile(const double* yv, int n, double q, uint64_t kmin, uint64_t kmax, int lane) {
+    int lo, hi;
+    double gamma;
+    percentile_index(n, q, lo, hi, gamma);
+    double a, b;
+    warp_select2(yv, n, lo, kmin, kmax, lane, a, b);
+    return np_lerp(a, b, gamma);
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = a.G;
+    unsigned char* wbase = smem_raw + (size_t)warp * fit_warp_smem_bytes(a.cap, G);
+    double* slab = reinterpret_cast<double*>(wbase);
+    double* scratch = slab + a.cap + 2;
+    double* Nsm = scratch + 66 * G;
+    double* lw = Nsm + 2 * G;
+    double* Asm = lw + 2 * G;
+    double* psis = Asm + G;
+    double* sc = psis + G;
+    int* goff = reinterpret_cast<int*>(sc + 4);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(goff + ((G + 2) & ~1));
+
+    if (lane == 0) {
+        mbar_init(mbar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    uint32_t parity = 0;
+    const unsigned n_work = *a.n_work;
+    const double conc0 = a.conc0;
+
+    for (;;) {
+        unsigned w = 0;
+        if (lane == 0) w = atomicAdd(a.ticket, 1u);
+        w = __shfl_sync(kFull, w, 0);
+        if (w >= n_work) break;
+        const int p = a.worklist ? a.worklist[w] : (int)w;
+        const int64_t off = a.read_off[p];
+        const int n = (int)(a.read_off[p + 1] - off);
+        if (n > a.cap || n <= 0) {  // cannot happen when the host sized the slab from max_reads
+            if (lane == 0) {
+                a.status[p] |= STATUS_SELECTED;
+                a.n_iter[p] = -1;
+            }
+            continue;
+        }
+        // ---- stage the reads: one TMA bulk copy of the 16-byte aligned superset -------------
+        const int sh = (int)(off & 1);
+        const uint32_t bytes = (uint32_t)((n + sh + 1) & ~1) * 8u;
+        fence_proxy_async();  // order this warp's generic-proxy slab accesses before the async-proxy write
+        __syncwarp();
+        if (lane == 0) {
+            mbar_expect_tx(mbar, bytes);
+            tma_bulk_g2s(slab, a.y + (off - sh), bytes, mbar);
+        }
+        const double m0 = a.kmer_mean[p];
+        const double sd = a.kmer_std[p];
+        const double tau = 1.0 / (sd * sd);          // diffmod.py:24
+        const double a0 = tau;                       // diffmod.py:40
+        const double b0 = 0.5 * (1.0 / tau);         // diffmod.py:41
+        for (int g = lane; g < G; g += 32) goff[g + 1] = a.grp_len[(size_t)p * G + g];
+        __syncwarp();
+        if (lane == 0) {
+            int acc = 0;
+            goff[0] = 0;
+            for (int g = 0; g < G; ++g) {
+                acc += goff[g + 1];
+                goff[g + 1] = acc;
+            }
+        }
+        __syncwarp();
+        // per-position constants: psi/lgamma of sum_k c_gk, lgamma(a0)   (lane-parallel)
+        double kpart = 0.0, lga0 = 0.0;
+        for (int s = lane; s <= G; s += 32) {
+            double ps, lg;
+            if (s < G) {
+                const int ng = goff[s + 1] - goff[s];
+                psi_lgamma(2.0 * conc0 + (double)ng, &ps, &lg);
+                psis[s] = ps;
+                if (ng > 0) kpart += a.lg_prior_w - lg;  // lnC(prior_g) - lgamma(sum_k c_gk)
+            } else {
+                psi_lgamma(a0, &ps, &lg);
+                lga0 = lg;
+            }
+        }
+        const double Kconst = warp_sum(kpart);
+        lga0 = __shfl_sync(kFull, lga0, G & 31);
+        const double prior_gamma = a0 * xlog(b0) - lga0;  // a0 ln b0 - lgamma(a0)   (gmm.py:334)
+
+        mbar_wait(mbar, parity);
+        parity ^= 1u;
+        double* yv = slab + sh;
+        // centre on the k-mer mean; track min/max keys for the percentile bisection
+        uint64_t kmin = ~0ull, kmax = 0ull;
+        for (int i = lane; i < n; i += 32) {
+            const double v = yv[i] - m0;
+            yv[i] = v;
+            const uint64_t k = dkey(v);
+            kmin = k < kmin ? k : kmin;
+            kmax = k > kmax ? k : kmax;
+        }
+        kmin = warp_min_u64(kmin);
+        kmax = warp_max_u64(kmax);
+        __syncwarp();
+        // ---- initial locations (gmm.py:39-44) -------------------------------------------------
+        const double med = warp_percentile(yv, n, 0.5, kmin, kmax, lane);
+        const double loc1 = warp_percentile(yv, n, (0.0 < med) ? 0.75 : 0.25, kmin, kmax, lane);
+
+        for (int s = lane; s < 2 * G; s += 32) Nsm[s] = 0.0;
+        Comp c0 = mstep(0.0, 0.0, 0.0, a0, b0);
+        Comp c1 = c0;
+        c1.mp = loc1;
+        double N0 = 0, N1 = 0, S10 = 0, S11 = 0, S20 = 0, S21 = 0, Hq = 0;
+        double elbo_old = -INFINITY, elbo = -INFINITY;
+        int it = 0;
+        uint32_t st = STATUS_SELECTED;
+        __syncwarp();
+
+        for (;;) {
+            // ---- scalar phase: special functions spread over lanes ---------------------------
+            double e_loc = 0.0;
+            for (int s = lane; s < 2 * G + 2; s += 32) {
+                const bool is_c = s < 2 * G;
+                const int k = s & 1;
+                const Comp& c = k ? c1 : c0;
+                const double x = is_c ? (conc0 + Nsm[s]) : c.alpha;
+                double ps, lg;
+                psi_lgamma(x, &ps, &lg);
+                if (is_c) {
+                    const int g = s >> 1;
+                    lw[s] = ps - psis[g];
+                    if (goff[g + 1] > goff[g]) e_loc += lg;  // + sum_k lgamma(c_gk)
+                } else {
+                    double tb, lt;
+                    e_loc += elbo_component(c, k ? N1 : N0, k ? S11 : S10, k ? S21 : S20, a0, b0, prior_gamma, ps, lg,
+                                            xlog(c.beta), xlog(c.lam), tb, lt);
+                    sc[2 * k] = tb;
+                    sc[2 * k + 1] = lt;
+                }
+            }
+            __syncwarp();
+            elbo = warp_sum(e_loc) + Kconst - Hq;
+            if (it >= 1) {
+                const int rule = stop_rule(elbo, elbo_old, a.stopping);
+                if (rule == 2) {
+                    st |= STATUS_ELBO_DECREASED;
+                    break;
+                }
+                elbo_old = elbo;
+                if (rule == 1) {
+                    st |= STATUS_CONVERGED;
+                    break;
+                }
+            }
+            if (it >= a.max_iters - 1) {
+                if (it >= 1) st |= STATUS_HIT_MAX;
+                break;
+            }
+            ++it;
+            // ---- coefficients of d_n = A_g + y'(B + C y') ------------------------------------
+            double base, B, C;
+            estep_coefficients(c0, c1, sc[0], sc[2], sc[1], sc[3], base, B, C);
+            for (int g = lane; g < G; g += 32) Asm[g] = base + (lw[2 * g + 1] - lw[2 * g]);
+            for (int s = 0; s < 2 * G; ++s) scratch[s * 33 + lane] = 0.0;
+            __syncwarp();
+            // ---- E-step + moments: one pass over the resident reads -------------------------
+            double aN0 = 0, aN1 = 0, hq = 0;
+            S10 = S11 = S20 = S21 = 0.0;
+            {
+                int g = 0, gend = goff[1];
+                double A = Asm[0];
+                for (int i = lane; i < n; i += 32) {
+                    if (i >= gend) {
+                        scratch[(2 * g) * 33 + lane] = aN0;
+                        scratch[(2 * g + 1) * 33 + lane] = aN1;
+                        aN0 = aN1 = 0.0;
+                        do {
+                            ++g;
+                            gend = goff[g + 1];
+                        } while (i >= gend);
+                        A = Asm[g];
+                    }
+                    const double yy = yv[i];
+                    const double d = fma(yy, fma(C, yy, B), A);
+                    double r0, r1, h;
+                    estep_read(d, r0, r1, h);
+                    const double y2 = yy * yy;
+                    aN0 += r0;
+                    aN1 += r1;
+                    S10 = fma(r0, yy, S10);
+                    S11 = fma(r1, yy, S11);
+                    S20 = fma(r0, y2, S20);
+                    S21 = fma(r1, y2, S21);
+                    hq += h;
+                }
+                scratch[(2 * g) * 33 + lane] = aN0;
+                scratch[(2 * g + 1) * 33 + lane] = aN1;
+            }
+            __syncwarp();
+            S10 = warp_sum(S10);
+            S11 = warp_sum(S11);
+            S20 = warp_sum(S20);
+            S21 = warp_sum(S21);
+            Hq = warp_sum(hq);
+            for (int s = lane; s < 2 * G; s += 32) {
+                double t = 0.0;
+#pragma unroll 8
+                for (int l = 0; l < 32; ++l) t += scratch[s * 33 + l];
+                Nsm[s] = t;
+            }
+            __syncwarp();
+            N0 = N1 = 0.0;
+            for (int g = 0; g < G; ++g) {
+                N0 += Nsm[2 * g];
+                N1 += Nsm[2 * g + 1];
+            }
+            // ---- M-step (gmm.py:292-294, 364-370) -------------------------------------------
+            c0 = mstep(N0, S10, S20, a0, b0);
+            c1 = mstep(N1, S11, S21, a0, b0);
+        }
+        // ---- write the fit record ------------------------------------------------------------
+        double* out = a.fit + (size_t)p * fit_width(G);
+        if (lane == 0) {
+            out[FIT_MU] = m0 + c0.mp;
+            out[FIT_MU + 1] = m0 + c1.mp;
+            out[FIT_LAM] = c0.lam;
+            out[FIT_LAM + 1] = c1.lam;
+            out[FIT_ALPHA] = c0.alpha;
+            out[FIT_ALPHA + 1] = c1.alpha;
+            out[FIT_BETA] = c0.beta;
+            out[FIT_BETA + 1] = c1.beta;
+            out[FIT_ELBO] = elbo;
+            a.n_iter[p] = it;
+            a.status[p] = (a.status[p] & STATUS_TTEST_VALID) | st;
+        }
+        for (int s = lane; s < 2 * G; s += 32) out[FIT_N + s] = Nsm[s];
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: statistics, one thread per fitted position.
+// ------------------------------------------------------------------------------------------
+struct StatsArgs {
+    const int32_t* worklist;  // null => identity over P
+    const uint32_t* n_work;   // null => P
+    int P, G, C;
+    const int32_t* grp_cond;
+    const int32_t* grp_len;
+    const double* kmer_mean;
+    const double* kmer_std;
+    double conc0;
+    const double* fit;
+    double* stats;
+    uint32_t* status;
+};
+
+__global__ void xp_stats_kernel(StatsArgs a) {
+    __shared__ int s_cond[kMaxGroups];
+    for (int g = threadIdx.x; g < a.G; g += blockDim.x) s_cond[g] = a.grp_cond[g];
+    __syncthreads();
+    const unsigned n = a.n_work ? *a.n_work : (unsigned)a.P;
+    const unsigned w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    const int p = a.worklist ? a.worklist[w] : (int)w;
+    double w_mod[kMaxGroups], cov[kMaxGroups];
+    const uint32_t fl = compute_stats(a.G, a.C, s_cond, a.grp_len + (size_t)p * a.G, a.conc0, a.kmer_mean[p],
+                                      a.kmer_std[p], a.fit + (size_t)p * fit_width(a.G),
+                                      a.stats + (size_t)p * stats_width(a.G, a.C), w_mod, cov);
+    a.status[p] = (a.status[p] & ~(STATUS_KEEP_ROW | STATUS_MOD_IS_1 | STATUS_HIGHER)) | fl;
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 peak: 8 independent DFMA chains per thread, no memory traffic.
+// ------------------------------------------------------------------------------------------
+__global__ void xp_dfma_peak_kernel(double* out, int iters, double seed) {
+    double x0 = seed + threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+           x7 = x0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, m, c); x1 = fma(x1, m, c); x2 = fma(x2, m, c); x3 = fma(x3, m, c);
+        x4 = fma(x4, m, c); x5 = fma(x5, m, c); x6 = fma(x6, m, c); x7 = fma(x7, m, c);
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) out[0] = s;  // never true; keeps the chains alive
+}
+
+// Special functions as the kernels evaluate them (accuracy tests).
+__global__ void xp_eval_special_kernel(int which, const double* x, const double* aux, double* out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    double r = NAN, ps, lg;
+    switch (which) {
+        case 0: psi_lgamma(v, &ps, &lg); r = ps; break;
+        case 1: psi_lgamma(v, &ps, &lg); r = lg; break;
+        case 2: r = xlog(v); break;
+        case 3: r = xexp(v); break;
+        case 4: r = student_t_two_sided(v, aux[i]); break;
+        case 5: { double r0, r1, h; estep_read(v, r0, r1, h); r = r1; } break;
+        case 6: { double r0, r1, h; estep_read(v, r0, r1, h); r = h; } break;
+    }
+    out[i] = r;
+}
+
+}  // namespace xpk

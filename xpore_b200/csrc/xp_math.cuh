@@ -1,0 +1,265 @@
+// xp_math.cuh — FP64 special functions for the diffmod kernels (host+device).
+//
+// Everything here is written against IEEE-754 double with explicit fma(), so the same source
+// gives the same bits under nvcc (device) and g++ (host emulator used by the CPU tests), except
+// xrcp() which uses the hardware reciprocal seed on the device.
+//
+// Replaces the third-party calls the reference makes from its hot loop
+// (/root/reference/xpore/diffmod/gmm.py): np.exp :241, scipy.special.logsumexp :243,
+// scipy.special.digamma :283-284,350, scipy.special.gammaln :297,334,343, np.log :350; and
+// from the statistics (statstest.py:15-17 scipy.stats.ttest_ind / t.sf; utils/stats.py:15
+// norm.sf; io.py:373 norm.cdf; stats.py:36 math.erf).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define XP_HD __host__ __device__ __forceinline__
+#else
+#define XP_HD inline
+#endif
+
+namespace xpm {
+
+XP_HD uint64_t d2u(double x) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(x);
+#else
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    return u;
+#endif
+}
+XP_HD double u2d(uint64_t u) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double x;
+    memcpy(&x, &u, 8);
+    return x;
+#endif
+}
+
+constexpr double kLn2Hi = 6.93147180369123816490e-01;
+constexpr double kLn2Lo = 1.90821492927058770002e-10;
+constexpr double kLn2 = 6.931471805599453094e-01;
+constexpr double kLog2e = 1.44269504088896338700e+00;
+constexpr double kSqrt2 = 1.41421356237309504880e+00;
+constexpr double kLn2Pi = 1.83787706640934548356e+00;
+constexpr double kHalfLn2Pi = 0.91893853320467274178e+00;
+constexpr double kInvSqrt2 = 0.70710678118654752440e+00;
+
+// 1/x for normal positive x.  Device: 20-bit hardware seed + two Newton steps (<= 1 ulp).
+XP_HD double xrcp(double x) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+#else
+    return 1.0 / x;
+#endif
+}
+
+// log(1+f) kernel for f in [sqrt(1/2)-1, sqrt(2)-1], given s = f/(2+f).
+// Classic atanh form: log(1+f) = 2 atanh(s) = f - f^2/2 + s*(f^2/2 + R(s^2)); R is the degree-7
+// minimax polynomial of the freely published fdlibm/msun e_log.c (|err| < 2^-58.45).
+XP_HD double log1p_core(double f, double s) {
+    const double z = s * s;
+    double R = 1.479819860511658591e-01;
+    R = fma(R, z, 1.531383769920937332e-01);
+    R = fma(R, z, 1.818357216161805012e-01);
+    R = fma(R, z, 2.222219843214978396e-01);
+    R = fma(R, z, 2.857142874366239149e-01);
+    R = fma(R, z, 3.999999999940941908e-01);
+    R = fma(R, z, 6.666666666666735130e-01);
+    R = R * z;
+    const double hfsq = 0.5 * f * f;
+    return f - (hfsq - s * (hfsq + R));
+}
+
+// Natural log of a positive, normal double.
+XP_HD double xlog(double x) {
+    uint64_t u = d2u(x);
+    int e = (int)(u >> 52) - 1023;
+    u = (u & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull;
+    double m = u2d(u);  // [1,2)
+    if (m > kSqrt2) {
+        m *= 0.5;
+        e += 1;
+    }
+    const double f = m - 1.0;
+    const double s = f / (2.0 + f);
+    const double dk = (double)e;
+    const double l = log1p_core(f, s);
+    return fma(dk, kLn2Hi, fma(dk, kLn2Lo, l));
+}
+
+// log(1+u) for u > -0.29 (accurate for tiny u).
+XP_HD double xlog1p(double u) {
+    if (u < 0.41 && u > -0.29) return log1p_core(u, u / (2.0 + u));
+    return xlog(1.0 + u);
+}
+
+// exp(r) for |r| <= 0.35: Taylor to degree 13 (truncation < 5e-18 relative).
+XP_HD double exp_poly(double r) {
+    double p = 1.6059043836821613e-10;       // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);     // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);    // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);    // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);   // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);     // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);    // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);    // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);    // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);   // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);   // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return p;
+}
+
+// exp(x) for x in [-708, 708] (result stays a normal double).
+XP_HD double xexp(double x) {
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer by addition
+    const double t = fma(x, kLog2e, magic);
+    const double kf = t - magic;
+    const int64_t k = (int64_t)(int32_t)(uint32_t)d2u(t);
+    double r = fma(kf, -kLn2Hi, x);
+    r = fma(kf, -kLn2Lo, r);
+    const double p = exp_poly(r);
+    return u2d(d2u(p) + ((uint64_t)k << 52));
+}
+
+// psi(x) and lgamma(x) for x > 0 in one pass: shift to z >= 10 by the recurrences
+//   psi(x) = psi(x+m) - sum_{j<m} 1/(x+j),   lgamma(x) = lgamma(x+m) - log prod_{j<m}(x+j)
+// (the sum is kept as one fraction num/den so it costs a single division), then the Stirling
+// series with Bernoulli terms through B14.  |err| ~ 1e-15 relative.
+XP_HD void psi_lgamma(double x, double* psi, double* lgam) {
+    double num = 0.0, den = 1.0;
+    double z = x;
+    while (z < 10.0) {
+        num = fma(num, z, den);
+        den = den * z;
+        z += 1.0;
+    }
+    const double lz = xlog(z);
+    const double iz = 1.0 / z;
+    const double w = iz * iz;
+    // psi tail: sum B_2k / (2k z^2k)
+    double a = 8.33333333333333333333e-2;
+    a = fma(a, w, -2.10927960927960927961e-2);
+    a = fma(a, w, 7.57575757575757575758e-3);
+    a = fma(a, w, -4.16666666666666666667e-3);
+    a = fma(a, w, 3.96825396825396825397e-3);
+    a = fma(a, w, -8.33333333333333333333e-3);
+    a = fma(a, w, 8.33333333333333333333e-2);
+    double ps = lz - 0.5 * iz - a * w;
+    // lgamma tail: sum B_2k / (2k(2k-1) z^(2k-1))
+    double b = 6.41025641025641025641e-3;    //  1/156
+    b = fma(b, w, -1.91752691752691752692e-3);   // -691/360360
+    b = fma(b, w, 8.41750841750841750842e-4);    //  1/1188
+    b = fma(b, w, -5.95238095238095238095e-4);   // -1/1680
+    b = fma(b, w, 7.93650793650793650794e-4);    //  1/1260
+    b = fma(b, w, -2.77777777777777777778e-3);   // -1/360
+    b = fma(b, w, 8.33333333333333333333e-2);    //  1/12
+    double lg = fma(z - 0.5, lz, -z) + kHalfLn2Pi + b * iz;
+    if (den != 1.0) {
+        ps -= num / den;
+        lg -= xlog(den);
+    }
+    *psi = ps;
+    *lgam = lg;
+}
+
+XP_HD double xlgamma(double x) {
+    double p, l;
+    psi_lgamma(x, &p, &l);
+    return l;
+}
+
+XP_HD double xerfc(double x) { return erfc(x); }
+XP_HD double xerf(double x) { return erf(x); }
+
+// Regularised incomplete beta I_x(a,b) by the modified Lentz continued fraction.
+// xc must be 1-x computed without cancellation by the caller.
+XP_HD double betacf(double a, double b, double x) {
+    const double tiny = 1e-300;
+    const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double c = 1.0;
+    double d = 1.0 - qab * x / qap;
+    if (fabs(d) < tiny) d = tiny;
+    d = 1.0 / d;
+    double h = d;
+    for (int m = 1; m <= 500; ++m) {
+        const double m2 = 2.0 * m;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d;
+        if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c;
+        if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        h *= d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d;
+        if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c;
+        if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 2e-16) break;
+    }
+    return h;
+}
+
+// Stirling correction  sum_k B_2k / (2k(2k-1) z^(2k-1))  for z >= 10.
+XP_HD double stirling_corr(double z) {
+    const double iz = 1.0 / z, w = iz * iz;
+    double b = 6.41025641025641025641e-3;
+    b = fma(b, w, -1.91752691752691752692e-3);
+    b = fma(b, w, 8.41750841750841750842e-4);
+    b = fma(b, w, -5.95238095238095238095e-4);
+    b = fma(b, w, 7.93650793650793650794e-4);
+    b = fma(b, w, -2.77777777777777777778e-3);
+    b = fma(b, w, 8.33333333333333333333e-2);
+    return b * iz;
+}
+
+// lgamma(a+b) - lgamma(a) without the cancellation of two large lgammas (a >= 10):
+//   (a-1/2) log1p(b/a) + b ln(a+b) - b + corr(a+b) - corr(a)
+XP_HD double lgamma_diff(double a, double b) {
+    if (a < 10.0) return xlgamma(a + b) - xlgamma(a);
+    return (a - 0.5) * xlog1p(b / a) + b * xlog(a + b) - b + (stirling_corr(a + b) - stirling_corr(a));
+}
+
+XP_HD double betainc(double a, double b, double x, double xc, double lnx, double lnxc) {
+    if (x <= 0.0) return 0.0;
+    if (xc <= 0.0) return 1.0;
+    const double lbeta = lgamma_diff(a, b) - xlgamma(b);
+    const double lfront = lbeta + a * lnx + b * lnxc;
+    const double front = (lfront < -700.0) ? 0.0 : xexp(lfront);
+    if (x < (a + 1.0) / (a + b + 2.0)) return front * betacf(a, b, x) / a;
+    return 1.0 - front * betacf(b, a, xc) / b;
+}
+
+// Two-sided Student-t p-value 2*sf(|t|, df) = I_{df/(df+t^2)}(df/2, 1/2)   (statstest.py:17).
+XP_HD double student_t_two_sided(double t, double df) {
+    if (t != t || df != df) return NAN;
+    if (!(df > 0.0)) return NAN;
+    const double t2 = t * t;
+    if (t2 == INFINITY) return 0.0;
+    if (t2 < 1e-280) return 1.0;
+    const double x = df / (df + t2);
+    const double xc = t2 / (df + t2);  // 1-x without cancellation
+    const double lnx = -xlog1p(t2 / df);
+    const double lnxc = xlog(xc);
+    return betainc(0.5 * df, 0.5, x, xc, lnx, lnxc);
+}
+
+}  // namespace xpm
