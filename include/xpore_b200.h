@@ -98,7 +98,8 @@ int32_t xpb200_fit_device(const xpb200_batch* batch, const xpb200_method* method
 
 /* Same path on HOST pointers (the drop-in call): copies the batch to the device, runs, copies
  * the results back, synchronises.  `device` is the CUDA ordinal.  Pinned host buffers make the
- * copies asynchronous; pageable ones work too.  `n_fitted` (optional) gets the selected count. */
+ * copies asynchronous; pageable ones work too; the result arrays may also be device memory
+ * (copies use cudaMemcpyDefault).  `n_fitted` (optional) gets the selected count. */
 int32_t xpb200_fit_host(int32_t device, const xpb200_batch* batch, const xpb200_method* method,
                         const xpb200_result* result, uint32_t* n_fitted);
 
@@ -119,6 +120,12 @@ int32_t xpb200_fit_launch_info(int32_t device, int32_t n_groups, int32_t max_rea
 
 /* Kernel launches issued by this library in the calling thread since load (bench.py's gpu_launches). */
 uint64_t xpb200_launch_count(void);
+
+/* Per-stage device timing of the calling thread's xpb200_fit_device calls, with CUDA events on
+ * the launch stream: after xpb200_set_stage_timing(1), xpb200_get_stage_ms returns the duration of
+ * the last call's stages {prefilter, worklist, fit, stats} in milliseconds (it synchronises). */
+int32_t xpb200_set_stage_timing(int32_t on);
+int32_t xpb200_get_stage_ms(float* ms4);
 
 /* FP64 roofline denominator: dependent-free DFMA streams on every SM; returns TFLOP/s
  * (2 flop per FMA) measured with CUDA events over `repeats` launches. */

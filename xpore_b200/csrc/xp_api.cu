@@ -16,6 +16,16 @@ namespace {
 thread_local std::string g_err;
 thread_local uint64_t g_launches = 0;
 
+// optional per-stage CUDA-event timing of xpb200_fit_device (bench.py's roofline numbers)
+struct StageTimer {
+    bool on = false, valid = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+thread_local StageTimer g_timer;
+void stage_mark(int i, cudaStream_t st) {
+    if (g_timer.on && g_timer.ev[i]) cudaEventRecord(g_timer.ev[i], st);
+}
+
 int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
@@ -180,6 +190,7 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
     if (!workspace || workspace_bytes < xpb200_workspace_bytes(P)) return fail(XPB200_ENOMEM, "workspace too small");
     Workspace ws = carve(workspace);
     CK(cudaMemsetAsync(workspace, 0, ws_header_bytes(), st));
+    stage_mark(0, st);
 
     // K1 prefilter (or: everything selected, p-value NaN)
     const uint32_t* sel = nullptr;
@@ -190,6 +201,7 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
         CK(cudaMemsetAsync(r->status, 0, (size_t)P * 4, st));
         CK(cudaMemsetAsync(r->pval, 0xFF, (size_t)P * 8, st));  // all-ones = NaN
     }
+    stage_mark(1, st);
     // worklist, longest positions first
     xpk::WorklistArgs wa;
     wa.status = sel; wa.read_off = b->read_off; wa.P = P; wa.hist = ws.hist; wa.cursor = ws.cursor;
@@ -202,6 +214,7 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
     g_launches += 3;
     CK(cudaGetLastError());
 
+    stage_mark(2, st);
     // K3 fit: persistent CTAs, one warp per position
     Geometry g;
     if (int rc = fit_geometry(b->n_groups, b->max_reads, &g)) return rc;
@@ -221,8 +234,11 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
     ++g_launches;
     CK(cudaGetLastError());
 
+    stage_mark(3, st);
     // K4 statistics
     if (int rc = launch_stats(b, m, r, ws.worklist, ws.n_work, st)) return rc;
+    stage_mark(4, st);
+    g_timer.valid = g_timer.on;
     if (n_fitted_dev) CK(cudaMemcpyAsync(n_fitted_dev, ws.n_work, 4, cudaMemcpyDeviceToDevice, st));
     return 0;
 }
@@ -289,13 +305,13 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
     char* d = reinterpret_cast<char*>(dc->buf);
     cudaStream_t st = dc->stream;
     if (P > 0) {
-        CK(cudaMemcpyAsync(d + o_y, b->y, (size_t)b->n_reads * 8, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d + o_off, b->read_off, (size_t)(P + 1) * 8, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d + o_glen, b->grp_len, (size_t)P * G * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d + o_km, b->kmer_mean, (size_t)P * 8, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d + o_ks, b->kmer_std, (size_t)P * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d + o_y, b->y, (size_t)b->n_reads * 8, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(d + o_off, b->read_off, (size_t)(P + 1) * 8, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(d + o_glen, b->grp_len, (size_t)P * G * 4, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(d + o_km, b->kmer_mean, (size_t)P * 8, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(d + o_ks, b->kmer_std, (size_t)P * 8, cudaMemcpyDefault, st));
     }
-    CK(cudaMemcpyAsync(d + o_gc, b->grp_cond, (size_t)G * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + o_gc, b->grp_cond, (size_t)G * 4, cudaMemcpyDefault, st));
     xpb200_batch db = *b;
     db.y = (const double*)(d + o_y); db.read_off = (const int64_t*)(d + o_off);
     db.grp_len = (const int32_t*)(d + o_glen); db.kmer_mean = (const double*)(d + o_km);
@@ -311,14 +327,14 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
     if (int rc = xpb200_fit_device(&db, m, &dr, d + o_ws, xpb200_workspace_bytes(P), (uint32_t*)(d + o_nf), st))
         return rc;
     if (P > 0) {
-        CK(cudaMemcpyAsync(r->status, dr.status, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(r->n_iter, dr.n_iter, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(r->pval, dr.pval, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(r->fit, dr.fit, (size_t)P * FW * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(r->stats, dr.stats, (size_t)P * SW * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(r->status, dr.status, (size_t)P * 4, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(r->n_iter, dr.n_iter, (size_t)P * 4, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(r->pval, dr.pval, (size_t)P * 8, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(r->fit, dr.fit, (size_t)P * FW * 8, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(r->stats, dr.stats, (size_t)P * SW * 8, cudaMemcpyDefault, st));
     }
     uint32_t nf = 0;
-    CK(cudaMemcpyAsync(&nf, d + o_nf, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&nf, d + o_nf, 4, cudaMemcpyDefault, st));
     CK(cudaStreamSynchronize(st));
     if (n_fitted) *n_fitted = nf;
     return 0;
@@ -364,6 +380,22 @@ int32_t xpb200_measure_fp64_peak(int32_t device, int32_t repeats, double* tflops
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(out);
+    return 0;
+}
+
+int32_t xpb200_set_stage_timing(int32_t on) {
+    if (on && !g_timer.ev[0])
+        for (auto& e : g_timer.ev) CK(cudaEventCreate(&e));
+    g_timer.on = on != 0;
+    g_timer.valid = false;
+    return 0;
+}
+
+int32_t xpb200_get_stage_ms(float* ms4) {
+    if (!ms4) return fail(XPB200_EINVAL, "null out");
+    if (!g_timer.valid) return fail(XPB200_EINVAL, "no timed xpb200_fit_device call on this thread");
+    CK(cudaEventSynchronize(g_timer.ev[4]));
+    for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&ms4[i], g_timer.ev[i], g_timer.ev[i + 1]));
     return 0;
 }
 

@@ -16,6 +16,7 @@ Model: k-mer per position uniform over the 1024 non-``N`` 5-mers; unmodified rea
 from __future__ import annotations
 
 import json
+import math
 import os
 from collections import OrderedDict
 from dataclasses import dataclass, field
@@ -215,3 +216,76 @@ def make_batch(spec: Spec, km: KmerModel | None = None, n_positions: int | None 
         b.positions = [str(100 + i % spec.pos_per_gene) for i in range(b.n_positions)]
         b.kmers = [km.kmers[k] for k in krow]
     return b.validate()
+
+
+def make_batch_device(spec: Spec, device, km: KmerModel | None = None, n_positions: int | None = None,
+                      seed_offset: int = 0, chunk: int = 250000) -> Batch:
+    """Same statistical model as :func:`make_batch`, drawn with torch on ``device`` (the numpy
+    generator needs ~40 s for the 3.6e8 reads of config c2; this takes about a second) and
+    returned as a host :class:`Batch`.  Not bit-identical to :func:`make_batch`."""
+    import torch
+
+    km = km or KmerModel.load()
+    gen = torch.Generator(device=device)
+    gen.manual_seed(1000003 * spec.seed + seed_offset)
+    pooling = bool(spec.method.get("pooling", False))
+    info = spec.data_info()
+    lay_runs = Layout.from_data_info(info, pooling=False)
+    lay = Layout.from_data_info(info, pooling=pooling)
+    crit = spec.criteria or {"readcount_min": 15, "readcount_max": 1000}
+    lo, hi = crit["readcount_min"], crit["readcount_max"]
+    P_all = n_positions if n_positions is not None else spec.n_genes * spec.pos_per_gene
+    Gr = lay_runs.n_groups
+    run_cond = torch.tensor(lay_runs.run_cond, device=device)
+    C = lay.n_conditions
+    if pooling:
+        assert lay_runs.run_cond == sorted(lay_runs.run_cond), "pooled synthetic data needs sorted conditions"
+    rows = torch.tensor(km.usable_rows(), device=device)
+    kmean = torch.tensor(km.mean, device=device)
+    kstd = torch.tensor(km.stdv, device=device)
+    ko = torch.tensor([lay_runs.condition_names[c] in spec.ko_like for c in lay_runs.run_cond], device=device)
+    ys, glens, kms, kss = [], [], [], []
+    for c0 in range(0, P_all, chunk):
+        P = min(chunk, P_all - c0)
+        krow = rows[torch.randint(0, len(rows), (P,), device=device, generator=gen)]
+        mu, sd = kmean[krow], kstd[krow]
+        is_mod = torch.rand(P, device=device, generator=gen) < spec.f_mod
+        shift = (3.0 + 5.0 * torch.rand(P, device=device, generator=gen, dtype=torch.float64)) * \
+            torch.where(torch.rand(P, device=device, generator=gen) < 0.5, -1.0, 1.0)
+        if spec.loguniform_total is not None:
+            l0, l1 = spec.loguniform_total
+            tot = torch.exp(math.log(l0) + (math.log(l1) - math.log(l0)) *
+                            torch.rand(P, device=device, generator=gen, dtype=torch.float64))
+            counts = torch.clamp(torch.round(tot / Gr), min=1).to(torch.int64)[:, None].repeat(1, Gr)
+        else:
+            counts = torch.randint(spec.reads_lo, spec.reads_hi + 1, (P, Gr), device=device, generator=gen)
+        rate = torch.where(ko, 0.05, 0.6)[None, :] * is_mod[:, None]
+        if pooling:
+            csum = torch.stack([counts[:, run_cond == c].sum(dim=1) for c in range(C)], dim=1)
+            keep = ((csum >= lo) & (csum <= hi)).sum(dim=1) >= 2
+        else:
+            ok = (counts >= lo) & (counts <= hi)
+            counts = torch.where(ok, counts, 0)
+            has = torch.stack([ok[:, run_cond == c].any(dim=1) for c in range(C)], dim=1)
+            keep = has.sum(dim=1) >= 2
+        mu, sd, shift, counts, rate = mu[keep], sd[keep], shift[keep], counts[keep], rate[keep]
+        n_cell = counts.reshape(-1)
+        R = int(n_cell.sum())
+        cell = torch.repeat_interleave(torch.arange(n_cell.numel(), device=device, dtype=torch.int32), n_cell,
+                                       output_size=R)
+        pos = (cell // Gr).long()
+        mod = torch.rand(R, device=device, generator=gen) < rate.reshape(-1)[cell.long()]
+        z = torch.randn(R, device=device, generator=gen, dtype=torch.float64)
+        y = torch.where(mod, mu[pos] + shift[pos] + 1.3 * sd[pos] * z, mu[pos] + sd[pos] * z)
+        y = torch.round(y * 100.0) / 100.0
+        glen = torch.stack([counts[:, run_cond == c].sum(dim=1) for c in range(C)], dim=1) if pooling else counts
+        ys.append(y.cpu())
+        glens.append(glen.to(torch.int32).cpu())
+        kms.append(mu.cpu())
+        kss.append(sd.cpu())
+        del cell, pos, mod, z, y
+    grp_len = torch.cat(glens).numpy()
+    read_off = np.zeros(len(grp_len) + 1, dtype=np.int64)
+    np.cumsum(grp_len.sum(axis=1, dtype=np.int64), out=read_off[1:])
+    return Batch(lay, torch.cat(ys).numpy(), read_off, np.ascontiguousarray(grp_len), torch.cat(kms).numpy(),
+                 torch.cat(kss).numpy()).validate()
