@@ -35,6 +35,7 @@ constexpr uint32_t STATUS_TTEST_VALID = 128u;  // exactly two conditions present
 
 struct Comp {
     double mp, lam, alpha, beta;  // centred location m', lambda, alpha, beta of q(mu_k, tau_k)
+    double il;                    // 1/lambda
 };
 
 // ---- E-step for one read (gmm.py:236-243) --------------------------------------------------
@@ -45,13 +46,13 @@ XP_HD void estep_read(double d, double& r0, double& r1, double& hq) {
     const double ad = fabs(d);
     const double t = xexp(-fmin(ad, 500.0));
     const double u = 1.0 + t;
-    const bool big = u > kSqrt2;
+    const bool big = u > XPT(kMisc)[4];  // sqrt 2
     const double f = big ? 0.5 * (t - 1.0) : t;  // u/2 - 1 or u - 1
     const double den = 2.0 + f;
     const double q = xrcp(u * den);
     const double inv = q * den;       // 1/(1+t)
     const double s = f * (q * u);     // f/(2+f)
-    const double l1p = log1p_core(f, s) + (big ? kLn2 : 0.0);  // log(1+t)
+    const double l1p = log1p_core(f, s) + (big ? XPT(kMisc)[3] : 0.0);  // log(1+t)
     const double rmin = t * inv;
     const bool pos = d > 0.0;
     r1 = pos ? inv : rmin;
@@ -63,10 +64,10 @@ XP_HD void estep_read(double d, double& r0, double& r1, double& hq) {
 XP_HD Comp mstep(double Nk, double S1, double S2, double a0, double b0) {
     Comp c;
     c.lam = 1.0 + Nk;
-    const double il = 1.0 / c.lam;
-    c.mp = S1 * il;
+    c.il = xdiv(1.0, c.lam);
+    c.mp = S1 * c.il;
     c.alpha = a0 + 0.5 * Nk;
-    c.beta = b0 + 0.5 * (S2 - S1 * S1 * il);
+    c.beta = b0 + 0.5 * (S2 - S1 * S1 * c.il);
     return c;
 }
 
@@ -77,9 +78,9 @@ XP_HD Comp mstep(double Nk, double S1, double S2, double a0, double b0) {
 XP_HD double elbo_component(const Comp& c, double Nk, double S1, double S2, double a0, double b0,
                             double prior_gamma, double psi_a, double lg_a, double ln_b, double ln_lam,
                             double& tbar, double& ltau) {
-    tbar = c.alpha / c.beta;
+    tbar = xdiv(c.alpha, c.beta);
     ltau = psi_a - ln_b;
-    const double il = 1.0 / c.lam;
+    const double il = c.il;
     const double m2 = c.mp * c.mp;
     const double quad = fma(m2, Nk, fma(-2.0 * c.mp, S1, S2));  // sum_n r_nk (y'-m')^2
     const double t1 = 0.5 * Nk * (ltau - kLn2Pi - il) - 0.5 * tbar * quad;
@@ -94,7 +95,7 @@ XP_HD double elbo_component(const Comp& c, double Nk, double S1, double S2, doub
 //   A_g = base + (E ln w_g1 - E ln w_g0)
 XP_HD void estep_coefficients(const Comp& c0, const Comp& c1, double tb0, double tb1, double lt0, double lt1,
                               double& base, double& B, double& C) {
-    const double il0 = 1.0 / c0.lam, il1 = 1.0 / c1.lam;
+    const double il0 = c0.il, il1 = c1.il;
     base = 0.5 * (lt1 - lt0) - 0.5 * (il1 - il0) - 0.5 * (tb1 * c1.mp * c1.mp - tb0 * c0.mp * c0.mp);
     B = tb1 * c1.mp - tb0 * c0.mp;
     C = -0.5 * (tb1 - tb0);
@@ -106,7 +107,8 @@ XP_HD void estep_coefficients(const Comp& c0, const Comp& c1, double tb0, double
 XP_HD int stop_rule(double elbo_new, double elbo_old, double stopping) {
     const double delta = elbo_new - elbo_old;
     if (rint(delta * 1e8) < 0.0) return 2;
-    const double diff = delta / fabs(elbo_old);
+    if (elbo_old == -INFINITY) return 0;  // first sweep: the reference compares with the ELBO of a random q(z)
+    const double diff = xdiv(delta, fabs(elbo_old));
     return (diff < stopping) ? 1 : 0;
 }
 

@@ -271,7 +271,7 @@ __global__ void xp_worklist_scatter(WorklistArgs a) {
 //   lw[2G]            E[ln w_gk] = psi(c_gk) - psi(c_g0 + c_g1)        (gmm.py:283-284)
 //   Asm[G]            per-group constant of d_n
 //   psis[G]           psi(2 c0 + n_g): sum_k c_gk = 2 c0 + n_g is constant over sweeps
-//   sc[4]             E[tau_k], E[ln tau_k] published by the lanes that own component k
+//   sc[8]             psi(alpha_k), lgamma(alpha_k), ln beta_k, ln lambda_k published by their lanes
 //   goff[G+1] (int)   group offsets inside the position
 //   mbar (u64)        TMA completion barrier
 // ------------------------------------------------------------------------------------------
@@ -292,7 +292,7 @@ struct FitArgs {
 };
 
 __host__ __device__ inline size_t fit_warp_smem_bytes(int cap, int G) {
-    size_t doubles = (size_t)(cap + 2) + 66 * (size_t)G + 2 * G + 2 * G + G + G + 4;
+    size_t doubles = (size_t)(cap + 2) + 66 * (size_t)G + 2 * G + 2 * G + G + G + 8;
     size_t bytes = doubles * 8 + (size_t)((G + 2) & ~1) * 4 + 8;
     return (bytes + 15) & ~(size_t)15;
 }
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
     double* Asm = lw + 2 * G;
     double* psis = Asm + G;
     double* sc = psis + G;
-    int* goff = reinterpret_cast<int*>(sc + 4);
+    int* goff = reinterpret_cast<int*>(sc + 8);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(goff + ((G + 2) & ~1));
 
     if (lane == 0) {
@@ -446,28 +446,52 @@ __global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
         __syncwarp();
 
         for (;;) {
-            // ---- scalar phase: special functions spread over lanes ---------------------------
+            // ---- scalar phase: special functions spread over lanes, one uniform code path --------
+            // slots: [0,2G) c_gk -> psi, lgamma;  2G+k alpha_k -> psi, lgamma;
+            //        2G+2+k -> ln beta_k;  2G+4+k -> ln lambda_k
             double e_loc = 0.0;
-            for (int s = lane; s < 2 * G + 2; s += 32) {
-                const bool is_c = s < 2 * G;
+            for (int s0 = 0; s0 < 2 * G + 6; s0 += 32) {
+                const int s = s0 + lane;
+                const int role = (s < 2 * G) ? 0 : (s < 2 * G + 2) ? 1 : (s < 2 * G + 6) ? 2 : 3;
                 const int k = s & 1;
                 const Comp& c = k ? c1 : c0;
-                const double x = is_c ? (conc0 + Nsm[s]) : c.alpha;
+                double x = 16.0;
+                if (role == 0) x = conc0 + Nsm[s];
+                else if (role == 1) x = c.alpha;
+                else if (role == 2) x = (s < 2 * G + 4) ? c.beta : c.lam;
+                double z, num, den;
+                shift_to_10(role == 2 ? 16.0 : x, z, num, den);
+                if (role == 2) z = x;
+                const double lz = xlog(z), lden = xlog(den);
+                const double q = xrcp(z * den);
                 double ps, lg;
-                psi_lgamma(x, &ps, &lg);
-                if (is_c) {
+                psi_lgamma_finish(z, lz, lden, q * den, num * (q * z), &ps, &lg);
+                if (role == 0) {
                     const int g = s >> 1;
                     lw[s] = ps - psis[g];
                     if (goff[g + 1] > goff[g]) e_loc += lg;  // + sum_k lgamma(c_gk)
-                } else {
-                    double tb, lt;
-                    e_loc += elbo_component(c, k ? N1 : N0, k ? S11 : S10, k ? S21 : S20, a0, b0, prior_gamma, ps, lg,
-                                            xlog(c.beta), xlog(c.lam), tb, lt);
-                    sc[2 * k] = tb;
-                    sc[2 * k + 1] = lt;
+                } else if (role == 1) {
+                    sc[k] = ps;
+                    sc[2 + k] = lg;
+                } else if (role == 2) {
+                    sc[4 + (s - 2 * G - 2)] = lz;
                 }
             }
             __syncwarp();
+            double tb0, tb1, lt0, lt1;
+            {   // component terms: even lanes take k = 0, odd lanes k = 1
+                const int k = lane & 1;
+                const Comp& c = k ? c1 : c0;
+                double tb, lt;
+                const double ek = elbo_component(c, k ? N1 : N0, k ? S11 : S10, k ? S21 : S20, a0, b0, prior_gamma,
+                                                 sc[k], sc[2 + k], sc[4 + k], sc[6 + k], tb, lt);
+                if (lane < 2) e_loc += ek;
+                const double tbo = __shfl_xor_sync(kFull, tb, 1), lto = __shfl_xor_sync(kFull, lt, 1);
+                tb0 = k ? tbo : tb;
+                tb1 = k ? tb : tbo;
+                lt0 = k ? lto : lt;
+                lt1 = k ? lt : lto;
+            }
             elbo = warp_sum(e_loc) + Kconst - Hq;
             if (it >= 1) {
                 const int rule = stop_rule(elbo, elbo_old, a.stopping);
@@ -488,7 +512,7 @@ __global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
             ++it;
             // ---- coefficients of d_n = A_g + y'(B + C y') ------------------------------------
             double base, B, C;
-            estep_coefficients(c0, c1, sc[0], sc[2], sc[1], sc[3], base, B, C);
+            estep_coefficients(c0, c1, tb0, tb1, lt0, lt1, base, B, C);
             for (int g = lane; g < G; g += 32) Asm[g] = base + (lw[2 * g + 1] - lw[2 * g]);
             for (int s = 0; s < 2 * G; ++s) scratch[s * 33 + lane] = 0.0;
             __syncwarp();

@@ -20,7 +20,42 @@
 #define XP_HD inline
 #endif
 
+// Polynomial coefficients live in __constant__ memory on the device so that DFMA takes them as
+// constant-bank operands (64-bit literals would be rebuilt with two UMOVs per use inside the
+// hot loops); the host build reads the same values from static arrays.
+#if defined(__CUDACC__)
+#define XP_TABLE(name, n, ...)                        \
+    static const double h_##name[n] = {__VA_ARGS__};  \
+    __constant__ double d_##name[n] = {__VA_ARGS__};
+#else
+#define XP_TABLE(name, n, ...) static const double h_##name[n] = {__VA_ARGS__};
+#endif
+#if defined(__CUDA_ARCH__)
+#define XPT(name) d_##name
+#else
+#define XPT(name) h_##name
+#endif
+
 namespace xpm {
+
+// log1p kernel R(z), fdlibm/msun e_log.c Lg7..Lg1
+XP_TABLE(kLg, 7, 1.479819860511658591e-01, 1.531383769920937332e-01, 1.818357216161805012e-01,
+         2.222219843214978396e-01, 2.857142874366239149e-01, 3.999999999940941908e-01, 6.666666666666735130e-01)
+// 1/13! .. 1/2!
+XP_TABLE(kExp, 12, 1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,
+         2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03,
+         8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5)
+// B_2k/(2k): 1/12 -691/32760 1/132 -1/240 1/252 -1/120 1/12   (highest order first)
+XP_TABLE(kPsi, 7, 8.33333333333333333333e-2, -2.10927960927960927961e-2, 7.57575757575757575758e-3,
+         -4.16666666666666666667e-3, 3.96825396825396825397e-3, -8.33333333333333333333e-3,
+         8.33333333333333333333e-2)
+// B_2k/(2k(2k-1)): 1/156 -691/360360 1/1188 -1/1680 1/1260 -1/360 1/12
+XP_TABLE(kLgam, 7, 6.41025641025641025641e-3, -1.91752691752691752692e-3, 8.41750841750841750842e-4,
+         -5.95238095238095238095e-4, 7.93650793650793650794e-4, -2.77777777777777777778e-3,
+         8.33333333333333333333e-2)
+// ln2 hi/lo, log2(e), ln2, sqrt2, round-to-int magic
+XP_TABLE(kMisc, 6, 6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.44269504088896338700e+00,
+         6.931471805599453094e-01, 1.41421356237309504880e+00, 6755399441055744.0)
 
 XP_HD uint64_t d2u(double x) {
 #if defined(__CUDA_ARCH__)
@@ -65,18 +100,23 @@ XP_HD double xrcp(double x) {
 #endif
 }
 
+// a/b: exact IEEE on the host, a * xrcp(b) (<= 2 ulp) on the device.
+XP_HD double xdiv(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return a * xrcp(b);
+#else
+    return a / b;
+#endif
+}
+
 // log(1+f) kernel for f in [sqrt(1/2)-1, sqrt(2)-1], given s = f/(2+f).
 // Classic atanh form: log(1+f) = 2 atanh(s) = f - f^2/2 + s*(f^2/2 + R(s^2)); R is the degree-7
 // minimax polynomial of the freely published fdlibm/msun e_log.c (|err| < 2^-58.45).
 XP_HD double log1p_core(double f, double s) {
     const double z = s * s;
-    double R = 1.479819860511658591e-01;
-    R = fma(R, z, 1.531383769920937332e-01);
-    R = fma(R, z, 1.818357216161805012e-01);
-    R = fma(R, z, 2.222219843214978396e-01);
-    R = fma(R, z, 2.857142874366239149e-01);
-    R = fma(R, z, 3.999999999940941908e-01);
-    R = fma(R, z, 6.666666666666735130e-01);
+    double R = XPT(kLg)[0];
+#pragma unroll
+    for (int i = 1; i < 7; ++i) R = fma(R, z, XPT(kLg)[i]);
     R = R * z;
     const double hfsq = 0.5 * f * f;
     return f - (hfsq - s * (hfsq + R));
@@ -93,32 +133,23 @@ XP_HD double xlog(double x) {
         e += 1;
     }
     const double f = m - 1.0;
-    const double s = f / (2.0 + f);
+    const double s = xdiv(f, 2.0 + f);
     const double dk = (double)e;
     const double l = log1p_core(f, s);
-    return fma(dk, kLn2Hi, fma(dk, kLn2Lo, l));
+    return fma(dk, XPT(kMisc)[0], fma(dk, XPT(kMisc)[1], l));
 }
 
 // log(1+u) for u > -0.29 (accurate for tiny u).
 XP_HD double xlog1p(double u) {
-    if (u < 0.41 && u > -0.29) return log1p_core(u, u / (2.0 + u));
+    if (u < 0.41 && u > -0.29) return log1p_core(u, xdiv(u, 2.0 + u));
     return xlog(1.0 + u);
 }
 
 // exp(r) for |r| <= 0.35: Taylor to degree 13 (truncation < 5e-18 relative).
 XP_HD double exp_poly(double r) {
-    double p = 1.6059043836821613e-10;       // 1/13!
-    p = fma(p, r, 2.08767569878681e-09);     // 1/12!
-    p = fma(p, r, 2.505210838544172e-08);    // 1/11!
-    p = fma(p, r, 2.755731922398589e-07);    // 1/10!
-    p = fma(p, r, 2.7557319223985893e-06);   // 1/9!
-    p = fma(p, r, 2.48015873015873e-05);     // 1/8!
-    p = fma(p, r, 1.984126984126984e-04);    // 1/7!
-    p = fma(p, r, 1.388888888888889e-03);    // 1/6!
-    p = fma(p, r, 8.333333333333333e-03);    // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);   // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);   // 1/3!
-    p = fma(p, r, 0.5);
+    double p = XPT(kExp)[0];
+#pragma unroll
+    for (int i = 1; i < 12; ++i) p = fma(p, r, XPT(kExp)[i]);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     return p;
@@ -126,55 +157,49 @@ XP_HD double exp_poly(double r) {
 
 // exp(x) for x in [-708, 708] (result stays a normal double).
 XP_HD double xexp(double x) {
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer by addition
-    const double t = fma(x, kLog2e, magic);
+    const double magic = XPT(kMisc)[5];  // 1.5 * 2^52: round-to-nearest-integer by addition
+    const double t = fma(x, XPT(kMisc)[2], magic);
     const double kf = t - magic;
     const int64_t k = (int64_t)(int32_t)(uint32_t)d2u(t);
-    double r = fma(kf, -kLn2Hi, x);
-    r = fma(kf, -kLn2Lo, r);
+    double r = fma(-kf, XPT(kMisc)[0], x);
+    r = fma(-kf, XPT(kMisc)[1], r);
     const double p = exp_poly(r);
     return u2d(d2u(p) + ((uint64_t)k << 52));
 }
 
 // psi(x) and lgamma(x) for x > 0 in one pass: shift to z >= 10 by the recurrences
 //   psi(x) = psi(x+m) - sum_{j<m} 1/(x+j),   lgamma(x) = lgamma(x+m) - log prod_{j<m}(x+j)
-// (the sum is kept as one fraction num/den so it costs a single division), then the Stirling
-// series with Bernoulli terms through B14.  |err| ~ 1e-15 relative.
-XP_HD void psi_lgamma(double x, double* psi, double* lgam) {
-    double num = 0.0, den = 1.0;
-    double z = x;
+// (the sum is kept as one fraction num/den), then the Stirling series with Bernoulli terms
+// through B14.  |err| ~ 1e-15 relative.  Split in three steps so the kernels can run the two
+// logarithms of all lanes' arguments through one uniform code path.
+XP_HD void shift_to_10(double x, double& z, double& num, double& den) {
+    num = 0.0;
+    den = 1.0;
+    z = x;
     while (z < 10.0) {
         num = fma(num, z, den);
         den = den * z;
         z += 1.0;
     }
-    const double lz = xlog(z);
-    const double iz = 1.0 / z;
+}
+// lz = ln z, lden = ln den, iz = 1/z, sden = num/den
+XP_HD void psi_lgamma_finish(double z, double lz, double lden, double iz, double sden, double* psi, double* lgam) {
     const double w = iz * iz;
-    // psi tail: sum B_2k / (2k z^2k)
-    double a = 8.33333333333333333333e-2;
-    a = fma(a, w, -2.10927960927960927961e-2);
-    a = fma(a, w, 7.57575757575757575758e-3);
-    a = fma(a, w, -4.16666666666666666667e-3);
-    a = fma(a, w, 3.96825396825396825397e-3);
-    a = fma(a, w, -8.33333333333333333333e-3);
-    a = fma(a, w, 8.33333333333333333333e-2);
-    double ps = lz - 0.5 * iz - a * w;
-    // lgamma tail: sum B_2k / (2k(2k-1) z^(2k-1))
-    double b = 6.41025641025641025641e-3;    //  1/156
-    b = fma(b, w, -1.91752691752691752692e-3);   // -691/360360
-    b = fma(b, w, 8.41750841750841750842e-4);    //  1/1188
-    b = fma(b, w, -5.95238095238095238095e-4);   // -1/1680
-    b = fma(b, w, 7.93650793650793650794e-4);    //  1/1260
-    b = fma(b, w, -2.77777777777777777778e-3);   // -1/360
-    b = fma(b, w, 8.33333333333333333333e-2);    //  1/12
-    double lg = fma(z - 0.5, lz, -z) + kHalfLn2Pi + b * iz;
-    if (den != 1.0) {
-        ps -= num / den;
-        lg -= xlog(den);
+    double a = XPT(kPsi)[0];
+    double b = XPT(kLgam)[0];
+#pragma unroll
+    for (int i = 1; i < 7; ++i) {
+        a = fma(a, w, XPT(kPsi)[i]);
+        b = fma(b, w, XPT(kLgam)[i]);
     }
-    *psi = ps;
-    *lgam = lg;
+    *psi = lz - 0.5 * iz - a * w - sden;
+    *lgam = fma(z - 0.5, lz, -z) + kHalfLn2Pi + b * iz - lden;
+}
+XP_HD void psi_lgamma(double x, double* psi, double* lgam) {
+    double z, num, den;
+    shift_to_10(x, z, num, den);
+    const double q = xdiv(1.0, z * den);
+    psi_lgamma_finish(z, xlog(z), (den != 1.0) ? xlog(den) : 0.0, q * den, num * (q * z), psi, lgam);
 }
 
 XP_HD double xlgamma(double x) {
@@ -221,13 +246,9 @@ XP_HD double betacf(double a, double b, double x) {
 // Stirling correction  sum_k B_2k / (2k(2k-1) z^(2k-1))  for z >= 10.
 XP_HD double stirling_corr(double z) {
     const double iz = 1.0 / z, w = iz * iz;
-    double b = 6.41025641025641025641e-3;
-    b = fma(b, w, -1.91752691752691752692e-3);
-    b = fma(b, w, 8.41750841750841750842e-4);
-    b = fma(b, w, -5.95238095238095238095e-4);
-    b = fma(b, w, 7.93650793650793650794e-4);
-    b = fma(b, w, -2.77777777777777777778e-3);
-    b = fma(b, w, 8.33333333333333333333e-2);
+    double b = XPT(kLgam)[0];
+#pragma unroll
+    for (int i = 1; i < 7; ++i) b = fma(b, w, XPT(kLgam)[i]);
     return b * iz;
 }
 
