@@ -1,0 +1,41 @@
+"""Command line: ``python -m xpore_b200.cli diffmod --config cfg.yml [...]``.
+
+Same sub-command and flags as the reference's ``xpore diffmod`` (``xpore/scripts/xpore.py:40-52``):
+``--config`` (required), ``--n_processes``, ``--save_models``, ``--resume``, ``--ids``.
+``dataprep`` and ``postprocessing`` are outside this repository's scope.
+"""
+import argparse
+import sys
+
+
+def parse_options(argv):
+    parser = argparse.ArgumentParser(prog="xpore", description="xpore_b200 - B200-native xPore diffmod")
+    sub = parser.add_subparsers(dest="cmd")
+    sub.required = True
+    p = sub.add_parser("diffmod", help="run mode for performing differential modification analysis")
+    req = p.add_argument_group("required arguments")
+    req.add_argument("--config", dest="config", help="YAML configuraion filepath.", required=True)
+    p.add_argument("--n_processes", dest="n_processes", type=int, default=1,
+                   help="number of host processes that parse data.json and select positions (the fit runs on the GPU).")
+    p.add_argument("--save_models", dest="save_models", default=False, action="store_true",
+                   help="accepted for compatibility; per-position model dumps are not written (needs h5py).")
+    p.add_argument("--resume", dest="resume", default=False, action="store_true",
+                   help="with this argument, the program will resume from the previous run.")
+    p.add_argument("--ids", dest="ids", default=[], nargs="*", help="gene or transcript ids to model.")
+    p.add_argument("--batch_positions", dest="batch_positions", type=int, default=262144,
+                   help="positions packed per GPU call.")
+    return parser.parse_args(argv[1:])
+
+
+def main(argv=None):
+    argv = sys.argv if argv is None else argv
+    options = parse_options(argv)
+    if options.cmd == "diffmod":
+        from .diffmod import diffmod
+        if options.save_models:
+            print("warning: --save_models is accepted but not implemented in xpore_b200", file=sys.stderr)
+        diffmod(options)
+
+
+if __name__ == "__main__":
+    main(sys.argv)

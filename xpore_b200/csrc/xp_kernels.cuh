@@ -274,6 +274,7 @@ __global__ void xp_worklist_scatter(WorklistArgs a) {
 //   sc[8]             psi(alpha_k), lgamma(alpha_k), ln beta_k, ln lambda_k published by their lanes
 //   goff[G+1] (int)   group offsets inside the position
 //   mbar (u64)        TMA completion barrier
+//   gid[cap+2] (u8)   group slot of every read
 // ------------------------------------------------------------------------------------------
 struct FitArgs {
     const double* y;
@@ -291,45 +292,95 @@ struct FitArgs {
     uint32_t* status;
 };
 
+__host__ __device__ inline size_t fit_scratch_doubles(int G) { return 66 * (size_t)G > 128 ? 66 * (size_t)G : 128; }
 __host__ __device__ inline size_t fit_warp_smem_bytes(int cap, int G) {
-    size_t doubles = (size_t)(cap + 2) + 66 * (size_t)G + 2 * G + 2 * G + G + G + 8;
-    size_t bytes = doubles * 8 + (size_t)((G + 2) & ~1) * 4 + 8;
+    size_t doubles = (size_t)(cap + 2) + fit_scratch_doubles(G) + 2 * G + 2 * G + G + G + 8;
+    size_t bytes = doubles * 8 + (size_t)((G + 2) & ~1) * 4 + 8 + (size_t)(cap + 2);  // + gid bytes
     return (bytes + 15) & ~(size_t)15;
 }
 
-__device__ __forceinline__ int warp_count_le(const double* yv, int n, uint64_t K, int lane) {
-    int c = 0;
-    for (int i = lane; i < n; i += 32) c += (dkey(yv[i]) <= K) ? 1 : 0;
-    return __reduce_add_sync(kFull, c);
-}
-
-// order statistics sorted[r] and sorted[min(r+1, n-1)] by bisection on the key space
-__device__ void warp_select2(const double* yv, int n, int r, uint64_t kmin, uint64_t kmax, int lane, double& a,
-                             double& b) {
-    uint64_t lo = kmin, hi = kmax;
-    while (lo < hi) {
-        const uint64_t mid = lo + ((hi - lo) >> 1);
-        if (warp_count_le(yv, n, mid, lane) >= r + 1) hi = mid;
-        else lo = mid + 1;
+// Order statistics sorted[r] and sorted[min(r+1, n-1)] of the n doubles in shared memory by an
+// MSD radix select over the order-preserving 64-bit keys: 8-bit digits, per-warp 256-bin
+// histogram (shared-memory integer atomics), starting below the common prefix of the smallest
+// and largest key and stopping as soon as one candidate is left.  Exact for any input.
+__device__ void warp_select2(const double* yv, int n, int r, uint64_t kmin, uint64_t kmax, int* hist, int lane,
+                             double& a, double& b) {
+    const uint64_t diff = kmin ^ kmax;
+    int hi = diff ? 64 - __clzll((long long)diff) : 0;  // bits [hi,64) are common to every key
+    uint64_t pre = (hi >= 64) ? 0ull : (kmin >> hi);    // value of the fixed bits
+    int rank = r, cnt = n;
+    while (hi > 0 && cnt > 1) {
+        const int lo = hi > 8 ? hi - 8 : 0;
+        const unsigned mask = (1u << (hi - lo)) - 1u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hist[j * 32 + lane] = 0;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            const uint64_t k = dkey(yv[i]);
+            if (hi >= 64 || (k >> hi) == pre) atomicAdd(&hist[(unsigned)(k >> lo) & mask], 1);
+        }
+        __syncwarp();
+        int h[8], s = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            h[j] = hist[lane * 8 + j];
+            s += h[j];
+        }
+        int incl = s;
+#pragma unroll
+        for (int m = 1; m < 32; m <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, m);
+            if (lane >= m) incl += v;
+        }
+        const unsigned bal = __ballot_sync(kFull, incl > rank);
+        const int L = __ffs(bal) - 1;  // lane whose bins hold the wanted rank
+        int below = incl - s, d = 0, c = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (c == 0) {
+                if (below + h[j] > rank) {
+                    d = j;
+                    c = h[j];
+                } else below += h[j];
+            }
+        }
+        d = __shfl_sync(kFull, lane * 8 + d, L);
+        below = __shfl_sync(kFull, below, L);
+        cnt = __shfl_sync(kFull, c, L);
+        rank -= below;
+        pre = (hi >= 64) ? (uint64_t)d : ((pre << (hi - lo)) | (uint64_t)d);
+        hi = lo;
+        __syncwarp();
     }
-    a = keyd(lo);
+    uint64_t ka;
+    if (hi == 0) ka = pre;
+    else {  // one candidate left: fetch it
+        uint64_t found = 0;
+        for (int i = lane; i < n; i += 32) {
+            const uint64_t k = dkey(yv[i]);
+            if ((k >> hi) == pre) found = k;
+        }
+        ka = warp_max_u64(found);
+    }
+    a = keyd(ka);
     b = a;
-    if (r + 1 < n && warp_count_le(yv, n, lo, lane) < r + 2) {
+    if (r + 1 < n && !(hi == 0 && rank + 1 < cnt)) {
         uint64_t mn = ~0ull;
         for (int i = lane; i < n; i += 32) {
             const uint64_t k = dkey(yv[i]);
-            if (k > lo && k < mn) mn = k;
+            if (k > ka && k < mn) mn = k;
         }
         b = keyd(warp_min_u64(mn));
     }
 }
 
-__device__ double warp_percentile(const double* yv, int n, double q, uint64_t kmin, uint64_t kmax, int lane) {
+__device__ double warp_percentile(const double* yv, int n, double q, uint64_t kmin, uint64_t kmax, int* hist,
+                                  int lane) {
     int lo, hi;
     double gamma;
     percentile_index(n, q, lo, hi, gamma);
     double a, b;
-    warp_select2(yv, n, lo, kmin, kmax, lane, a, b);
+    warp_select2(yv, n, lo, kmin, kmax, hist, lane, a, b);
     return np_lerp(a, b, gamma);
 }
 
@@ -341,13 +392,14 @@ __global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
     unsigned char* wbase = smem_raw + (size_t)warp * fit_warp_smem_bytes(a.cap, G);
     double* slab = reinterpret_cast<double*>(wbase);
     double* scratch = slab + a.cap + 2;
-    double* Nsm = scratch + 66 * G;
+    double* Nsm = scratch + fit_scratch_doubles(G);
     double* lw = Nsm + 2 * G;
     double* Asm = lw + 2 * G;
     double* psis = Asm + G;
     double* sc = psis + G;
     int* goff = reinterpret_cast<int*>(sc + 8);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(goff + ((G + 2) & ~1));
+    unsigned char* gid = reinterpret_cast<unsigned char*>(mbar + 1);  // group slot of every read
 
     if (lane == 0) {
         mbar_init(mbar, 1);
@@ -398,6 +450,16 @@ __global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
             }
         }
         __syncwarp();
+        {
+            int g = 0, gend = goff[1];
+            for (int i = lane; i < n; i += 32) {
+                while (i >= gend) {
+                    ++g;
+                    gend = goff[g + 1];
+                }
+                gid[i] = (unsigned char)g;
+            }
+        }
         // per-position constants: psi/lgamma of sum_k c_gk, lgamma(a0)   (lane-parallel)
         double kpart = 0.0, lga0 = 0.0;
         for (int s = lane; s <= G; s += 32) {
@@ -432,8 +494,9 @@ __global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
         kmax = warp_max_u64(kmax);
         __syncwarp();
         // ---- initial locations (gmm.py:39-44) -------------------------------------------------
-        const double med = warp_percentile(yv, n, 0.5, kmin, kmax, lane);
-        const double loc1 = warp_percentile(yv, n, (0.0 < med) ? 0.75 : 0.25, kmin, kmax, lane);
+        int* hist = reinterpret_cast<int*>(scratch);  // 256 ints; scratch is idle until the first sweep
+        const double med = warp_percentile(yv, n, 0.5, kmin, kmax, hist, lane);
+        const double loc1 = warp_percentile(yv, n, (0.0 < med) ? 0.75 : 0.25, kmin, kmax, hist, lane);
 
         for (int s = lane; s < 2 * G; s += 32) Nsm[s] = 0.0;
         Comp c0 = mstep(0.0, 0.0, 0.0, a0, b0);
@@ -516,38 +579,71 @@ __global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
             for (int g = lane; g < G; g += 32) Asm[g] = base + (lw[2 * g + 1] - lw[2 * g]);
             for (int s = 0; s < 2 * G; ++s) scratch[s * 33 + lane] = 0.0;
             __syncwarp();
-            // ---- E-step + moments: one pass over the resident reads -------------------------
+            // ---- E-step + moments: one pass over the resident reads, two reads per lane per trip
+            // (two independent exp/log chains in flight; constants fetched once per pair)
             double aN0 = 0, aN1 = 0, hq = 0;
             S10 = S11 = S20 = S21 = 0.0;
             {
-                int g = 0, gend = goff[1];
-                double A = Asm[0];
-                for (int i = lane; i < n; i += 32) {
-                    if (i >= gend) {
-                        scratch[(2 * g) * 33 + lane] = aN0;
-                        scratch[(2 * g + 1) * 33 + lane] = aN1;
+                int gcur = gid[lane < n ? lane : 0];
+                int i = lane;
+                for (; i + 32 < n; i += 64) {
+                    const int g0 = gid[i], g1 = gid[i + 32];
+                    const double ya = yv[i], yb = yv[i + 32];
+                    const double da = fma(ya, fma(C, ya, B), Asm[g0]);
+                    const double db = fma(yb, fma(C, yb, B), Asm[g1]);
+                    double ra0, ra1, ha, rb0, rb1, hb;
+                    estep_read(da, ra0, ra1, ha);
+                    estep_read(db, rb0, rb1, hb);
+                    if (g0 != gcur) {
+                        scratch[(2 * gcur) * 33 + lane] = aN0;
+                        scratch[(2 * gcur + 1) * 33 + lane] = aN1;
                         aN0 = aN1 = 0.0;
-                        do {
-                            ++g;
-                            gend = goff[g + 1];
-                        } while (i >= gend);
-                        A = Asm[g];
+                        gcur = g0;
                     }
-                    const double yy = yv[i];
-                    const double d = fma(yy, fma(C, yy, B), A);
-                    double r0, r1, h;
-                    estep_read(d, r0, r1, h);
-                    const double y2 = yy * yy;
-                    aN0 += r0;
-                    aN1 += r1;
-                    S10 = fma(r0, yy, S10);
-                    S11 = fma(r1, yy, S11);
-                    S20 = fma(r0, y2, S20);
-                    S21 = fma(r1, y2, S21);
-                    hq += h;
+                    aN0 += ra0;
+                    aN1 += ra1;
+                    if (g1 != gcur) {
+                        scratch[(2 * gcur) * 33 + lane] = aN0;
+                        scratch[(2 * gcur + 1) * 33 + lane] = aN1;
+                        aN0 = aN1 = 0.0;
+                        gcur = g1;
+                    }
+                    aN0 += rb0;
+                    aN1 += rb1;
+                    const double ya2 = ya * ya, yb2 = yb * yb;
+                    S10 = fma(ra0, ya, S10);
+                    S11 = fma(ra1, ya, S11);
+                    S20 = fma(ra0, ya2, S20);
+                    S21 = fma(ra1, ya2, S21);
+                    S10 = fma(rb0, yb, S10);
+                    S11 = fma(rb1, yb, S11);
+                    S20 = fma(rb0, yb2, S20);
+                    S21 = fma(rb1, yb2, S21);
+                    hq += ha + hb;
                 }
-                scratch[(2 * g) * 33 + lane] = aN0;
-                scratch[(2 * g + 1) * 33 + lane] = aN1;
+                if (i < n) {
+                    const int g0 = gid[i];
+                    const double ya = yv[i];
+                    const double da = fma(ya, fma(C, ya, B), Asm[g0]);
+                    double ra0, ra1, ha;
+                    estep_read(da, ra0, ra1, ha);
+                    if (g0 != gcur) {
+                        scratch[(2 * gcur) * 33 + lane] = aN0;
+                        scratch[(2 * gcur + 1) * 33 + lane] = aN1;
+                        aN0 = aN1 = 0.0;
+                        gcur = g0;
+                    }
+                    aN0 += ra0;
+                    aN1 += ra1;
+                    const double ya2 = ya * ya;
+                    S10 = fma(ra0, ya, S10);
+                    S11 = fma(ra1, ya, S11);
+                    S20 = fma(ra0, ya2, S20);
+                    S21 = fma(ra1, ya2, S21);
+                    hq += ha;
+                }
+                scratch[(2 * gcur) * 33 + lane] = aN0;
+                scratch[(2 * gcur + 1) * 33 + lane] = aN1;
             }
             __syncwarp();
             S10 = warp_sum(S10);

@@ -1,0 +1,245 @@
+"""``xpore diffmod`` driver: data.json/data.index -> CSR batches -> GPU -> diffmod.table.
+
+Mirrors ``xpore/scripts/diffmod.py:79-189`` (``diffmod(args)``) at the file level — same YAML,
+same inputs, same ``diffmod.table`` / ``diffmod.log`` (header row, ``--- DIFFMOD ---``, one id per
+line, ``--- SUCCESSFULLY FINISHED ---``), same ``--resume`` / ``--ids`` semantics — but replaces
+the process pool of per-gene workers (``helper.py:96-116``) with "pack many genes -> one C-ABI
+call -> single writer".  ``--n_processes`` sizes the pool that parses JSON and applies the
+position selection on the host; the fit itself always runs on the GPU(s).
+
+Multi-GPU: launch with ``torchrun``; ids are split into contiguous ranges balanced by their
+``data.index`` byte spans, every rank fits its range, the fixed-width records of fitted
+positions are gathered on rank 0 (NCCL ``gather``), which writes the table.
+"""
+from __future__ import annotations
+
+import csv
+import json
+import os
+from collections import OrderedDict
+
+import numpy as np
+
+from .batch import Batch, BatchBuilder, Layout
+from .config import Configurator
+from .kmer_model import KmerModel
+from .table import get_result_table_header, result_rows, write_rows
+
+
+def decor_message(text):  # helper.py:44-49
+    return "--- " + text.upper() + " ---\n"
+
+
+def read_index(dirpath):
+    """``data.index`` -> {idx: (start, end)} (diffmod.py:132-133)."""
+    out = OrderedDict()
+    with open(os.path.join(dirpath, "data.index")) as f:
+        header = next(f, None)
+        assert header is not None and header.strip().split(",")[:3] == ["idx", "start", "end"], header
+        for line in f:
+            line = line.rstrip("\n")
+            if not line:
+                continue
+            idx, s, e = line.rsplit(",", 2)
+            out[idx] = (int(s), int(e))
+    return out
+
+
+def get_ids(f_index, data_info):
+    """ids present in at least two conditions (union over a condition's runs), sorted
+    (``helper.get_ids``, helper.py:56-67)."""
+    count = {}
+    for cond, runs in data_info.items():
+        ids = set()
+        for run in runs:
+            ids.update(f_index[run].keys())
+        for i in ids:
+            count[i] = count.get(i, 0) + 1
+    return sorted(i for i, c in count.items() if c >= 2)
+
+
+class GeneReader:
+    """Seek + parse one gene from every run (diffmod.py:156-169)."""
+
+    def __init__(self, data_info, f_index):
+        self.data_info = data_info
+        self.f_index = f_index
+        self.handles = {}
+        for cond, runs in data_info.items():
+            for run, d in runs.items():
+                self.handles[run] = open(os.path.join(d, "data.json"), "r")
+
+    def read(self, idx):
+        dd = OrderedDict()
+        for cond, runs in self.data_info.items():
+            for run in runs:
+                span = self.f_index[run].get(idx)
+                if span is None:
+                    dd[(cond, run)] = None
+                else:
+                    fh = self.handles[run]
+                    fh.seek(span[0], 0)
+                    dd[(cond, run)] = json.loads(fh.read(span[1] - span[0]))
+        return dd
+
+    def close(self):
+        for fh in self.handles.values():
+            fh.close()
+
+
+# ---- host ingest workers (--n_processes) ----------------------------------------------------
+_W = {}
+
+
+def _worker_init(data_info, f_index, pooling, lo, hi, kmer_path):
+    _W["reader"] = GeneReader(data_info, f_index)
+    _W["layout"] = Layout.from_data_info(data_info, pooling)
+    _W["km"] = KmerModel.load(kmer_path)
+    _W["crit"] = (lo, hi)
+
+
+def _worker_pack(idx):
+    bb = BatchBuilder(_W["layout"], _W["km"], *_W["crit"])
+    bb.add_gene(idx, _W["reader"].read(idx))
+    b = bb.build()
+    return idx, b.y, b.grp_len, b.kmer_mean, b.kmer_std, b.positions, b.kmers
+
+
+def _concat(layout, parts) -> Batch:
+    ys, gl, km, ks, ids, pos, kmers = [], [], [], [], [], [], []
+    for idx, y, g, m, s, p, k in parts:
+        ys.append(y)
+        gl.append(g)
+        km.append(m)
+        ks.append(s)
+        ids += [idx] * len(p)
+        pos += p
+        kmers += k
+    G = layout.n_groups
+    grp_len = np.concatenate(gl) if gl else np.zeros((0, G), np.int32)
+    read_off = np.zeros(len(grp_len) + 1, np.int64)
+    np.cumsum(grp_len.sum(axis=1, dtype=np.int64), out=read_off[1:])
+    return Batch(layout, np.concatenate(ys) if ys else np.zeros(0), read_off, grp_len.astype(np.int32),
+                 np.concatenate(km) if km else np.zeros(0), np.concatenate(ks) if ks else np.zeros(0), ids, pos, kmers)
+
+
+def diffmod(args, fit_fn=None):
+    """Run the diffmod step.  ``fit_fn(batch, method) -> FitResult`` defaults to the CUDA path
+    (there is no CPU implementation in this package; tests inject their checker here)."""
+    from .fit import Method
+
+    config = Configurator(args.config)
+    paths = config.get_paths()
+    data_info = config.get_data_info()
+    method = config.get_method()
+    criteria = config.get_criteria()
+    km = KmerModel.load(paths["model_kmer"])
+    print("Using the signal of unmodified RNA from", km.path)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if fit_fn is None:
+        from .fit import fit_batch
+        fit_fn = lambda b, m: fit_batch(b, m, device=local_rank)  # noqa: E731
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+            if backend == "nccl":
+                torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend)
+
+    out_table = os.path.join(paths["out_dir"], "diffmod.table")
+    out_log = os.path.join(paths["out_dir"], "diffmod.log")
+    layout = Layout.from_data_info(data_info, method["pooling"])
+    m = Method.from_dict(method)
+    pm = m.prefilter_method
+
+    ids_done = []
+    if args.resume and os.path.exists(out_log):
+        ids_done = [line.rstrip("\n") for line in open(out_log, "r")]
+    elif rank == 0:
+        with open(out_table, "w", newline="") as f:
+            csv.writer(f, delimiter=",").writerow(get_result_table_header(layout, pm))
+        with open(out_log, "w") as f:
+            f.write(decor_message("diffmod"))
+
+    f_index = OrderedDict()
+    for cond, runs in data_info.items():
+        for run, d in runs.items():
+            f_index[run] = read_index(d)
+    ids = list(args.ids) if len(args.ids) else get_ids(f_index, data_info)
+    print(len(ids), "ids to be testing ...")
+    done = set(ids_done)
+    todo = [i for i in ids if not (args.resume and i in done)]
+
+    if world > 1:
+        from .dist import balanced_partition
+        cost = np.array([sum(f_index[r][i][1] - f_index[r][i][0] for r in f_index if i in f_index[r]) for i in todo],
+                        dtype=np.float64)
+        mine = [todo[j] for j in balanced_partition(cost, world)[rank]]
+    else:
+        mine = todo
+
+    n_proc = max(1, int(args.n_processes))
+    pool = None
+    lo, hi = criteria["readcount_min"], criteria["readcount_max"]
+    if n_proc > 1 and len(mine) > 1:
+        import multiprocessing as mp
+        pool = mp.get_context("fork").Pool(n_proc, initializer=_worker_init,
+                                           initargs=(data_info, f_index, method["pooling"], lo, hi, paths["model_kmer"]))
+        parts_iter = pool.imap(_worker_pack, mine, chunksize=4)
+    else:
+        _worker_init(data_info, f_index, method["pooling"], lo, hi, paths["model_kmer"])
+        parts_iter = map(_worker_pack, mine)
+
+    max_positions = int(getattr(args, "batch_positions", 0) or 262144)
+    gene_rows = []  # (idx, rows) of this rank, in id order
+
+    def flush(parts):
+        if not parts:
+            return
+        batch = _concat(layout, parts)
+        res = fit_fn(batch, m) if batch.n_positions else None
+        rows = result_rows(batch, res, pm) if res is not None else []
+        by_gene = OrderedDict((p[0], []) for p in parts)
+        for r in rows:
+            by_gene[r[0]].append(r)
+        if world == 1:
+            for idx, rws in by_gene.items():  # rows first, then the id (keeps --resume valid)
+                if rws:
+                    write_rows(out_table, rws)
+                with open(out_log, "a") as f:
+                    f.write(idx + "\n")
+        else:
+            gene_rows.extend(by_gene.items())
+
+    parts, n_pos = [], 0
+    for part in parts_iter:
+        parts.append(part)
+        n_pos += len(part[5])
+        if n_pos >= max_positions:
+            flush(parts)
+            parts, n_pos = [], 0
+    flush(parts)
+    if pool is not None:
+        pool.close()
+        pool.join()
+
+    if world > 1:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(gene_rows, gathered, dst=0)
+        if rank == 0:
+            for per_rank in gathered:
+                for idx, rws in per_rank:
+                    if rws:
+                        write_rows(out_table, rws)
+                    with open(out_log, "a") as f:
+                        f.write(idx + "\n")
+        dist.barrier()
+    if rank == 0:
+        with open(out_log, "a+") as f:
+            f.write(decor_message("successfully finished"))
