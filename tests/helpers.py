@@ -187,3 +187,110 @@ def _knife_edge_alternatives(hdr, row, lay):
         alt["pval_" + tag] = [t[1] for t in tr]
         alt["z_score_" + tag] = [t[2] for t in tr]
     return alt
+
+
+# ---------------------------------------------------------------------------------------------
+# host emulator of the kernel arithmetic (tests/emul/xp_emul.cpp) - checker only
+# ---------------------------------------------------------------------------------------------
+_EMUL = None
+
+
+def load_emulator():
+    import ctypes as C
+    import subprocess
+    global _EMUL
+    if _EMUL is not None:
+        return _EMUL
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = os.path.join(here, "emul", "xp_emul.cpp")
+    so = os.path.join(here, "emul", "libxp_emul.so")
+    deps = [src] + [os.path.join(here, "..", "xpore_b200", "csrc", f) for f in ("xp_math.cuh", "xp_core.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++",
+                               src, "-o", so])
+    L = C.CDLL(so)
+    L.emul_prefilter.restype = C.c_double
+    L.emul_prefilter.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double]
+    L.emul_fit.restype = None
+    L.emul_fit.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double,
+                           C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.emul_stats.restype = C.c_uint
+    L.emul_stats.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double,
+                             C.c_void_p, C.c_void_p]
+    L.emul_special.restype = None
+    L.emul_special.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]
+    _EMUL = L
+    return L
+
+
+def emul_fit_batch(L, batch, method):
+    """Run the emulator position by position and fill the same records the C ABI returns."""
+    import ctypes as C
+
+    import numpy as np
+
+    from xpore_b200 import fit as xf
+    P, G, Cn = batch.n_positions, batch.layout.n_groups, batch.layout.n_conditions
+    res = xf.FitResult(G, Cn, np.zeros(P, np.uint32), np.zeros(P, np.int32), np.full(P, np.nan),
+                       np.full((P, xf.fit_width(G)), np.nan), np.full((P, xf.stats_width(G, Cn)), np.nan), 0)
+    gc = np.ascontiguousarray(batch.layout.grp_cond, dtype=np.int32)
+    for p in range(P):
+        y = np.ascontiguousarray(batch.y[batch.read_off[p]:batch.read_off[p + 1]])
+        gl = np.ascontiguousarray(batch.grp_len[p])
+        sel = True
+        if method.prefilter_method is not None:
+            pv = np.nan
+            if method.prefilter_method == "t-test":
+                pv = L.emul_prefilter(len(y), y.ctypes.data, G, gl.ctypes.data, gc.ctypes.data, batch.kmer_mean[p])
+            res.pval[p] = pv
+            sel = bool(np.isnan(pv) or pv < method.prefilter_threshold)
+        if not sel:
+            continue
+        nit, st = C.c_int(0), C.c_uint(0)
+        L.emul_fit(len(y), y.ctypes.data, G, gl.ctypes.data, batch.kmer_mean[p], batch.kmer_std[p],
+                   method.max_iters, method.stopping_criteria, method.dirichlet_conc, res.fit[p].ctypes.data,
+                   C.byref(nit), C.byref(st), None)
+        fl = L.emul_stats(G, Cn, gc.ctypes.data, gl.ctypes.data, method.dirichlet_conc, batch.kmer_mean[p],
+                          batch.kmer_std[p], res.fit[p].ctypes.data, res.stats[p].ctypes.data)
+        res.n_iter[p] = nit.value
+        res.status[p] = st.value | fl
+        res.n_fitted += 1
+    return res
+
+
+def read_table(path):
+    """diffmod.table -> (header, {key: row}) with numeric cells parsed ('' -> None)."""
+    import csv
+    with open(path, newline="") as f:
+        rd = list(csv.reader(f))
+    header = rd[0]
+    rows = {}
+    for r in rd[1:]:
+        vals = list(r[:3])
+        for name, v in zip(header[3:], r[3:]):
+            if name == "mod_assignment":
+                vals.append(v)
+            else:
+                vals.append(None if v == "" else float(v))
+        rows[tuple(r[:3])] = vals
+    return header, rows
+
+
+def compare_tables(got_rows, exp_rows, header, layout, prefilter_method, rtol_param=1e-5, rtol_p=1e-4):
+    import numpy as np
+    assert set(got_rows) == set(exp_rows)
+    for k, r in got_rows.items():
+        e = exp_rows[k]
+        alt = _knife_edge_alternatives(header, e, layout)
+        for name, a, b in zip(header[3:], r[3:], e[3:]):
+            if b is None or isinstance(b, str) and name == "mod_assignment":
+                assert a == b, (k, name, a, b)
+                continue
+            b = _num(b)
+            if np.isnan(b):
+                assert np.isnan(a), (k, name)
+                continue
+            tol = rtol_p if (name.startswith("pval") or name == prefilter_method) else rtol_param
+            if np.isclose(a, b, rtol=tol, atol=1e-300):
+                continue
+            assert any(np.isclose(a, c, rtol=tol, atol=1e-300) for c in alt.get(name, [])), (k, name, a, b)

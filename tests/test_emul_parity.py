@@ -1,9 +1,5 @@
 """CPU checks of the kernels' arithmetic through the host emulator (tests/emul/xp_emul.cpp links
 the same xp_math.cuh / xp_core.cuh as the CUDA kernels)."""
-import ctypes as C
-import os
-import subprocess
-
 import numpy as np
 import pytest
 import scipy.special
@@ -12,30 +8,12 @@ import scipy.stats
 from xpore_b200 import fit as xf
 
 from helpers import compare_with_golden, pack_case
-
-HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "emul", "xp_emul.cpp")
-SO = os.path.join(HERE, "emul", "libxp_emul.so")
+from helpers import emul_fit_batch, load_emulator
 
 
 @pytest.fixture(scope="session")
 def emul():
-    deps = [SRC] + [os.path.join(HERE, "..", "xpore_b200", "csrc", f) for f in ("xp_math.cuh", "xp_core.cuh")]
-    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++",
-                               SRC, "-o", SO])
-    L = C.CDLL(SO)
-    L.emul_prefilter.restype = C.c_double
-    L.emul_prefilter.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double]
-    L.emul_fit.restype = None
-    L.emul_fit.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double,
-                           C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    L.emul_stats.restype = C.c_uint
-    L.emul_stats.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double,
-                             C.c_void_p, C.c_void_p]
-    L.emul_special.restype = None
-    L.emul_special.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]
-    return L
+    return load_emulator()
 
 
 def special(L, which, x, aux=None):
@@ -44,36 +22,6 @@ def special(L, which, x, aux=None):
     out = np.empty_like(x)
     L.emul_special(which, x.ctypes.data, aux.ctypes.data, out.ctypes.data, len(x))
     return out
-
-
-def emul_fit_batch(L, batch, method: xf.Method) -> xf.FitResult:
-    """Run the emulator position by position and fill the same records the C ABI returns."""
-    P, G, Cn = batch.n_positions, batch.layout.n_groups, batch.layout.n_conditions
-    res = xf.FitResult(G, Cn, np.zeros(P, np.uint32), np.zeros(P, np.int32), np.full(P, np.nan),
-                       np.full((P, xf.fit_width(G)), np.nan), np.full((P, xf.stats_width(G, Cn)), np.nan), 0)
-    gc = np.ascontiguousarray(batch.layout.grp_cond, dtype=np.int32)
-    for p in range(P):
-        y = np.ascontiguousarray(batch.y[batch.read_off[p]:batch.read_off[p + 1]])
-        gl = np.ascontiguousarray(batch.grp_len[p])
-        sel = True
-        if method.prefilter_method is not None:
-            pv = np.nan
-            if method.prefilter_method == "t-test":
-                pv = L.emul_prefilter(len(y), y.ctypes.data, G, gl.ctypes.data, gc.ctypes.data, batch.kmer_mean[p])
-            res.pval[p] = pv
-            sel = bool(np.isnan(pv) or pv < method.prefilter_threshold)
-        if not sel:
-            continue
-        nit, st = C.c_int(0), C.c_uint(0)
-        L.emul_fit(len(y), y.ctypes.data, G, gl.ctypes.data, batch.kmer_mean[p], batch.kmer_std[p],
-                   method.max_iters, method.stopping_criteria, method.dirichlet_conc, res.fit[p].ctypes.data,
-                   C.byref(nit), C.byref(st), None)
-        fl = L.emul_stats(G, Cn, gc.ctypes.data, gl.ctypes.data, method.dirichlet_conc, batch.kmer_mean[p],
-                          batch.kmer_std[p], res.fit[p].ctypes.data, res.stats[p].ctypes.data)
-        res.n_iter[p] = nit.value
-        res.status[p] = st.value | fl
-        res.n_fitted += 1
-    return res
 
 
 def test_special_functions(emul):
