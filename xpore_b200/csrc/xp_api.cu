@@ -244,15 +244,22 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
 }
 
 // ---- host-buffer entry point --------------------------------------------------------------
+// The batch is cut into chunks of positions (~kChunkBytes of reads each).  Chunk c's reads go up
+// on the copy-in stream while chunk c-1 is being fitted on the compute stream and chunk c-2's
+// records come back on the copy-out stream, so PCIe (full duplex) and the SMs work concurrently.
 namespace {
+constexpr int kMaxChunks = 64;
+constexpr size_t kChunkBytes = 192u << 20;
+
 struct DevCache {
     int device = -1;
-    cudaStream_t stream = nullptr;
+    cudaStream_t s_in = nullptr, s_c = nullptr, s_out = nullptr;
+    cudaEvent_t e_in[kMaxChunks], e_done[kMaxChunks];
     void* buf = nullptr;
     size_t cap = 0;
 };
 std::mutex g_cache_mu;
-std::vector<DevCache> g_cache;
+std::vector<DevCache*> g_cache;
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 }  // namespace
@@ -265,17 +272,37 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
     CK(cudaSetDevice(device));
     std::lock_guard<std::mutex> lk(g_cache_mu);
     DevCache* dc = nullptr;
-    for (auto& c : g_cache)
-        if (c.device == device) dc = &c;
+    for (auto* c : g_cache)
+        if (c->device == device) dc = c;
     if (!dc) {
-        g_cache.push_back(DevCache());
-        dc = &g_cache.back();
+        dc = new DevCache();
         dc->device = device;
-        CK(cudaStreamCreateWithFlags(&dc->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&dc->s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&dc->s_c, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&dc->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < kMaxChunks; ++i) {
+            CK(cudaEventCreateWithFlags(&dc->e_in[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&dc->e_done[i], cudaEventDisableTiming));
+        }
+        g_cache.push_back(dc);
     }
     const int P = b->n_positions, G = b->n_groups, C = b->n_conditions;
+    if (n_fitted) *n_fitted = 0;
+    if (P == 0) return 0;
     const size_t R2 = (size_t)((b->n_reads + 1) & ~(int64_t)1);
     const int FW = xpc::fit_width(G), SW = xpc::stats_width(G, C);
+
+    // chunk boundaries (positions), cut where the read offsets cross multiples of the chunk size
+    const int64_t* roff = b->read_off;
+    int nchunks = (int)std::min<size_t>(kMaxChunks, std::max<size_t>(1, ((size_t)b->n_reads * 8 + kChunkBytes - 1) / kChunkBytes));
+    std::vector<int> cut(nchunks + 1, 0);
+    cut[nchunks] = P;
+    for (int c = 1; c < nchunks; ++c) {
+        const int64_t target = (int64_t)((double)b->n_reads * c / nchunks);
+        cut[c] = (int)(std::lower_bound(roff, roff + P + 1, target) - roff);
+        cut[c] = std::min(std::max(cut[c], cut[c - 1]), P);
+    }
+
     // device layout
     size_t o = 0;
     const size_t o_y = o; o += align_up(R2 * 8);
@@ -289,8 +316,12 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
     const size_t o_pval = o; o += align_up((size_t)P * 8);
     const size_t o_fit = o; o += align_up((size_t)P * FW * 8);
     const size_t o_stats = o; o += align_up((size_t)P * SW * 8);
-    const size_t o_nf = o; o += 256;
-    const size_t o_ws = o; o += align_up(xpb200_workspace_bytes(P));
+    const size_t o_nf = o; o += align_up((size_t)kMaxChunks * 4);
+    std::vector<size_t> o_ws(nchunks);
+    for (int c = 0; c < nchunks; ++c) {
+        o_ws[c] = o;
+        o += align_up(xpb200_workspace_bytes(cut[c + 1] - cut[c]));
+    }
     if (o > dc->cap) {
         if (dc->buf) CK(cudaFree(dc->buf));
         dc->buf = nullptr;
@@ -303,49 +334,78 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
         dc->cap = want;
     }
     char* d = reinterpret_cast<char*>(dc->buf);
-    cudaStream_t st = dc->stream;
-    if (P > 0) {
-        CK(cudaMemcpyAsync(d + o_y, b->y, (size_t)b->n_reads * 8, cudaMemcpyDefault, st));
-        CK(cudaMemcpyAsync(d + o_off, b->read_off, (size_t)(P + 1) * 8, cudaMemcpyDefault, st));
-        CK(cudaMemcpyAsync(d + o_glen, b->grp_len, (size_t)P * G * 4, cudaMemcpyDefault, st));
-        CK(cudaMemcpyAsync(d + o_km, b->kmer_mean, (size_t)P * 8, cudaMemcpyDefault, st));
-        CK(cudaMemcpyAsync(d + o_ks, b->kmer_std, (size_t)P * 8, cudaMemcpyDefault, st));
+    double* d_y = (double*)(d + o_y);
+    int64_t* d_off = (int64_t*)(d + o_off);
+    int32_t* d_glen = (int32_t*)(d + o_glen);
+    double* d_km = (double*)(d + o_km);
+    double* d_ks = (double*)(d + o_ks);
+    uint32_t* d_status = (uint32_t*)(d + o_status);
+    int32_t* d_niter = (int32_t*)(d + o_niter);
+    double* d_pval = (double*)(d + o_pval);
+    double* d_fit = (double*)(d + o_fit);
+    double* d_stats = (double*)(d + o_stats);
+    uint32_t* d_nf = (uint32_t*)(d + o_nf);
+
+    CK(cudaMemcpyAsync(d + o_gc, b->grp_cond, (size_t)G * 4, cudaMemcpyDefault, dc->s_in));
+    CK(cudaMemsetAsync(d_nf, 0, (size_t)kMaxChunks * 4, dc->s_in));
+    for (int c = 0; c < nchunks; ++c) {
+        const int p0 = cut[c], p1 = cut[c + 1], pc = p1 - p0;
+        if (pc == 0) continue;
+        const int64_t r0 = roff[p0], r1 = roff[p1];
+        // copy-in
+        CK(cudaMemcpyAsync(d_y + r0, b->y + r0, (size_t)(r1 - r0) * 8, cudaMemcpyDefault, dc->s_in));
+        CK(cudaMemcpyAsync(d_off + p0, roff + p0, (size_t)(pc + 1) * 8, cudaMemcpyDefault, dc->s_in));
+        CK(cudaMemcpyAsync(d_glen + (size_t)p0 * G, b->grp_len + (size_t)p0 * G, (size_t)pc * G * 4, cudaMemcpyDefault, dc->s_in));
+        CK(cudaMemcpyAsync(d_km + p0, b->kmer_mean + p0, (size_t)pc * 8, cudaMemcpyDefault, dc->s_in));
+        CK(cudaMemcpyAsync(d_ks + p0, b->kmer_std + p0, (size_t)pc * 8, cudaMemcpyDefault, dc->s_in));
+        CK(cudaEventRecord(dc->e_in[c], dc->s_in));
+        // compute
+        CK(cudaStreamWaitEvent(dc->s_c, dc->e_in[c], 0));
+        xpb200_batch db = *b;
+        db.n_positions = pc;
+        db.n_reads = r1 - r0;
+        db.y = d_y; db.read_off = d_off + p0; db.grp_len = d_glen + (size_t)p0 * G;
+        db.kmer_mean = d_km + p0; db.kmer_std = d_ks + p0; db.grp_cond = (const int32_t*)(d + o_gc);
+        xpb200_result dr;
+        dr.status = d_status + p0; dr.n_iter = d_niter + p0; dr.pval = d_pval + p0;
+        dr.fit = d_fit + (size_t)p0 * FW; dr.stats = d_stats + (size_t)p0 * SW;
+        CK(cudaMemsetAsync(dr.n_iter, 0, (size_t)pc * 4, dc->s_c));
+        CK(cudaMemsetAsync(dr.fit, 0xFF, (size_t)pc * FW * 8, dc->s_c));
+        CK(cudaMemsetAsync(dr.stats, 0xFF, (size_t)pc * SW * 8, dc->s_c));
+        if (int rc = xpb200_fit_device(&db, m, &dr, d + o_ws[c], xpb200_workspace_bytes(pc), d_nf + c, dc->s_c))
+            return rc;
+        CK(cudaEventRecord(dc->e_done[c], dc->s_c));
+        // copy-out
+        CK(cudaStreamWaitEvent(dc->s_out, dc->e_done[c], 0));
+        CK(cudaMemcpyAsync(r->status + p0, dr.status, (size_t)pc * 4, cudaMemcpyDefault, dc->s_out));
+        CK(cudaMemcpyAsync(r->n_iter + p0, dr.n_iter, (size_t)pc * 4, cudaMemcpyDefault, dc->s_out));
+        CK(cudaMemcpyAsync(r->pval + p0, dr.pval, (size_t)pc * 8, cudaMemcpyDefault, dc->s_out));
+        CK(cudaMemcpyAsync(r->fit + (size_t)p0 * FW, dr.fit, (size_t)pc * FW * 8, cudaMemcpyDefault, dc->s_out));
+        CK(cudaMemcpyAsync(r->stats + (size_t)p0 * SW, dr.stats, (size_t)pc * SW * 8, cudaMemcpyDefault, dc->s_out));
     }
-    CK(cudaMemcpyAsync(d + o_gc, b->grp_cond, (size_t)G * 4, cudaMemcpyDefault, st));
-    xpb200_batch db = *b;
-    db.y = (const double*)(d + o_y); db.read_off = (const int64_t*)(d + o_off);
-    db.grp_len = (const int32_t*)(d + o_glen); db.kmer_mean = (const double*)(d + o_km);
-    db.kmer_std = (const double*)(d + o_ks); db.grp_cond = (const int32_t*)(d + o_gc);
-    xpb200_result dr;
-    dr.status = (uint32_t*)(d + o_status); dr.n_iter = (int32_t*)(d + o_niter); dr.pval = (double*)(d + o_pval);
-    dr.fit = (double*)(d + o_fit); dr.stats = (double*)(d + o_stats);
-    if (P > 0) {
-        CK(cudaMemsetAsync(dr.n_iter, 0, (size_t)P * 4, st));
-        CK(cudaMemsetAsync(dr.fit, 0xFF, (size_t)P * FW * 8, st));
-        CK(cudaMemsetAsync(dr.stats, 0xFF, (size_t)P * SW * 8, st));
-    }
-    if (int rc = xpb200_fit_device(&db, m, &dr, d + o_ws, xpb200_workspace_bytes(P), (uint32_t*)(d + o_nf), st))
-        return rc;
-    if (P > 0) {
-        CK(cudaMemcpyAsync(r->status, dr.status, (size_t)P * 4, cudaMemcpyDefault, st));
-        CK(cudaMemcpyAsync(r->n_iter, dr.n_iter, (size_t)P * 4, cudaMemcpyDefault, st));
-        CK(cudaMemcpyAsync(r->pval, dr.pval, (size_t)P * 8, cudaMemcpyDefault, st));
-        CK(cudaMemcpyAsync(r->fit, dr.fit, (size_t)P * FW * 8, cudaMemcpyDefault, st));
-        CK(cudaMemcpyAsync(r->stats, dr.stats, (size_t)P * SW * 8, cudaMemcpyDefault, st));
-    }
-    uint32_t nf = 0;
-    CK(cudaMemcpyAsync(&nf, d + o_nf, 4, cudaMemcpyDefault, st));
-    CK(cudaStreamSynchronize(st));
-    if (n_fitted) *n_fitted = nf;
+    uint32_t nf[kMaxChunks];
+    CK(cudaMemcpyAsync(nf, d_nf, sizeof(nf), cudaMemcpyDefault, dc->s_out));
+    CK(cudaStreamSynchronize(dc->s_out));
+    CK(cudaStreamSynchronize(dc->s_c));
+    CK(cudaStreamSynchronize(dc->s_in));
+    uint32_t total = 0;
+    for (int c = 0; c < nchunks; ++c) total += nf[c];
+    if (n_fitted) *n_fitted = total;
     return 0;
 }
 
 void xpb200_release(void) {
     std::lock_guard<std::mutex> lk(g_cache_mu);
-    for (auto& c : g_cache) {
-        cudaSetDevice(c.device);
-        if (c.buf) cudaFree(c.buf);
-        if (c.stream) cudaStreamDestroy(c.stream);
+    for (auto* c : g_cache) {
+        cudaSetDevice(c->device);
+        if (c->buf) cudaFree(c->buf);
+        for (cudaStream_t st : {c->s_in, c->s_c, c->s_out})
+            if (st) cudaStreamDestroy(st);
+        for (int i = 0; i < kMaxChunks; ++i) {
+            cudaEventDestroy(c->e_in[i]);
+            cudaEventDestroy(c->e_done[i]);
+        }
+        delete c;
     }
     g_cache.clear();
 }
