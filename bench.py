@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--positions", type=int, default=None, help="positions per GPU (default: the config's)")
     ap.add_argument("--cpu-positions", type=int, default=None, help="positions in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--y-format", default="auto", choices=["auto", "f64"],
+                    help="auto: ship reads as scaled u16/i32 when that is bit-exact (2-decimal dataprep output)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -235,6 +237,7 @@ def main():
 
     batch = make_batch_device(spec, dev, km, n_positions=P, seed_offset=rank)
     method = xf.Method.from_dict(spec.method)
+    yfmt = batch.encode_reads() if args.y_format == "auto" else 0
     db = xf.DeviceBatch(batch, device=dev, pin=True)
     out = xf.DeviceResult(db.P, db.G, db.C, dev)
     torch.cuda.synchronize()
@@ -316,7 +319,7 @@ def main():
     hb = db.host
     cb = _lib.XpBatch(db.P, db.G, db.C, db.max_reads, db.R, hb["y"].data_ptr(), hb["read_off"].data_ptr(),
                       hb["grp_len"].data_ptr(), hb["kmer_mean"].data_ptr(), hb["kmer_std"].data_ptr(),
-                      hb["grp_cond"].data_ptr())
+                      hb["grp_cond"].data_ptr(), db.y_format, 0, db.y_scale)
     cm = method.c_struct()
     # N = 1: results land in pinned host memory.  N > 1: results stay on the device of each rank,
     # fitted records are gathered to rank 0 over NCCL and copied to its host there.
@@ -361,7 +364,8 @@ def main():
         G = db.G
         flops = read_iters * FLOP_PER_READ_ITER + pos_iters * (6 * G + 4) * FLOP_PER_SPECIAL
         achieved = flops / (fit_ms * 1e-3) / 1e12
-        alg_bytes = sel_reads * 8 + n_fitted * (8 + 4 * G + 16 + 4) + n_fitted * (fit_w * 8 + 8)
+        ybytes = {0: 8, 1: 4, 2: 2}[yfmt]
+        alg_bytes = sel_reads * ybytes + n_fitted * (8 + 4 * G + 16 + 4) + n_fitted * (fit_w * 8 + 8)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
@@ -378,8 +382,9 @@ def main():
                        "positions_fitted_per_gpu": n_fitted, "groups": db.G, "conditions": db.C,
                        "max_iters": method.max_iters, "prefilter": method.prefilter_method,
                        "pooling": method.pooling, "parallelism": "positions sharded, dp%d" % world,
+                       "y_format": {0: "f64", 1: "i32 scaled by 100", 2: "u16 scaled by 100"}[yfmt],
                        "l2": "inputs (%.2f GB per GPU) larger than the 126 MB L2; no explicit flush"
-                             % (db.R * 8 / 1e9),
+                             % (db.h2d_bytes / 1e9),
                        "sweeps_mean": float(it_sel.mean().item()) if n_fitted else 0.0,
                        "sweeps_max": int(it_sel.max().item()) if n_fitted else 0,
                        "positions_tested_per_s": tested_all / (ms_per_step * 1e-3),
@@ -400,8 +405,8 @@ def main():
                                  "frac": alg_bytes / (fit_ms * 1e-3) / 1e9 / hbm_peak}},
             "stages_ms": {"prefilter": float(np.median(stage_ms[:, 0])), "worklist": float(np.median(stage_ms[:, 1])),
                           "fit": fit_ms, "stats": float(np.median(stage_ms[:, 3]))},
-            "prefilter_hbm": {"bytes": db.R * 8 + db.P * (8 + 4 * G + 8 + 12),
-                              "achieved_gbs": (db.R * 8 + db.P * (8 + 4 * G + 8 + 12))
+            "prefilter_hbm": {"bytes": db.R * ybytes + db.P * (8 + 4 * G + 8 + 12),
+                              "achieved_gbs": (db.R * ybytes + db.P * (8 + 4 * G + 8 + 12))
                               / (float(np.median(stage_ms[:, 0])) * 1e-3) / 1e9 if stage_ms[:, 0].any() else None,
                               "peak_gbs": hbm_peak},
             "launch": {"sm_count": info.sm_count, "ctas_per_sm": info.ctas_per_sm, "warps_per_cta": info.warps_per_cta,

@@ -55,13 +55,24 @@ typedef struct xpb200_batch {
     int32_t n_conditions;     /* C  (1..32) */
     int32_t max_reads;        /* max over positions of reads per position */
     int64_t n_reads;          /* R = read_off[P] */
-    const double* y;          /* [R rounded up to even]  event means (data.json values)      */
+    const void* y;            /* [R + padding]  event means (data.json values), see y_format  */
     const int64_t* read_off;  /* [P+1]                                                       */
     const int32_t* grp_len;   /* [P*G]                                                       */
     const double* kmer_mean;  /* [P] model_kmer.csv model_mean of the position's k-mer       */
     const double* kmer_std;   /* [P] model_kmer.csv model_stdv                               */
     const int32_t* grp_cond;  /* [G] condition index (rank among sorted condition names)     */
+    int32_t y_format;         /* XPB200_Y_F64 | XPB200_Y_I32 | XPB200_Y_U16                   */
+    int32_t reserved;
+    double y_scale;           /* scaled-integer formats: value = (double)q / y_scale, exactly */
 } xpb200_batch;
+
+/* Encodings of `y`.  dataprep rounds event means to 2 decimals (dataprep.py:638; 1 decimal in
+ * gene mode, :133), so a read is q/100 for an integer q: the packer may ship q as u16 or i32
+ * when (double)q / y_scale reproduces every value bit for bit, which quarters / halves the
+ * PCIe and HBM bytes.  The buffer must be padded to a multiple of 16 bytes (2 / 4 / 8 elements). */
+#define XPB200_Y_F64 0
+#define XPB200_Y_I32 1
+#define XPB200_Y_U16 2
 
 /* method section of the YAML (configurator.py:46-60) + the fixed priors (:62-77). */
 typedef struct xpb200_method {

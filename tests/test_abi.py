@@ -42,14 +42,14 @@ def test_record_widths(library):
 
 def test_struct_layouts_match_header():
     # field order/sizes of the ctypes mirrors (x86-64 / LP64)
-    assert C.sizeof(_lib.XpBatch) == 4 * 4 + 8 + 6 * 8
+    assert C.sizeof(_lib.XpBatch) == 4 * 4 + 8 + 6 * 8 + 2 * 4 + 8
     assert C.sizeof(_lib.XpMethod) == 2 * 4 + 3 * 8
     assert C.sizeof(_lib.XpResult) == 5 * 8
     assert C.sizeof(_lib.XpLaunchInfo) == 6 * 4
 
 
 def test_argument_validation_without_gpu(library):
-    b = _lib.XpBatch(0, 0, 2, 0, 0, None, None, None, None, None, None)
+    b = _lib.XpBatch(0, 0, 2, 0, 0, None, None, None, None, None, None, 0, 0, 1.0)
     m = _lib.XpMethod(500, 0, 1e-5, float("nan"), 0.001)
     r = _lib.XpResult(None, None, None, None, None)
     rc = library.xpb200_fit_device(C.byref(b), C.byref(m), C.byref(r), None, 0, None, None)

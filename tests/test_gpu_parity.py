@@ -147,6 +147,32 @@ def test_device_path_vs_oracle(torch_cuda, shape):
     assert same_iters == len(idx)
 
 
+@pytest.mark.parametrize("shift,expect", [(0.0, 2), (-200.0, 1), (1e-9, 0)])
+def test_encoded_reads_bit_identical(torch_cuda, shift, expect):
+    """u16 / i32 scaled-integer read buffers decode to the very same doubles: every record must be
+    bit-identical to the f64 path, through both entry points; non-representable data stays f64."""
+    torch = torch_cuda
+    spec = Spec({"KO": 2, "WT": 3}, reads_lo=10, reads_hi=70, f_mod=0.4, seed=41,
+                method={"prefiltering": {"method": "t-test", "threshold": 0.2}})
+    batch = make_batch(spec, KmerModel.load(), n_positions=700)
+    batch.y[:] = np.round(batch.y + shift, 2) if shift <= 0 else batch.y + shift
+    method = xf.Method.from_dict(spec.method)
+    ref = xf.fit_batch(batch, method)
+    assert batch.encode_reads() == expect
+    enc = xf.fit_batch(batch, method)
+    out = xf.fit_device(xf.DeviceBatch(batch), method)
+    torch.cuda.synchronize()
+    dev = out.to_host()
+    for r in (enc, dev):
+        np.testing.assert_array_equal(r.status, ref.status)
+        np.testing.assert_array_equal(r.n_iter, ref.n_iter)
+        np.testing.assert_array_equal(r.pval, ref.pval)
+        sel = ref.selected
+        np.testing.assert_array_equal(r.fit[sel], ref.fit[sel])
+        np.testing.assert_array_equal(r.stats[sel], ref.stats[sel])
+    assert 50 < ref.n_fitted < 700
+
+
 def test_empty_and_tiny_batches(torch_cuda):
     spec = Spec({"KO": 2, "WT": 2}, reads_lo=15, reads_hi=16, seed=3)
     b0 = make_batch(spec, KmerModel.load(), n_positions=0) if False else None

@@ -22,7 +22,8 @@ class XpBatch(C.Structure):
     _fields_ = [("n_positions", C.c_int32), ("n_groups", C.c_int32), ("n_conditions", C.c_int32),
                 ("max_reads", C.c_int32), ("n_reads", C.c_int64), ("y", C.c_void_p), ("read_off", C.c_void_p),
                 ("grp_len", C.c_void_p), ("kmer_mean", C.c_void_p), ("kmer_std", C.c_void_p),
-                ("grp_cond", C.c_void_p)]
+                ("grp_cond", C.c_void_p), ("y_format", C.c_int32), ("reserved", C.c_int32),
+                ("y_scale", C.c_double)]
 
 
 class XpMethod(C.Structure):

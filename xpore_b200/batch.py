@@ -83,6 +83,10 @@ class Batch:
     ids: list = field(default_factory=list)
     positions: list = field(default_factory=list)
     kmers: list = field(default_factory=list)
+    # optional compact encoding of y (see include/xpore_b200.h: XPB200_Y_*)
+    y_enc: np.ndarray | None = None
+    y_format: int = 0
+    y_scale: float = 1.0
 
     @property
     def n_positions(self) -> int:
@@ -101,6 +105,28 @@ class Batch:
         assert self.y.shape[0] >= self.read_off[-1]
         assert self.kmer_mean.shape == (P,) and self.kmer_std.shape == (P,)
         return self
+
+    def encode_reads(self, scale: float = 100.0) -> int:
+        """Try to store the reads as scaled integers q = rint(y*scale): dataprep rounds event means
+        to 2 decimals (``dataprep.py:638``), so q / scale reproduces y bit for bit and the batch
+        needs 2 (u16) or 4 (i32) bytes per read instead of 8.  Falls back to f64 when any value
+        does not round-trip.  Returns the chosen format code."""
+        Y_F64, Y_I32, Y_U16 = 0, 1, 2
+        self.y_enc, self.y_format, self.y_scale = None, Y_F64, 1.0
+        y = self.y[:self.n_reads]
+        if y.size == 0:
+            return Y_F64
+        q = np.rint(y * scale)
+        if not (np.abs(q) < 2 ** 31 - 1).all() or not np.array_equal(q / scale, y):
+            return Y_F64
+        if q.min() >= 0 and q.max() < 65536:
+            enc, fmt, per16 = q.astype(np.uint16), Y_U16, 8
+        else:
+            enc, fmt, per16 = q.astype(np.int32), Y_I32, 4
+        pad = (-len(enc)) % per16 + per16
+        self.y_enc = np.concatenate([enc, np.zeros(pad, enc.dtype)])
+        self.y_format, self.y_scale = fmt, float(scale)
+        return fmt
 
     def subset(self, index) -> "Batch":
         """Positions ``index`` (ascending array) re-packed — used for sharding across ranks."""

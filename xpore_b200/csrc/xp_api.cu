@@ -66,6 +66,8 @@ int check_batch(const xpb200_batch* b, const xpb200_method* m) {
     if (b->n_conditions < 1 || b->n_conditions > xpk::kMaxConditions)
         return fail(XPB200_EINVAL, "n_conditions must be 1..32");
     if (!(m->dirichlet_conc > 0.0)) return fail(XPB200_EINVAL, "dirichlet_conc must be > 0");
+    if (b->y_format < 0 || b->y_format > 2) return fail(XPB200_EINVAL, "unknown y_format");
+    if (b->y_format != XPB200_Y_F64 && !(b->y_scale > 0.0)) return fail(XPB200_EINVAL, "y_scale must be > 0");
     return 0;
 }
 
@@ -112,7 +114,8 @@ int launch_prefilter(const xpb200_batch* b, const xpb200_method* m, uint32_t* st
                      cudaStream_t st) {
     if (b->n_positions == 0) return 0;
     xpk::PrefilterArgs a;
-    a.y = b->y; a.read_off = b->read_off; a.grp_len = b->grp_len; a.kmer_mean = b->kmer_mean;
+    a.y = b->y; a.y_format = b->y_format; a.y_scale = b->y_scale;
+    a.read_off = b->read_off; a.grp_len = b->grp_len; a.kmer_mean = b->kmer_mean;
     a.grp_cond = b->grp_cond; a.P = b->n_positions; a.G = b->n_groups;
     a.enabled = (m->prefilter == 1);
     a.threshold = m->prefilter_threshold;
@@ -219,7 +222,8 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
     Geometry g;
     if (int rc = fit_geometry(b->n_groups, b->max_reads, &g)) return rc;
     xpk::FitArgs fa;
-    fa.y = b->y; fa.read_off = b->read_off; fa.grp_len = b->grp_len; fa.kmer_mean = b->kmer_mean;
+    fa.y = b->y; fa.y_format = b->y_format; fa.y_scale = b->y_scale;
+    fa.read_off = b->read_off; fa.grp_len = b->grp_len; fa.kmer_mean = b->kmer_mean;
     fa.kmer_std = b->kmer_std; fa.worklist = ws.worklist; fa.n_work = ws.n_work; fa.ticket = ws.ticket;
     fa.G = b->n_groups; fa.max_iters = m->max_iters; fa.cap = g.cap; fa.stopping = m->stopping_criteria;
     fa.conc0 = m->dirichlet_conc;
@@ -289,12 +293,12 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
     const int P = b->n_positions, G = b->n_groups, C = b->n_conditions;
     if (n_fitted) *n_fitted = 0;
     if (P == 0) return 0;
-    const size_t R2 = (size_t)((b->n_reads + 1) & ~(int64_t)1);
+    const size_t eb = b->y_format == XPB200_Y_F64 ? 8 : (b->y_format == XPB200_Y_I32 ? 4 : 2);
     const int FW = xpc::fit_width(G), SW = xpc::stats_width(G, C);
 
     // chunk boundaries (positions), cut where the read offsets cross multiples of the chunk size
     const int64_t* roff = b->read_off;
-    int nchunks = (int)std::min<size_t>(kMaxChunks, std::max<size_t>(1, ((size_t)b->n_reads * 8 + kChunkBytes - 1) / kChunkBytes));
+    int nchunks = (int)std::min<size_t>(kMaxChunks, std::max<size_t>(1, ((size_t)b->n_reads * eb + kChunkBytes - 1) / kChunkBytes));
     std::vector<int> cut(nchunks + 1, 0);
     cut[nchunks] = P;
     for (int c = 1; c < nchunks; ++c) {
@@ -305,7 +309,7 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
 
     // device layout
     size_t o = 0;
-    const size_t o_y = o; o += align_up(R2 * 8);
+    const size_t o_y = o; o += align_up((size_t)b->n_reads * eb + 64);
     const size_t o_off = o; o += align_up((size_t)(P + 1) * 8);
     const size_t o_glen = o; o += align_up((size_t)P * G * 4);
     const size_t o_km = o; o += align_up((size_t)P * 8);
@@ -334,7 +338,7 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
         dc->cap = want;
     }
     char* d = reinterpret_cast<char*>(dc->buf);
-    double* d_y = (double*)(d + o_y);
+    char* d_y = d + o_y;
     int64_t* d_off = (int64_t*)(d + o_off);
     int32_t* d_glen = (int32_t*)(d + o_glen);
     double* d_km = (double*)(d + o_km);
@@ -353,7 +357,8 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
         if (pc == 0) continue;
         const int64_t r0 = roff[p0], r1 = roff[p1];
         // copy-in
-        CK(cudaMemcpyAsync(d_y + r0, b->y + r0, (size_t)(r1 - r0) * 8, cudaMemcpyDefault, dc->s_in));
+        CK(cudaMemcpyAsync(d_y + (size_t)r0 * eb, (const char*)b->y + (size_t)r0 * eb, (size_t)(r1 - r0) * eb,
+                           cudaMemcpyDefault, dc->s_in));
         CK(cudaMemcpyAsync(d_off + p0, roff + p0, (size_t)(pc + 1) * 8, cudaMemcpyDefault, dc->s_in));
         CK(cudaMemcpyAsync(d_glen + (size_t)p0 * G, b->grp_len + (size_t)p0 * G, (size_t)pc * G * 4, cudaMemcpyDefault, dc->s_in));
         CK(cudaMemcpyAsync(d_km + p0, b->kmer_mean + p0, (size_t)pc * 8, cudaMemcpyDefault, dc->s_in));

@@ -94,8 +94,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // conditions, lane j keeps position j's moments; then all 32 lanes evaluate their Student-t
 // p-value in parallel.
 // ------------------------------------------------------------------------------------------
+// decode element i of a read buffer: f64, or scaled integer q / scale (IEEE division: exact
+// reproduction of the packed double)
+enum { kYF64 = 0, kYI32 = 1, kYU16 = 2 };
+__device__ __forceinline__ int y_elem_bytes(int fmt) { return fmt == kYF64 ? 8 : (fmt == kYI32 ? 4 : 2); }
+__device__ __forceinline__ double y_load_global(const void* y, int fmt, double scale, int64_t i) {
+    if (fmt == kYF64) return __ldg(reinterpret_cast<const double*>(y) + i);
+    if (fmt == kYI32) return __ddiv_rn((double)__ldg(reinterpret_cast<const int*>(y) + i), scale);
+    return __ddiv_rn((double)__ldg(reinterpret_cast<const unsigned short*>(y) + i), scale);
+}
+
 struct PrefilterArgs {
-    const double* y;
+    const void* y;
+    int y_format;
+    double y_scale;
     const int64_t* read_off;
     const int32_t* grp_len;
     const double* kmer_mean;
@@ -152,13 +164,12 @@ __global__ void __launch_bounds__(WARPS * 32) xp_prefilter_kernel(PrefilterArgs 
             double s1a = 0, s2a = 0, s1b = 0, s2b = 0;
             int na = 0, nb = 0;
             int g = 0, gend = goff[1];
-            const double* yp = a.y + off;
             for (int i = lane; i < n; i += 32) {
                 while (i >= gend) {
                     ++g;
                     gend = goff[g + 1];
                 }
-                const double v = __ldg(yp + i) - m0;
+                const double v = y_load_global(a.y, a.y_format, a.y_scale, off + i) - m0;
                 if (side[g] == 0) {
                     s1a += v;
                     s2a = fma(v, v, s2a);
@@ -266,8 +277,9 @@ __global__ void xp_worklist_scatter(WorklistArgs a) {
 //
 // Per-warp shared memory (doubles unless noted):
 //   slab[cap+2]       centred reads y' (TMA bulk copy lands here; +2 for 16-byte alignment slack)
-//   scratch[2G][33]   per-lane partial N_gk of the current sweep (33: bank-conflict-free columns)
-//   Nsm[2G]           N_gk
+//   scratch[2G+5][33] per-lane partials of the current sweep: N_gk rows, then S1_0 S1_1 S2_0 S2_1 Hq
+//                     (33: bank-conflict-free columns); lane s sums row s
+//   Nsm[2G+5]         the row totals: N_gk, then the five moments
 //   lw[2G]            E[ln w_gk] = psi(c_gk) - psi(c_g0 + c_g1)        (gmm.py:283-284)
 //   Asm[G]            per-group constant of d_n
 //   psis[G]           psi(2 c0 + n_g): sum_k c_gk = 2 c0 + n_g is constant over sweeps
@@ -277,7 +289,9 @@ __global__ void xp_worklist_scatter(WorklistArgs a) {
 //   gid[cap+2] (u8)   group slot of every read
 // ------------------------------------------------------------------------------------------
 struct FitArgs {
-    const double* y;
+    const void* y;
+    int y_format;
+    double y_scale;
     const int64_t* read_off;
     const int32_t* grp_len;
     const double* kmer_mean;
@@ -292,9 +306,11 @@ struct FitArgs {
     uint32_t* status;
 };
 
-__host__ __device__ inline size_t fit_scratch_doubles(int G) { return 66 * (size_t)G > 128 ? 66 * (size_t)G : 128; }
+__host__ __device__ inline size_t fit_scratch_doubles(int G) {  // (2G N rows + 5 moment rows) x 33, >= 1 KB histogram
+    return 33 * (size_t)(2 * G + 5) > 128 ? 33 * (size_t)(2 * G + 5) : 128;
+}
 __host__ __device__ inline size_t fit_warp_smem_bytes(int cap, int G) {
-    size_t doubles = (size_t)(cap + 2) + fit_scratch_doubles(G) + 2 * G + 2 * G + G + G + 8;
+    size_t doubles = (size_t)(cap + 2) + fit_scratch_doubles(G) + (2 * G + 6) + 2 * G + G + G + 8;
     size_t bytes = doubles * 8 + (size_t)((G + 2) & ~1) * 4 + 8 + (size_t)(cap + 2);  // + gid bytes
     return (bytes + 15) & ~(size_t)15;
 }
@@ -393,7 +409,7 @@ __global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
     double* slab = reinterpret_cast<double*>(wbase);
     double* scratch = slab + a.cap + 2;
     double* Nsm = scratch + fit_scratch_doubles(G);
-    double* lw = Nsm + 2 * G;
+    double* lw = Nsm + 2 * G + 6;
     double* Asm = lw + 2 * G;
     double* psis = Asm + G;
     double* sc = psis + G;
@@ -426,13 +442,16 @@ __global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
             continue;
         }
         // ---- stage the reads: one TMA bulk copy of the 16-byte aligned superset -------------
-        const int sh = (int)(off & 1);
-        const uint32_t bytes = (uint32_t)((n + sh + 1) & ~1) * 8u;
+        const int fmt = a.y_format;
+        const int eb = y_elem_bytes(fmt);
+        const int per16 = 16 / eb;                         // elements per 16 bytes
+        const int sh = (int)(off & (per16 - 1));           // elements in front of this position
+        const uint32_t bytes = (uint32_t)(((n + sh) * eb + 15) & ~15);
         fence_proxy_async();  // order this warp's generic-proxy slab accesses before the async-proxy write
         __syncwarp();
         if (lane == 0) {
             mbar_expect_tx(mbar, bytes);
-            tma_bulk_g2s(slab, a.y + (off - sh), bytes, mbar);
+            tma_bulk_g2s(slab, reinterpret_cast<const char*>(a.y) + (off - sh) * eb, bytes, mbar);
         }
         const double m0 = a.kmer_mean[p];
         const double sd = a.kmer_std[p];
@@ -480,15 +499,26 @@ __global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
 
         mbar_wait(mbar, parity);
         parity ^= 1u;
-        double* yv = slab + sh;
-        // centre on the k-mer mean; track min/max keys for the percentile bisection
+        // decode (scaled integers expand in place, last 32-read step first so no unread raw bytes
+        // are overwritten), centre on the k-mer mean, track min/max keys for the radix select
+        double* yv = slab + (fmt == kYF64 ? sh : 0);
         uint64_t kmin = ~0ull, kmax = 0ull;
-        for (int i = lane; i < n; i += 32) {
-            const double v = yv[i] - m0;
-            yv[i] = v;
-            const uint64_t k = dkey(v);
-            kmin = k < kmin ? k : kmin;
-            kmax = k > kmax ? k : kmax;
+        for (int i0 = ((n - 1) >> 5) << 5; i0 >= 0; i0 -= 32) {
+            const int i = i0 + lane;
+            double v = 0.0;
+            if (i < n) {
+                if (fmt == kYF64) v = yv[i];
+                else if (fmt == kYI32) v = __ddiv_rn((double)reinterpret_cast<const int*>(slab)[sh + i], a.y_scale);
+                else v = __ddiv_rn((double)reinterpret_cast<const unsigned short*>(slab)[sh + i], a.y_scale);
+                v -= m0;
+            }
+            __syncwarp();
+            if (i < n) {
+                yv[i] = v;
+                const uint64_t k = dkey(v);
+                kmin = k < kmin ? k : kmin;
+                kmax = k > kmax ? k : kmax;
+            }
         }
         kmin = warp_min_u64(kmin);
         kmax = warp_max_u64(kmax);
@@ -645,23 +675,42 @@ __global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
                 scratch[(2 * gcur) * 33 + lane] = aN0;
                 scratch[(2 * gcur + 1) * 33 + lane] = aN1;
             }
-            __syncwarp();
-            S10 = warp_sum(S10);
-            S11 = warp_sum(S11);
-            S20 = warp_sum(S20);
-            S21 = warp_sum(S21);
-            Hq = warp_sum(hq);
-            for (int s = lane; s < 2 * G; s += 32) {
-                double t = 0.0;
-#pragma unroll 8
-                for (int l = 0; l < 32; ++l) t += scratch[s * 33 + l];
-                Nsm[s] = t;
+            {
+                double* mrow = scratch + (size_t)(2 * G) * 33 + lane;
+                mrow[0] = S10;
+                mrow[33] = S11;
+                mrow[66] = S20;
+                mrow[99] = S21;
+                mrow[132] = hq;
             }
             __syncwarp();
-            N0 = N1 = 0.0;
-            for (int g = 0; g < G; ++g) {
-                N0 += Nsm[2 * g];
-                N1 += Nsm[2 * g + 1];
+            // transpose-reduce through shared memory: lane s owns row s (2G rows of N_gk + 5 moments)
+            for (int s = lane; s < 2 * G + 5; s += 32) {
+                const double* row = scratch + (size_t)s * 33;
+                double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+                for (int l = 0; l < 32; l += 4) {
+                    t0 += row[l];
+                    t1 += row[l + 1];
+                    t2 += row[l + 2];
+                    t3 += row[l + 3];
+                }
+                Nsm[s] = (t0 + t1) + (t2 + t3);
+            }
+            __syncwarp();
+            S10 = Nsm[2 * G];
+            S11 = Nsm[2 * G + 1];
+            S20 = Nsm[2 * G + 2];
+            S21 = Nsm[2 * G + 3];
+            Hq = Nsm[2 * G + 4];
+            {   // N_k = sum_g N_gk: slots of equal parity, butterfly over lane strides 2..16
+                double nk = 0.0;
+                for (int s = lane; s < 2 * G; s += 32) nk += Nsm[s];
+#pragma unroll
+                for (int m = 2; m < 32; m <<= 1) nk += __shfl_xor_sync(kFull, nk, m);
+                const double other = __shfl_xor_sync(kFull, nk, 1);
+                N0 = (lane & 1) ? other : nk;
+                N1 = (lane & 1) ? nk : other;
             }
             // ---- M-step (gmm.py:292-294, 364-370) -------------------------------------------
             c0 = mstep(N0, S10, S20, a0, b0);

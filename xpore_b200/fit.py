@@ -122,11 +122,18 @@ def _padded_y(y: np.ndarray) -> np.ndarray:
     return out
 
 
+def _y_buffer(batch: Batch):
+    """(array, format, scale) of the read buffer the library should see."""
+    if batch.y_enc is not None and batch.y_format != 0:
+        return np.ascontiguousarray(batch.y_enc), int(batch.y_format), float(batch.y_scale)
+    return _padded_y(np.ascontiguousarray(batch.y, dtype=np.float64)), 0, 1.0
+
+
 def fit_batch(batch: Batch, method: Method, device: int = 0) -> FitResult:
     """Fit every position of ``batch`` on GPU ``device`` through ``xpb200_fit_host``."""
     L = _lib.lib()
     P, G, Cn = batch.n_positions, batch.layout.n_groups, batch.layout.n_conditions
-    y = _padded_y(np.ascontiguousarray(batch.y, dtype=np.float64))
+    y, yfmt, yscale = _y_buffer(batch)
     read_off = np.ascontiguousarray(batch.read_off, dtype=np.int64)
     grp_len = np.ascontiguousarray(batch.grp_len, dtype=np.int32)
     km = np.ascontiguousarray(batch.kmer_mean, dtype=np.float64)
@@ -136,7 +143,7 @@ def fit_batch(batch: Batch, method: Method, device: int = 0) -> FitResult:
                     np.full((P, fit_width(G)), np.nan), np.full((P, stats_width(G, Cn)), np.nan), 0)
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
     b = _lib.XpBatch(P, G, Cn, _max_reads(batch), batch.n_reads, ptr(y), ptr(read_off), ptr(grp_len), ptr(km),
-                     ptr(ks), ptr(gc))
+                     ptr(ks), ptr(gc), yfmt, 0, yscale)
     r = _lib.XpResult(ptr(res.status), ptr(res.n_iter), ptr(res.pval), ptr(res.fit), ptr(res.stats))
     m = method.c_struct()
     nf = C.c_uint32(0)
@@ -155,8 +162,11 @@ class DeviceBatch:
         self.P, self.G, self.C = batch.n_positions, batch.layout.n_groups, batch.layout.n_conditions
         self.R = batch.n_reads
         self.max_reads = _max_reads(batch)
+        ybuf, self.y_format, self.y_scale = _y_buffer(batch)
+        if ybuf.dtype == np.uint16:  # torch has no arithmetic on uint16; it is only a byte container here
+            ybuf = ybuf.view(np.int16)
         self.host = {
-            "y": torch.from_numpy(_padded_y(np.ascontiguousarray(batch.y, dtype=np.float64))),
+            "y": torch.from_numpy(ybuf),
             "read_off": torch.from_numpy(np.ascontiguousarray(batch.read_off, dtype=np.int64)),
             "grp_len": torch.from_numpy(np.ascontiguousarray(batch.grp_len, dtype=np.int32).reshape(-1)),
             "kmer_mean": torch.from_numpy(np.ascontiguousarray(batch.kmer_mean, dtype=np.float64)),
@@ -180,7 +190,7 @@ class DeviceBatch:
         d = self.dev
         return _lib.XpBatch(self.P, self.G, self.C, self.max_reads, self.R, d["y"].data_ptr(),
                             d["read_off"].data_ptr(), d["grp_len"].data_ptr(), d["kmer_mean"].data_ptr(),
-                            d["kmer_std"].data_ptr(), d["grp_cond"].data_ptr())
+                            d["kmer_std"].data_ptr(), d["grp_cond"].data_ptr(), self.y_format, 0, self.y_scale)
 
 
 class DeviceResult:
