@@ -244,6 +244,7 @@ def make_batch_device(spec: Spec, device, km: KmerModel | None = None, n_positio
     kmean = torch.tensor(km.mean, device=device)
     kstd = torch.tensor(km.stdv, device=device)
     ko = torch.tensor([lay_runs.condition_names[c] in spec.ko_like for c in lay_runs.run_cond], device=device)
+    hundred = torch.tensor(100.0, dtype=torch.float64, device=device)
     ys, glens, kms, kss = [], [], [], []
     for c0 in range(0, P_all, chunk):
         P = min(chunk, P_all - c0)
@@ -277,7 +278,9 @@ def make_batch_device(spec: Spec, device, km: KmerModel | None = None, n_positio
         mod = torch.rand(R, device=device, generator=gen) < rate.reshape(-1)[cell.long()]
         z = torch.randn(R, device=device, generator=gen, dtype=torch.float64)
         y = torch.where(mod, mu[pos] + shift[pos] + 1.3 * sd[pos] * z, mu[pos] + sd[pos] * z)
-        y = torch.round(y * 100.0) / 100.0
+        # true division by a device tensor: torch turns `/ python_scalar` into a multiplication by the
+        # reciprocal on CUDA, which would not give the correctly rounded 2-decimal doubles
+        y = torch.round(y * 100.0) / hundred
         glen = torch.stack([counts[:, run_cond == c].sum(dim=1) for c in range(C)], dim=1) if pooling else counts
         ys.append(y.cpu())
         glens.append(glen.to(torch.int32).cpu())
