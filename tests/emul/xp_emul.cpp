@@ -28,8 +28,8 @@ void emul_special(int which, const double* x, const double* aux, double* out, lo
             case 2: out[i] = xlog(x[i]); break;
             case 3: out[i] = xexp(x[i]); break;
             case 4: out[i] = student_t_two_sided(x[i], aux[i]); break;
-            case 5: estep_read(x[i], r0, r1, h); out[i] = r1; break;
-            case 6: estep_read(x[i], r0, r1, h); out[i] = h; break;
+            case 5: estep_read(HostTab(), x[i], r0, r1, h); out[i] = r1; break;
+            case 6: estep_read(HostTab(), x[i], r0, r1, h); out[i] = h; break;
             default: out[i] = NAN;
         }
     }
@@ -137,7 +137,7 @@ void emul_fit(int n, const double* y, int G, const int* glen, double km, double 
                 const double yy = yv[i];
                 const double d = fma(yy, fma(C, yy, B), Asm[g]);
                 double r0, r1, h;
-                estep_read(d, r0, r1, h);
+                estep_read(HostTab(), d, r0, r1, h);
                 const double y2 = yy * yy;
                 n0 += r0; n1 += r1;
                 S1[0] = fma(r0, yy, S1[0]); S1[1] = fma(r1, yy, S1[1]);

@@ -42,17 +42,49 @@ struct Comp {
 // d = ln rho_1 - ln rho_0.  r0 = 1/(1+exp(clip(d,+-500))), r1 = 1-r0 (gmm.py:240-242); here both
 // are formed from t = exp(-|d|) so neither loses relative precision.  hq = r0 ln r0 + r1 ln r1
 // (this read's share of E[ln q(z)], gmm.py:217-219) = -(r_minor |d| + log1p(t)).
-XP_HD void estep_read(double d, double& r0, double& r1, double& hq) {
+//
+// Table-driven: exp(x) = 2^m 2^(j/32) e^r with |r| <= ln2/64 (degree-6 Taylor), and
+// ln(1+t) = ln1p(u/c_i - 1) + ln c_i with u = 1+t in [1,2] and c_i the centre of its 1/32-wide
+// interval (degree-7 series, |u/c_i - 1| <= 1/64).  `Tab` supplies the three 32-entry tables:
+// plain arrays on the host, one entry per lane + warp shuffles on the device (no bank conflicts).
+struct HostTab {
+    XP_HD double exp2(int j) const { return XPT(kExp2)[j]; }
+    XP_HD double invc(int i) const { return XPT(kInvC)[i]; }
+    XP_HD double logc(int i) const { return XPT(kLogC)[i]; }
+};
+
+template <class Tab>
+XP_HD void estep_read(const Tab& tab, double d, double& r0, double& r1, double& hq) {
     const double ad = fabs(d);
-    const double t = xexp(-fmin(ad, 500.0));
-    const double u = 1.0 + t;
-    const bool big = u > XPT(kMisc)[4];  // sqrt 2
-    const double f = big ? 0.5 * (t - 1.0) : t;  // u/2 - 1 or u - 1
-    const double den = 2.0 + f;
-    const double q = xrcp(u * den);
-    const double inv = q * den;       // 1/(1+t)
-    const double s = f * (q * u);     // f/(2+f)
-    const double l1p = log1p_core(f, s) + (big ? XPT(kMisc)[3] : 0.0);  // log(1+t)
+    const double x = -fmin(ad, 500.0);
+    const double magic = XPT(kMisc)[5];
+    const double t0 = fma(x, XPT(kE32)[0], magic);
+    const double kf = t0 - magic;
+    const int k = (int)(uint32_t)d2u(t0);  // low word of the magic sum = rint(32 x / ln 2), two's complement
+    double r = fma(-kf, XPT(kE32)[1], x);
+    r = fma(-kf, XPT(kE32)[2], r);
+    double p = XPT(kE32)[3];                // r^6/720 ... Horner
+    p = fma(p, r, XPT(kE32)[4]);
+    p = fma(p, r, XPT(kE32)[5]);
+    p = fma(p, r, XPT(kE32)[6]);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    double t = tab.exp2(k & 31) * p;
+    t = u2d(d2u(t) + ((uint64_t)(int64_t)(k >> 5) << 52));  // * 2^m, result stays normal (x >= -500)
+    const double u = 1.0 + t;                               // [1, 2]
+    int i = (int)((d2u(u) - 0x3FF0000000000000ull) >> 47);  // top five mantissa bits; u == 2 gives 32
+    i = i > 31 ? 31 : i;
+    const double rr = fma(u, tab.invc(i), -1.0);
+    double q = XPT(kL1p)[0];
+    q = fma(q, rr, XPT(kL1p)[1]);
+    q = fma(q, rr, XPT(kL1p)[2]);
+    q = fma(q, rr, XPT(kL1p)[3]);
+    q = fma(q, rr, XPT(kL1p)[4]);
+    q = fma(q, rr, XPT(kL1p)[5]);
+    q = fma(q, rr, 1.0);
+    const double l1p = fma(q, rr, tab.logc(i));  // ln(1+t)
+    const double inv = xrcp(u);
     const double rmin = t * inv;
     const bool pos = d > 0.0;
     r1 = pos ? inv : rmin;

@@ -49,6 +49,20 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
     return v;
 }
 
+// The E-step lookup tables, one entry per lane, fetched with warp shuffles (every lane of the
+// warp must call together).
+struct LaneTab {
+    double e2, ic, lc;
+    __device__ __forceinline__ void load(int lane) {
+        e2 = XPT(kExp2)[lane];
+        ic = XPT(kInvC)[lane];
+        lc = XPT(kLogC)[lane];
+    }
+    __device__ __forceinline__ double exp2(int j) const { return __shfl_sync(kFull, e2, j); }
+    __device__ __forceinline__ double invc(int i) const { return __shfl_sync(kFull, ic, i); }
+    __device__ __forceinline__ double logc(int i) const { return __shfl_sync(kFull, lc, i); }
+};
+
 // order-preserving map double -> uint64
 __device__ __forceinline__ uint64_t dkey(double x) {
     const uint64_t u = d2u(x);
@@ -423,6 +437,8 @@ __global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
     }
     __syncwarp();
     uint32_t parity = 0;
+    LaneTab tab;
+    tab.load(lane);
     const unsigned n_work = *a.n_work;
     const double conc0 = a.conc0;
 
@@ -610,20 +626,22 @@ __global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
             for (int s = 0; s < 2 * G; ++s) scratch[s * 33 + lane] = 0.0;
             __syncwarp();
             // ---- E-step + moments: one pass over the resident reads, two reads per lane per trip
-            // (two independent exp/log chains in flight; constants fetched once per pair)
+            // (two independent exp/log chains in flight).  Trip counts are warp-uniform because the
+            // table lookups are warp shuffles: n/64 full trips, then one masked trip for the rest.
             double aN0 = 0, aN1 = 0, hq = 0;
             S10 = S11 = S20 = S21 = 0.0;
             {
                 int gcur = gid[lane < n ? lane : 0];
                 int i = lane;
-                for (; i + 32 < n; i += 64) {
+                const int nfull = n >> 6;
+                for (int trip = 0; trip < nfull; ++trip, i += 64) {
                     const int g0 = gid[i], g1 = gid[i + 32];
                     const double ya = yv[i], yb = yv[i + 32];
                     const double da = fma(ya, fma(C, ya, B), Asm[g0]);
                     const double db = fma(yb, fma(C, yb, B), Asm[g1]);
                     double ra0, ra1, ha, rb0, rb1, hb;
-                    estep_read(da, ra0, ra1, ha);
-                    estep_read(db, rb0, rb1, hb);
+                    estep_read(tab, da, ra0, ra1, ha);
+                    estep_read(tab, db, rb0, rb1, hb);
                     if (g0 != gcur) {
                         scratch[(2 * gcur) * 33 + lane] = aN0;
                         scratch[(2 * gcur + 1) * 33 + lane] = aN1;
@@ -651,26 +669,48 @@ __global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
                     S21 = fma(rb1, yb2, S21);
                     hq += ha + hb;
                 }
-                if (i < n) {
-                    const int g0 = gid[i];
-                    const double ya = yv[i];
+                if (n & 63) {  // masked tail: reads i and i+32 where they exist
+                    const bool va = i < n, vb = i + 32 < n;
+                    const int ia = va ? i : 0, ib = vb ? i + 32 : 0;
+                    const int g0 = gid[ia], g1 = gid[ib];
+                    const double ya = yv[ia], yb = yv[ib];
                     const double da = fma(ya, fma(C, ya, B), Asm[g0]);
-                    double ra0, ra1, ha;
-                    estep_read(da, ra0, ra1, ha);
-                    if (g0 != gcur) {
-                        scratch[(2 * gcur) * 33 + lane] = aN0;
-                        scratch[(2 * gcur + 1) * 33 + lane] = aN1;
-                        aN0 = aN1 = 0.0;
-                        gcur = g0;
+                    const double db = fma(yb, fma(C, yb, B), Asm[g1]);
+                    double ra0, ra1, ha, rb0, rb1, hb;
+                    estep_read(tab, da, ra0, ra1, ha);
+                    estep_read(tab, db, rb0, rb1, hb);
+                    if (va) {
+                        if (g0 != gcur) {
+                            scratch[(2 * gcur) * 33 + lane] = aN0;
+                            scratch[(2 * gcur + 1) * 33 + lane] = aN1;
+                            aN0 = aN1 = 0.0;
+                            gcur = g0;
+                        }
+                        aN0 += ra0;
+                        aN1 += ra1;
+                        const double ya2 = ya * ya;
+                        S10 = fma(ra0, ya, S10);
+                        S11 = fma(ra1, ya, S11);
+                        S20 = fma(ra0, ya2, S20);
+                        S21 = fma(ra1, ya2, S21);
+                        hq += ha;
                     }
-                    aN0 += ra0;
-                    aN1 += ra1;
-                    const double ya2 = ya * ya;
-                    S10 = fma(ra0, ya, S10);
-                    S11 = fma(ra1, ya, S11);
-                    S20 = fma(ra0, ya2, S20);
-                    S21 = fma(ra1, ya2, S21);
-                    hq += ha;
+                    if (vb) {
+                        if (g1 != gcur) {
+                            scratch[(2 * gcur) * 33 + lane] = aN0;
+                            scratch[(2 * gcur + 1) * 33 + lane] = aN1;
+                            aN0 = aN1 = 0.0;
+                            gcur = g1;
+                        }
+                        aN0 += rb0;
+                        aN1 += rb1;
+                        const double yb2 = yb * yb;
+                        S10 = fma(rb0, yb, S10);
+                        S11 = fma(rb1, yb, S11);
+                        S20 = fma(rb0, yb2, S20);
+                        S21 = fma(rb1, yb2, S21);
+                        hq += hb;
+                    }
                 }
                 scratch[(2 * gcur) * 33 + lane] = aN0;
                 scratch[(2 * gcur + 1) * 33 + lane] = aN1;
@@ -786,19 +826,25 @@ __global__ void xp_dfma_peak_kernel(double* out, int iters, double seed) {
 // Special functions as the kernels evaluate them (accuracy tests).
 __global__ void xp_eval_special_kernel(int which, const double* x, const double* aux, double* out, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double v = x[i];
+    LaneTab tab;
+    tab.load(threadIdx.x & 31);
+    const bool valid = i < n;  // whole warps stay alive: the E-step tables are fetched with shuffles
+    const double v = valid ? x[i] : 0.0;
     double r = NAN, ps, lg;
-    switch (which) {
-        case 0: psi_lgamma(v, &ps, &lg); r = ps; break;
-        case 1: psi_lgamma(v, &ps, &lg); r = lg; break;
-        case 2: r = xlog(v); break;
-        case 3: r = xexp(v); break;
-        case 4: r = student_t_two_sided(v, aux[i]); break;
-        case 5: { double r0, r1, h; estep_read(v, r0, r1, h); r = r1; } break;
-        case 6: { double r0, r1, h; estep_read(v, r0, r1, h); r = h; } break;
+    if (which == 5 || which == 6) {
+        double r0, r1, h;
+        estep_read(tab, v, r0, r1, h);
+        r = (which == 5) ? r1 : h;
+    } else if (valid) {
+        switch (which) {
+            case 0: psi_lgamma(v, &ps, &lg); r = ps; break;
+            case 1: psi_lgamma(v, &ps, &lg); r = lg; break;
+            case 2: r = xlog(v); break;
+            case 3: r = xexp(v); break;
+            case 4: r = student_t_two_sided(v, aux[i]); break;
+        }
     }
-    out[i] = r;
+    if (valid) out[i] = r;
 }
 
 }  // namespace xpk

@@ -57,6 +57,14 @@ XP_TABLE(kLgam, 7, 6.41025641025641025641e-3, -1.91752691752691752692e-3, 8.4175
 XP_TABLE(kMisc, 6, 6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.44269504088896338700e+00,
          6.931471805599453094e-01, 1.41421356237309504880e+00, 6755399441055744.0)
 
+#include "xp_tables.inc"
+// 32/ln2, ln2/32 split hi/lo (hi has 20 trailing zero bits), 1/6!, 1/5!, 1/4!, 1/3!
+XP_TABLE(kE32, 7, 46.16624130844683, 0.021660849390173098, 2.3251928472369475e-12,
+         1.388888888888889e-03, 8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01)
+// log1p(r) = r (1 + r (c1 + r (c2 + ...))):  1/7 -1/6 1/5 -1/4 1/3 -1/2
+XP_TABLE(kL1p, 6, 1.4285714285714285e-01, -1.6666666666666666e-01, 2.0e-01, -2.5e-01, 3.3333333333333331e-01,
+         -5.0e-01)
+
 XP_HD uint64_t d2u(double x) {
 #if defined(__CUDA_ARCH__)
     return (uint64_t)__double_as_longlong(x);
