@@ -19,6 +19,9 @@ namespace xpk {
 
 using namespace xpc;
 
+#ifndef XP_FIT_MIN_CTAS
+#define XP_FIT_MIN_CTAS 1
+#endif
 constexpr int kMaxGroups = 64;
 constexpr int kMaxConditions = 32;
 constexpr int kBuckets = 512;
@@ -415,7 +418,7 @@ __device__ double warp_percentile(const double* yv, int n, double q, uint64_t km
 }
 
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, XP_FIT_MIN_CTAS) xp_fit_kernel(FitArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = a.G;
