@@ -220,7 +220,7 @@ def main():
 
     from xpore_b200 import _lib
     from xpore_b200 import fit as xf
-    from xpore_b200.dist import gather_records, pack_records
+    from xpore_b200.dist import gather_records
     from xpore_b200.synth import make_batch_device
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
@@ -244,10 +244,12 @@ def main():
     n_reads = torch.from_numpy(np.diff(batch.read_off)).to(dev)
     fit_w, stats_w = xf.fit_width(db.G), xf.stats_width(db.G, db.C)
 
+    recbuf = [None]
+
     def step_device():
         xf.fit_device(db, method, out)
         if world > 1:
-            rec = pack_records(out.status, out.n_iter, out.pval, out.fit, out.stats, index_offset=rank * db.P)
+            rec, recbuf[0] = xf.pack_records_device(out, index_offset=rank * db.P, buf=recbuf[0])
             return gather_records(rec, rank, world)
         return None
 
@@ -332,11 +334,14 @@ def main():
     d2h_box = [0]
 
     def step_e2e():
-        _lib.check(L.xpb200_fit_host(local_rank, C.byref(cb), C.byref(cm), C.byref(cr), C.byref(nf)))
         if world == 1:
+            _lib.check(L.xpb200_fit_host(local_rank, C.byref(cb), C.byref(cm), C.byref(cr), C.byref(nf)))
             d2h_box[0] = sum(v.numel() * v.element_size() for v in hres.values()) + 4
         else:
-            rec = pack_records(out.status, out.n_iter, out.pval, out.fit, out.stats, index_offset=rank * db.P)
+            # pinned host -> HBM, fit, compact, NCCL gather to rank 0, rank 0 copies the records to its host
+            db.upload()
+            xf.fit_device(db, method, out)
+            rec, recbuf[0] = xf.pack_records_device(out, index_offset=rank * db.P, buf=recbuf[0])
             allrec = gather_records(rec, rank, world)
             if rank == 0:
                 host = allrec.cpu()
@@ -391,7 +396,9 @@ def main():
                        "read_sweeps_per_s": read_iters * world / (ms_per_step * 1e-3)},
             "e2e": {"value": e2e_value, "unit": "positions fitted/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_box[0],
-                    "api": "xpb200_fit_host (C ABI, pinned host buffers)"},
+                    "api": "xpb200_fit_host (C ABI, pinned host buffers)" if world == 1 else
+                           "pinned host -> DeviceBatch.upload -> xpb200_fit_device -> xpb200_pack_records -> "
+                           "NCCL gather -> rank-0 host"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "xp_fit_kernel", "bound": "fp64", "achieved": achieved, "peak": peak.value,

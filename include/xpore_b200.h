@@ -123,6 +123,14 @@ int32_t xpb200_prefilter_device(const xpb200_batch* batch, const xpb200_method* 
 int32_t xpb200_stats_device(const xpb200_batch* batch, const xpb200_method* method, const xpb200_result* result,
                             const int32_t* worklist, const uint32_t* n_work_dev, void* cuda_stream);
 
+/* Compact records of the fitted positions of the last xpb200_fit_device call that used `workspace`
+ * (worklist order): row = [index_offset + position, status, n_iter, pval, fit[FW], stats[SW]] as
+ * f64, written to out[capacity_rows, 4+FW+SW] (device).  This is the payload of the final gather to
+ * the writer rank (the reference appends rows under a file lock instead, scripts/diffmod.py:68-69). */
+int32_t xpb200_pack_records(const xpb200_result* result, int32_t n_positions, int32_t n_groups,
+                            int32_t n_conditions, const void* workspace, int64_t index_offset, double* out,
+                            int64_t capacity_rows, void* cuda_stream);
+
 /* Launch geometry the fit kernel would use for this batch (for reporting): */
 typedef struct xpb200_launch_info {
     int32_t sm_count, ctas_per_sm, warps_per_cta, smem_per_cta, slab_reads, regs_per_thread;

@@ -216,3 +216,28 @@ def test_full_size_properties(torch_cuda):
     n_reads = np.diff(shuffled.read_off)[sel]
     np.testing.assert_allclose(N.sum(axis=(1, 2)), n_reads, rtol=1e-12)
     assert (b.n_iter[sel] >= 2).all() and (b.n_iter[sel] <= 499).all()
+
+
+def test_pack_records_device(torch_cuda):
+    """Compact records (payload of the final gather) = the selected rows of the dense arrays."""
+    torch = torch_cuda
+    from xpore_b200.dist import unpack_records
+    spec = Spec({"KO": 2, "WT": 2}, reads_lo=20, reads_hi=60, f_mod=0.4, seed=51,
+                method={"prefiltering": {"method": "t-test", "threshold": 0.1}})
+    batch = make_batch(spec, KmerModel.load(), n_positions=3000)
+    out = xf.fit_device(xf.DeviceBatch(batch), xf.Method.from_dict(spec.method))
+    rec, _ = xf.pack_records_device(out, index_offset=7000)
+    res = out.to_host()
+    idx, status, n_iter, pval, fit, stats = unpack_records(rec.cpu().numpy(), xf.fit_width(4), xf.stats_width(4, 2))
+    assert len(idx) == res.n_fitted == int(res.selected.sum())
+    order = np.argsort(idx)
+    sel = np.nonzero(res.selected)[0]
+    np.testing.assert_array_equal(idx[order] - 7000, sel)
+    np.testing.assert_array_equal(status[order], res.status[sel])
+    np.testing.assert_array_equal(n_iter[order], res.n_iter[sel])
+    np.testing.assert_array_equal(pval[order], res.pval[sel])
+    np.testing.assert_array_equal(fit[order], res.fit[sel])
+    np.testing.assert_array_equal(stats[order], res.stats[sel])
+    # longest positions first (worklist order)
+    n = np.diff(batch.read_off)[idx - 7000]
+    assert n[0] >= n[-1]

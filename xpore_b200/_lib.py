@@ -44,7 +44,7 @@ class XpLaunchInfo(C.Structure):
 EXPORTS = ["xpb200_fit_width", "xpb200_stats_width", "xpb200_workspace_bytes", "xpb200_fit_device",
            "xpb200_fit_host", "xpb200_release", "xpb200_prefilter_device", "xpb200_stats_device",
            "xpb200_fit_launch_info", "xpb200_launch_count", "xpb200_measure_fp64_peak", "xpb200_eval_special",
-           "xpb200_set_stage_timing", "xpb200_get_stage_ms",
+           "xpb200_set_stage_timing", "xpb200_get_stage_ms", "xpb200_pack_records",
            "xpb200_last_error", "xpb200_version"]
 
 
@@ -111,6 +111,9 @@ def lib():
         L.xpb200_set_stage_timing.argtypes = [C.c_int32]
         L.xpb200_get_stage_ms.restype = C.c_int32
         L.xpb200_get_stage_ms.argtypes = [C.POINTER(C.c_float)]
+        L.xpb200_pack_records.restype = C.c_int32
+        L.xpb200_pack_records.argtypes = [C.POINTER(XpResult), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_int64, C.c_void_p]
         L.xpb200_last_error.restype = C.c_char_p
         L.xpb200_version.restype = C.c_char_p
         _lib = L

@@ -448,6 +448,23 @@ int32_t xpb200_measure_fp64_peak(int32_t device, int32_t repeats, double* tflops
     return 0;
 }
 
+int32_t xpb200_pack_records(const xpb200_result* r, int32_t P, int32_t G, int32_t C, const void* workspace,
+                            int64_t index_offset, double* out, int64_t capacity_rows, void* stream) {
+    if (!r || !workspace || !out) return fail(XPB200_EINVAL, "null argument");
+    if (P <= 0) return 0;
+    Workspace ws = carve(const_cast<void*>(workspace));
+    xpk::PackArgs a;
+    a.worklist = ws.worklist; a.n_work = ws.n_work; a.status = r->status; a.n_iter = r->n_iter; a.pval = r->pval;
+    a.fit = r->fit; a.stats = r->stats; a.FW = xpc::fit_width(G); a.SW = xpc::stats_width(G, C);
+    a.index_offset = index_offset; a.capacity = capacity_rows; a.out = out;
+    const int threads = 256, wpb = threads / 32;
+    const int blocks = std::max(1, std::min((P + wpb - 1) / wpb, 148 * 8));
+    xpk::xp_pack_records_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(a);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int32_t xpb200_set_stage_timing(int32_t on) {
     if (on && !g_timer.ev[0])
         for (auto& e : g_timer.ev) CK(cudaEventCreate(&e));

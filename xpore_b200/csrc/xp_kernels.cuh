@@ -19,9 +19,6 @@ namespace xpk {
 
 using namespace xpc;
 
-#ifndef XP_FIT_MIN_CTAS
-#define XP_FIT_MIN_CTAS 1
-#endif
 constexpr int kMaxGroups = 64;
 constexpr int kMaxConditions = 32;
 constexpr int kBuckets = 512;
@@ -418,7 +415,7 @@ __device__ double warp_percentile(const double* yv, int n, double q, uint64_t km
 }
 
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, XP_FIT_MIN_CTAS) xp_fit_kernel(FitArgs a) {
+__global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = a.G;
@@ -809,6 +806,45 @@ __global__ void xp_stats_kernel(StatsArgs a) {
                                       a.kmer_std[p], a.fit + (size_t)p * fit_width(a.G),
                                       a.stats + (size_t)p * stats_width(a.G, a.C), w_mod, cov);
     a.status[p] = (a.status[p] & ~(STATUS_KEEP_ROW | STATUS_MOD_IS_1 | STATUS_HIGHER)) | fl;
+}
+
+// ------------------------------------------------------------------------------------------
+// Compact fixed-width records of the fitted positions (worklist order), one warp per record:
+//   [global position index, status, n_iter, pval, fit[FW], stats[SW]]  as f64
+// This is what the final NCCL gather ships to the writer rank.
+// ------------------------------------------------------------------------------------------
+struct PackArgs {
+    const int32_t* worklist;
+    const uint32_t* n_work;
+    const uint32_t* status;
+    const int32_t* n_iter;
+    const double* pval;
+    const double* fit;
+    const double* stats;
+    int FW, SW;
+    long long index_offset, capacity;
+    double* out;
+};
+
+__global__ void xp_pack_records_kernel(PackArgs a) {
+    const unsigned n = *a.n_work;
+    const int lane = threadIdx.x & 31;
+    const int W = 4 + a.FW + a.SW;
+    for (unsigned w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n && (long long)w < a.capacity;
+         w += gridDim.x * (blockDim.x >> 5)) {
+        const int p = a.worklist[w];
+        double* o = a.out + (size_t)w * W;
+        if (lane == 0) {
+            o[0] = (double)(a.index_offset + p);
+            o[1] = (double)a.status[p];
+            o[2] = (double)a.n_iter[p];
+            o[3] = a.pval[p];
+        }
+        const double* f = a.fit + (size_t)p * a.FW;
+        const double* t = a.stats + (size_t)p * a.SW;
+        for (int c = lane; c < a.FW; c += 32) o[4 + c] = f[c];
+        for (int c = lane; c < a.SW; c += 32) o[4 + a.FW + c] = t[c];
+    }
 }
 
 // ------------------------------------------------------------------------------------------

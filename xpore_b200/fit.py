@@ -228,3 +228,20 @@ def fit_device(dbatch: DeviceBatch, method: Method, out: DeviceResult | None = N
         _lib.check(L.xpb200_fit_device(C.byref(b), C.byref(m), C.byref(r), out.workspace.data_ptr(),
                                        out.workspace.numel(), out.n_fitted.data_ptr(), C.c_void_p(stream)))
     return out
+
+
+def pack_records_device(out: DeviceResult, index_offset: int = 0, buf=None):
+    """Compact [n_fitted, 4+FW+SW] record matrix of the fitted positions on the device (see
+    ``xpb200_pack_records``); synchronises only to read the fitted count."""
+    torch = out.torch
+    L = _lib.lib()
+    W = 4 + fit_width(out.G) + stats_width(out.G, out.C)
+    if buf is None or buf.shape[0] < out.P or buf.shape[1] != W:
+        buf = torch.empty((max(out.P, 1), W), dtype=torch.float64, device=out.status.device)
+    r = out.c_struct()
+    with torch.cuda.device(out.status.device):
+        stream = torch.cuda.current_stream(out.status.device).cuda_stream
+        _lib.check(L.xpb200_pack_records(C.byref(r), out.P, out.G, out.C, out.workspace.data_ptr(), int(index_offset),
+                                         buf.data_ptr(), buf.shape[0], C.c_void_p(stream)))
+    n = int(out.n_fitted.item())
+    return buf[:n], buf
