@@ -332,6 +332,7 @@ def main():
     nf = C.c_uint32(0)
     h2d = db.h2d_bytes
     d2h_box = [0]
+    pinned_out = [None]
 
     def step_e2e():
         if world == 1:
@@ -344,8 +345,12 @@ def main():
             rec, recbuf[0] = xf.pack_records_device(out, index_offset=rank * db.P, buf=recbuf[0])
             allrec = gather_records(rec, rank, world)
             if rank == 0:
-                host = allrec.cpu()
-                d2h_box[0] = host.numel() * 8 + 4
+                if pinned_out[0] is None or pinned_out[0].shape[0] < allrec.shape[0]:
+                    pinned_out[0] = torch.empty((int(allrec.shape[0] * 1.2) + 1, allrec.shape[1]),
+                                                dtype=torch.float64).pin_memory()
+                pinned_out[0][:allrec.shape[0]].copy_(allrec, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                d2h_box[0] = allrec.numel() * 8 + 4
 
     for _ in range(max(1, min(args.warmup, 2))):
         step_e2e()

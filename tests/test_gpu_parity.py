@@ -241,3 +241,26 @@ def test_pack_records_device(torch_cuda):
     # longest positions first (worklist order)
     n = np.diff(batch.read_off)[idx - 7000]
     assert n[0] >= n[-1]
+
+
+def test_scaled_integer_decode_exhaustive(torch_cuda):
+    """The division-free decode of u16/i32 reads equals IEEE q/100 for every u16 value and for random
+    i32 values (prefilter p-values of single-value positions would differ otherwise); checked through
+    the fit of a batch whose reads enumerate all u16 codes."""
+    torch = torch_cuda
+    from xpore_b200.batch import Batch, Layout
+    lay = Layout(["A", "B"], ["A-r1", "B-r1"], [0, 1], False)
+    rng = np.random.default_rng(3)
+    for fmt, q in ((2, np.arange(65536, dtype=np.int64)), (1, rng.integers(-2 ** 31 + 2, 2 ** 31 - 2, 65536))):
+        y = q / 100.0
+        P = 64
+        per = len(y) // P
+        grp_len = np.full((P, 2), per // 2, dtype=np.int32)
+        read_off = np.arange(P + 1, dtype=np.int64) * per
+        b = Batch(lay, y.copy(), read_off, grp_len, np.full(P, 100.0), np.full(P, 3.0))
+        m = xf.Method(max_iters=3, prefilter_method="t-test", prefilter_threshold=2.0)
+        ref = xf.fit_batch(b, m)
+        assert b.encode_reads() == fmt
+        enc = xf.fit_batch(b, m)
+        np.testing.assert_array_equal(ref.pval, enc.pval)
+        np.testing.assert_array_equal(ref.fit, enc.fit)

@@ -108,14 +108,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // conditions, lane j keeps position j's moments; then all 32 lanes evaluate their Student-t
 // p-value in parallel.
 // ------------------------------------------------------------------------------------------
-// decode element i of a read buffer: f64, or scaled integer q / scale (IEEE division: exact
-// reproduction of the packed double)
+// Decode of the scaled-integer read formats: y = q / scale, correctly rounded, without a division
+// instruction sequence.  With rs = RN(1/scale):  a = q*rs;  r = fma(-a, scale, q) (exact residual);
+// y = fma(r, rs, a)  (Markstein's correction step; equal to IEEE q/scale - verified exhaustively over
+// the u16 range and on random i32 values in tests/test_gpu_parity.py).
 enum { kYF64 = 0, kYI32 = 1, kYU16 = 2 };
 __device__ __forceinline__ int y_elem_bytes(int fmt) { return fmt == kYF64 ? 8 : (fmt == kYI32 ? 4 : 2); }
-__device__ __forceinline__ double y_load_global(const void* y, int fmt, double scale, int64_t i) {
+__device__ __forceinline__ double y_decode(double q, double scale, double rscale) {
+    const double a = q * rscale;
+    const double r = fma(-a, scale, q);
+    return fma(r, rscale, a);
+}
+__device__ __forceinline__ double y_load_global(const void* y, int fmt, double scale, double rscale, int64_t i) {
     if (fmt == kYF64) return __ldg(reinterpret_cast<const double*>(y) + i);
-    if (fmt == kYI32) return __ddiv_rn((double)__ldg(reinterpret_cast<const int*>(y) + i), scale);
-    return __ddiv_rn((double)__ldg(reinterpret_cast<const unsigned short*>(y) + i), scale);
+    if (fmt == kYI32) return y_decode((double)__ldg(reinterpret_cast<const int*>(y) + i), scale, rscale);
+    return y_decode((double)__ldg(reinterpret_cast<const unsigned short*>(y) + i), scale, rscale);
 }
 
 struct PrefilterArgs {
@@ -178,20 +185,33 @@ __global__ void __launch_bounds__(WARPS * 32) xp_prefilter_kernel(PrefilterArgs 
             double s1a = 0, s2a = 0, s1b = 0, s2b = 0;
             int na = 0, nb = 0;
             int g = 0, gend = goff[1];
-            for (int i = lane; i < n; i += 32) {
-                while (i >= gend) {
-                    ++g;
-                    gend = goff[g + 1];
+            const double rscale = 1.0 / a.y_scale;
+            for (int base = 0; base < n; base += 128) {  // four loads in flight per lane
+                double v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = base + lane + 32 * k;
+                    v[k] = (i < n) ? y_load_global(a.y, a.y_format, a.y_scale, rscale, off + i) : 0.0;
                 }
-                const double v = y_load_global(a.y, a.y_format, a.y_scale, off + i) - m0;
-                if (side[g] == 0) {
-                    s1a += v;
-                    s2a = fma(v, v, s2a);
-                    ++na;
-                } else {
-                    s1b += v;
-                    s2b = fma(v, v, s2b);
-                    ++nb;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = base + lane + 32 * k;
+                    if (i < n) {
+                        while (i >= gend) {
+                            ++g;
+                            gend = goff[g + 1];
+                        }
+                        const double c = v[k] - m0;
+                        if (side[g] == 0) {
+                            s1a += c;
+                            s2a = fma(c, c, s2a);
+                            ++na;
+                        } else {
+                            s1b += c;
+                            s2b = fma(c, c, s2b);
+                            ++nb;
+                        }
+                    }
                 }
             }
             s1a = warp_sum(s1a);
@@ -518,14 +538,15 @@ __global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
         // decode (scaled integers expand in place, last 32-read step first so no unread raw bytes
         // are overwritten), centre on the k-mer mean, track min/max keys for the radix select
         double* yv = slab + (fmt == kYF64 ? sh : 0);
+        const double rscale = 1.0 / a.y_scale;
         uint64_t kmin = ~0ull, kmax = 0ull;
         for (int i0 = ((n - 1) >> 5) << 5; i0 >= 0; i0 -= 32) {
             const int i = i0 + lane;
             double v = 0.0;
             if (i < n) {
                 if (fmt == kYF64) v = yv[i];
-                else if (fmt == kYI32) v = __ddiv_rn((double)reinterpret_cast<const int*>(slab)[sh + i], a.y_scale);
-                else v = __ddiv_rn((double)reinterpret_cast<const unsigned short*>(slab)[sh + i], a.y_scale);
+                else if (fmt == kYI32) v = y_decode((double)reinterpret_cast<const int*>(slab)[sh + i], a.y_scale, rscale);
+                else v = y_decode((double)reinterpret_cast<const unsigned short*>(slab)[sh + i], a.y_scale, rscale);
                 v -= m0;
             }
             __syncwarp();
