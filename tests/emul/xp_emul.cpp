@@ -21,15 +21,16 @@ int emul_stats_width(int G, int C) { return stats_width(G, C); }
 
 void emul_special(int which, const double* x, const double* aux, double* out, long long n) {
     for (long long i = 0; i < n; ++i) {
-        double ps, lg, r0, r1, h;
+        double ps, lg, inv, rmin, h;
+        bool pos;
         switch (which) {
             case 0: psi_lgamma(x[i], &ps, &lg); out[i] = ps; break;
             case 1: psi_lgamma(x[i], &ps, &lg); out[i] = lg; break;
             case 2: out[i] = xlog(x[i]); break;
             case 3: out[i] = xexp(x[i]); break;
             case 4: out[i] = student_t_two_sided(x[i], aux[i]); break;
-            case 5: estep_read(HostTab(), x[i], r0, r1, h); out[i] = r1; break;
-            case 6: estep_read(HostTab(), x[i], r0, r1, h); out[i] = h; break;
+            case 5: estep_read(HostTab(), x[i], inv, rmin, h, pos); out[i] = pos ? inv : rmin; break;  // r_n1
+            case 6: estep_read(HostTab(), x[i], inv, rmin, h, pos); out[i] = -h; break;  // sum_k r ln r
             default: out[i] = NAN;
         }
     }
@@ -67,15 +68,17 @@ void emul_fit(int n, const double* y, int G, const int* glen, double km, double 
     const double tau = 1.0 / (ks * ks);
     const double a0 = tau, b0 = 0.5 * (1.0 / tau);
     const double lg_prior_w = xlgamma(2.0 * conc0) - 2.0 * xlgamma(conc0);
-    std::vector<double> psis(G), Nsm(2 * G, 0.0), lw(2 * G), Asm(G);
+    std::vector<double> N0g(G, 0.0), dpsi(G), Asm(G);   // N_g0; psi(c_g1) - psi(c_g0)
     double Kconst = 0.0;
     for (int g = 0; g < G; ++g) {
         double ps, lg;
         psi_lgamma(2.0 * conc0 + (double)glen[g], &ps, &lg);
-        psis[g] = ps;
         if (glen[g] > 0) Kconst += lg_prior_w - lg;
     }
     const double prior_gamma = a0 * xlog(b0) - xlgamma(a0);
+    // totals: component 1 follows from them because r_n1 = 1 - r_n0 (gmm.py:242)
+    double T1 = 0.0, T2 = 0.0;
+    for (int i = 0; i < n; ++i) { T1 += yv[i]; T2 = fma(yv[i], yv[i], T2); }
     // initial locations
     std::vector<double> sorted(yv);
     std::sort(sorted.begin(), sorted.end());
@@ -92,28 +95,30 @@ void emul_fit(int n, const double* y, int G, const int* glen, double km, double 
     c[0] = mstep(0, 0, 0, a0, b0);
     c[1] = c[0];
     c[1].mp = loc1;
-    double Nk[2] = {0, 0}, S1[2] = {0, 0}, S2[2] = {0, 0}, Hq = 0;
+    double Nk[2] = {0, 0}, S1[2] = {0, 0}, S2[2] = {0, 0}, Hent = 0;
     double elbo_old = -INFINITY, elbo = -INFINITY;
     int it = 0;
     unsigned st = STATUS_SELECTED;
     double tb[2], lt[2];
+    bool first = true;
     for (;;) {
         double e = 0.0;
-        for (int s = 0; s < 2 * G + 2; ++s) {
-            const bool is_c = s < 2 * G;
-            const int k = s & 1;
-            double ps, lg;
-            psi_lgamma(is_c ? conc0 + Nsm[s] : c[k].alpha, &ps, &lg);
-            if (is_c) {
-                const int g = s >> 1;
-                lw[s] = ps - psis[g];
-                if (glen[g] > 0) e += lg;
-            } else {
-                e += elbo_component(c[k], Nk[k], S1[k], S2[k], a0, b0, prior_gamma, ps, lg, xlog(c[k].beta),
-                                    xlog(c[k].lam), tb[k], lt[k]);
+        for (int g = 0; g < G; ++g) {
+            double ps[2], lg[2];
+            for (int k = 0; k < 2; ++k) {
+                const double N = first ? 0.0 : (k ? (double)glen[g] - N0g[g] : N0g[g]);
+                psi_lgamma(conc0 + N, &ps[k], &lg[k]);
+                if (glen[g] > 0) e += lg[k];
             }
+            dpsi[g] = ps[1] - ps[0];
         }
-        elbo = e + Kconst - Hq;
+        for (int k = 0; k < 2; ++k) {
+            double ps, lg;
+            psi_lgamma(c[k].alpha, &ps, &lg);
+            e += elbo_component(c[k], Nk[k], S1[k], S2[k], a0, b0, prior_gamma, ps, lg, xlog(c[k].beta),
+                                xlog(c[k].lam), tb[k], lt[k]);
+        }
+        elbo = e + Kconst + Hent;
         if (it >= 1) {
             if (elbos) elbos[it - 1] = elbo;
             const int rule = stop_rule(elbo, elbo_old, stopping);
@@ -126,29 +131,33 @@ void emul_fit(int n, const double* y, int G, const int* glen, double km, double 
             break;
         }
         ++it;
+        first = false;
         double base, B, C;
         estep_coefficients(c[0], c[1], tb[0], tb[1], lt[0], lt[1], base, B, C);
-        for (int g = 0; g < G; ++g) Asm[g] = base + (lw[2 * g + 1] - lw[2 * g]);
-        S1[0] = S1[1] = S2[0] = S2[1] = 0.0;
-        Hq = 0.0;
+        for (int g = 0; g < G; ++g) Asm[g] = base + dpsi[g];
+        double s10 = 0.0, s20 = 0.0, n0tot = 0.0;
+        Hent = 0.0;
         for (int g = 0; g < G; ++g) {
-            double n0 = 0, n1 = 0;
+            double n0 = 0;
             for (int i = goff[g]; i < goff[g + 1]; ++i) {
                 const double yy = yv[i];
                 const double d = fma(yy, fma(C, yy, B), Asm[g]);
-                double r0, r1, h;
-                estep_read(HostTab(), d, r0, r1, h);
-                const double y2 = yy * yy;
-                n0 += r0; n1 += r1;
-                S1[0] = fma(r0, yy, S1[0]); S1[1] = fma(r1, yy, S1[1]);
-                S2[0] = fma(r0, y2, S2[0]); S2[1] = fma(r1, y2, S2[1]);
-                Hq += h;
+                double inv, rmin, h;
+                bool pos;
+                estep_read(HostTab(), d, inv, rmin, h, pos);
+                const double r0 = pos ? rmin : inv;
+                const double w = r0 * yy;
+                n0 += r0;
+                s10 += w;
+                s20 = fma(w, yy, s20);
+                Hent += h;
             }
-            Nsm[2 * g] = n0;
-            Nsm[2 * g + 1] = n1;
+            N0g[g] = n0;
+            n0tot += n0;
         }
-        Nk[0] = Nk[1] = 0.0;
-        for (int g = 0; g < G; ++g) { Nk[0] += Nsm[2 * g]; Nk[1] += Nsm[2 * g + 1]; }
+        Nk[0] = n0tot; Nk[1] = (double)n - n0tot;
+        S1[0] = s10; S1[1] = T1 - s10;
+        S2[0] = s20; S2[1] = T2 - s20;
         c[0] = mstep(Nk[0], S1[0], S2[0], a0, b0);
         c[1] = mstep(Nk[1], S1[1], S2[1], a0, b0);
     }
@@ -157,7 +166,10 @@ void emul_fit(int n, const double* y, int G, const int* glen, double km, double 
     fit[FIT_ALPHA] = c[0].alpha; fit[FIT_ALPHA + 1] = c[1].alpha;
     fit[FIT_BETA] = c[0].beta; fit[FIT_BETA + 1] = c[1].beta;
     fit[FIT_ELBO] = elbo;
-    for (int s = 0; s < 2 * G; ++s) fit[FIT_N + s] = Nsm[s];
+    for (int g = 0; g < G; ++g) {
+        fit[FIT_N + 2 * g] = (it == 0) ? 0.0 : N0g[g];
+        fit[FIT_N + 2 * g + 1] = (it == 0) ? 0.0 : (double)glen[g] - N0g[g];
+    }
     *n_iter = it;
     *status = st;
 }

@@ -1,6 +1,7 @@
 // xp_api.cu — C ABI (include/xpore_b200.h) over the kernels in xp_kernels.cuh.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -37,14 +38,19 @@ int fail(int code, const std::string& msg) {
             return fail(XPB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
     } while (0)
 
-constexpr int kFitWarps = 4;
 constexpr size_t kMaxSmemPerCta = 227 * 1024;
+// Positions with at least this many reads are fitted by 4-warp teams, the rest by single warps, so
+// a few deep positions do not dictate the slab size (and with it the resident warps) of all.
+// Must be a boundary of xpk::cost_bucket (a power of two is).
+constexpr int kSplitReads = 1024;
 
 struct Workspace {  // carved out of the caller's buffer
     uint32_t* hist;
     uint32_t* cursor;
     uint32_t* n_work;
     unsigned int* ticket;
+    uint32_t* n_large;
+    unsigned int* ticket_large;
     int32_t* worklist;
 };
 size_t ws_header_bytes() { return (size_t)(2 * xpk::kBuckets + 64) * 4; }
@@ -55,6 +61,8 @@ Workspace carve(void* ws) {
     w.cursor = u + xpk::kBuckets;
     w.n_work = u + 2 * xpk::kBuckets;
     w.ticket = u + 2 * xpk::kBuckets + 1;
+    w.n_large = u + 2 * xpk::kBuckets + 2;
+    w.ticket_large = u + 2 * xpk::kBuckets + 3;
     w.worklist = reinterpret_cast<int32_t*>(u + 2 * xpk::kBuckets + 64);
     return w;
 }
@@ -71,42 +79,69 @@ int check_batch(const xpb200_batch* b, const xpb200_method* m) {
     return 0;
 }
 
+// Launch geometry of one fit-kernel flavour: `tw` warps per team (position), `teams` teams per CTA.
 struct Geometry {
-    int warps, cap, ctas_per_sm, sms;
+    int tw, teams, threads, maxt, cap, ctas_per_sm, sms, regs;
     size_t smem;
 };
 
-template <int W>
-int occupancy_for(size_t smem, int* ctas) {
-    CK(cudaFuncSetAttribute(xpk::xp_fit_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, xpk::xp_fit_kernel<W>, W * 32, smem));
+template <int TW, int MAXT>
+int prepare_kernel(Geometry* g) {
+    auto* k = xpk::xp_fit_kernel<TW, MAXT>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g->ctas_per_sm, k, g->threads, g->smem));
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, k));
+    g->regs = fa.numRegs;
     return 0;
 }
 
-// Slab sized to the batch's longest position; warps per CTA shrink when one slab set no longer
-// fits 227 KB.
-int fit_geometry(int G, int max_reads, Geometry* g) {
-    int dev = 0, sms = 0;
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// Teams per CTA: as many as 227 KB of shared memory (after the 24.5 KB of tables) and the thread
+// limit of the flavour allow.  Single-warp teams run <= 16 warps with 128 registers per thread or up
+// to 20 warps with 96.
+int fit_geometry(int G, int cap_reads, int tw, Geometry* g) {
+    int dev = 0;
     CK(cudaGetDevice(&dev));
-    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int cap = std::max(32, (max_reads + 1 + 7) & ~7);
-    const size_t per_warp = xpk::fit_warp_smem_bytes(cap, G);
-    int warps = kFitWarps;
-    while (warps > 1 && per_warp * warps > kMaxSmemPerCta) warps >>= 1;
-    if (per_warp * warps > kMaxSmemPerCta)
+    CK(cudaDeviceGetAttribute(&g->sms, cudaDevAttrMultiProcessorCount, dev));
+    g->tw = tw;
+    g->cap = std::max(32, (cap_reads + 1 + 7) & ~7);
+    const size_t per_team = xpk::fit_team_smem_bytes(g->cap, G, tw);
+    if (xpk::kFitTableBytes + per_team > kMaxSmemPerCta)
         return fail(XPB200_EINVAL, "a position has more reads than one CTA's shared memory holds (max_reads=" +
-                                       std::to_string(max_reads) + ")");
-    g->warps = warps;
-    g->cap = cap;
-    g->smem = per_warp * warps;
-    g->sms = sms;
-    int ctas = 0, rc = 0;
-    if (warps == 4) rc = occupancy_for<4>(g->smem, &ctas);
-    else if (warps == 2) rc = occupancy_for<2>(g->smem, &ctas);
-    else rc = occupancy_for<1>(g->smem, &ctas);
+                                       std::to_string(cap_reads) + ")");
+    int teams = (int)((kMaxSmemPerCta - xpk::kFitTableBytes) / per_team);
+    if (tw == 1) {
+        teams = std::min(teams, std::max(1, env_int("XPB200_FIT_WARPS", 20)));
+        teams = std::min(teams, 20);
+        g->maxt = teams <= 16 ? 512 : 640;
+    } else {
+        teams = std::min(teams, 4);
+        g->maxt = 512;
+    }
+    g->teams = teams;
+    g->threads = teams * tw * 32;
+    g->smem = xpk::kFitTableBytes + per_team * teams;
+    int rc;
+    if (tw == 1) rc = (g->maxt == 512) ? prepare_kernel<1, 512>(g) : prepare_kernel<1, 640>(g);
+    else rc = prepare_kernel<4, 512>(g);
     if (rc) return rc;
-    if (ctas < 1) return fail(XPB200_ECUDA, "fit kernel does not fit on an SM");
-    g->ctas_per_sm = ctas;
+    if (g->ctas_per_sm < 1) return fail(XPB200_ECUDA, "fit kernel does not fit on an SM");
+    return 0;
+}
+
+int launch_fit(const Geometry& g, const xpk::FitArgs& fa, int max_teams_needed, cudaStream_t st) {
+    const int need = (max_teams_needed + g.teams - 1) / g.teams;
+    const int grid = std::max(1, std::min(g.sms * g.ctas_per_sm, need));
+    if (g.tw == 1 && g.maxt == 512) xpk::xp_fit_kernel<1, 512><<<grid, g.threads, g.smem, st>>>(fa);
+    else if (g.tw == 1) xpk::xp_fit_kernel<1, 640><<<grid, g.threads, g.smem, st>>>(fa);
+    else xpk::xp_fit_kernel<4, 512><<<grid, g.threads, g.smem, st>>>(fa);
+    ++g_launches;
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -156,14 +191,10 @@ size_t xpb200_workspace_bytes(int32_t P) { return ws_header_bytes() + (size_t)st
 int32_t xpb200_fit_launch_info(int32_t device, int32_t G, int32_t max_reads, xpb200_launch_info* out) {
     if (!out) return fail(XPB200_EINVAL, "null out");
     CK(cudaSetDevice(device));
-    Geometry g;
-    if (int rc = fit_geometry(G, max_reads, &g)) return rc;
-    cudaFuncAttributes fa;
-    if (g.warps == 4) CK(cudaFuncGetAttributes(&fa, xpk::xp_fit_kernel<4>));
-    else if (g.warps == 2) CK(cudaFuncGetAttributes(&fa, xpk::xp_fit_kernel<2>));
-    else CK(cudaFuncGetAttributes(&fa, xpk::xp_fit_kernel<1>));
-    out->sm_count = g.sms; out->ctas_per_sm = g.ctas_per_sm; out->warps_per_cta = g.warps;
-    out->smem_per_cta = (int32_t)g.smem; out->slab_reads = g.cap; out->regs_per_thread = fa.numRegs;
+    Geometry g;  // the single-warp flavour (the 4-warp teams only take positions >= kSplitReads reads)
+    if (int rc = fit_geometry(G, std::min(max_reads, kSplitReads - 1), 1, &g)) return rc;
+    out->sm_count = g.sms; out->ctas_per_sm = g.ctas_per_sm; out->warps_per_cta = g.teams;
+    out->smem_per_cta = (int32_t)g.smem; out->slab_reads = g.cap; out->regs_per_thread = g.regs;
     return 0;
 }
 
@@ -208,7 +239,9 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
     // worklist, longest positions first
     xpk::WorklistArgs wa;
     wa.status = sel; wa.read_off = b->read_off; wa.P = P; wa.hist = ws.hist; wa.cursor = ws.cursor;
-    wa.n_work = ws.n_work; wa.worklist = ws.worklist;
+    wa.n_work = ws.n_work; wa.worklist = ws.worklist; wa.n_large = ws.n_large;
+    const bool two_class = b->max_reads >= kSplitReads;
+    wa.split = two_class ? kSplitReads : 0;
     const int wthreads = 256;
     const int wblocks = std::min((P + wthreads - 1) / wthreads, 1184);
     xpk::xp_worklist_count<<<wblocks, wthreads, 0, st>>>(wa);
@@ -218,25 +251,25 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
     CK(cudaGetLastError());
 
     stage_mark(2, st);
-    // K3 fit: persistent CTAs, one warp per position
-    Geometry g;
-    if (int rc = fit_geometry(b->n_groups, b->max_reads, &g)) return rc;
+    // K3 fit: persistent CTAs; 4-warp teams for the deep positions first, then one warp per position
     xpk::FitArgs fa;
     fa.y = b->y; fa.y_format = b->y_format; fa.y_scale = b->y_scale;
     fa.read_off = b->read_off; fa.grp_len = b->grp_len; fa.kmer_mean = b->kmer_mean;
-    fa.kmer_std = b->kmer_std; fa.worklist = ws.worklist; fa.n_work = ws.n_work; fa.ticket = ws.ticket;
-    fa.G = b->n_groups; fa.max_iters = m->max_iters; fa.cap = g.cap; fa.stopping = m->stopping_criteria;
+    fa.kmer_std = b->kmer_std; fa.worklist = ws.worklist;
+    fa.G = b->n_groups; fa.max_iters = m->max_iters; fa.stopping = m->stopping_criteria;
     fa.conc0 = m->dirichlet_conc;
     fa.lg_prior_w = xpm::xlgamma(2.0 * m->dirichlet_conc) - 2.0 * xpm::xlgamma(m->dirichlet_conc);
     fa.fit = r->fit; fa.n_iter = r->n_iter; fa.status = r->status;
-    const int max_ctas = g.sms * g.ctas_per_sm;
-    const int need = (P + g.warps - 1) / g.warps;
-    const int grid = std::max(1, std::min(max_ctas, need));
-    if (g.warps == 4) xpk::xp_fit_kernel<4><<<grid, 128, g.smem, st>>>(fa);
-    else if (g.warps == 2) xpk::xp_fit_kernel<2><<<grid, 64, g.smem, st>>>(fa);
-    else xpk::xp_fit_kernel<1><<<grid, 32, g.smem, st>>>(fa);
-    ++g_launches;
-    CK(cudaGetLastError());
+    if (two_class) {
+        Geometry gl;
+        if (int rc = fit_geometry(b->n_groups, b->max_reads, 4, &gl)) return rc;
+        fa.cap = gl.cap; fa.w_begin = nullptr; fa.w_end = ws.n_large; fa.ticket = ws.ticket_large;
+        if (int rc = launch_fit(gl, fa, P, st)) return rc;
+    }
+    Geometry g;
+    if (int rc = fit_geometry(b->n_groups, two_class ? kSplitReads - 1 : b->max_reads, 1, &g)) return rc;
+    fa.cap = g.cap; fa.w_begin = two_class ? ws.n_large : nullptr; fa.w_end = ws.n_work; fa.ticket = ws.ticket;
+    if (int rc = launch_fit(g, fa, P, st)) return rc;
 
     stage_mark(3, st);
     // K4 statistics

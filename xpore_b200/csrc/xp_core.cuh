@@ -39,57 +39,63 @@ struct Comp {
 };
 
 // ---- E-step for one read (gmm.py:236-243) --------------------------------------------------
-// d = ln rho_1 - ln rho_0.  r0 = 1/(1+exp(clip(d,+-500))), r1 = 1-r0 (gmm.py:240-242); here both
-// are formed from t = exp(-|d|) so neither loses relative precision.  hq = r0 ln r0 + r1 ln r1
-// (this read's share of E[ln q(z)], gmm.py:217-219) = -(r_minor |d| + log1p(t)).
+// d = ln rho_1 - ln rho_0.  The reference forms r0 = 1/(1+exp(clip(d,+-500))), r1 = 1-r0
+// (gmm.py:240-242); here t = exp(-|d|), inv = 1/(1+t) is the responsibility of the likelier
+// component and rmin = t inv that of the other one (neither loses relative precision);
+// `pos` (d > 0) says component 1 is the likelier one.  h = -(r0 ln r0 + r1 ln r1) = rmin |d| + log1p(t)
+// is this read's share of -E[ln q(z)] (gmm.py:217-219).
 //
-// Table-driven: exp(x) = 2^m 2^(j/32) e^r with |r| <= ln2/64 (degree-6 Taylor), and
+// Table-driven: exp(x) = 2^m 2^(j/32) e^r with |r| <= ln2/64 (degree-6 series), and
 // ln(1+t) = ln1p(u/c_i - 1) + ln c_i with u = 1+t in [1,2] and c_i the centre of its 1/32-wide
-// interval (degree-7 series, |u/c_i - 1| <= 1/64).  `Tab` supplies the three 32-entry tables:
-// plain arrays on the host, one entry per lane + warp shuffles on the device (no bank conflicts).
+// interval (degree-7 series, |u/c_i - 1| <= 1/64; entry 32 = {1/2, ln 2} serves u == 2).  `Tab`
+// supplies the tables: constant arrays here, [entry][lane] shared-memory columns in xp_fit.cuh
+// (xpk::estep_dev is the same arithmetic with the coefficients held in registers).
 struct HostTab {
     XP_HD double exp2(int j) const { return XPT(kExp2)[j]; }
-    XP_HD double invc(int i) const { return XPT(kInvC)[i]; }
-    XP_HD double logc(int i) const { return XPT(kLogC)[i]; }
+    XP_HD void logc(int i, double& ic, double& lc) const {
+        ic = XPT(kInvC)[i];
+        lc = XPT(kLogC)[i];
+    }
 };
 
 template <class Tab>
-XP_HD void estep_read(const Tab& tab, double d, double& r0, double& r1, double& hq) {
-    const double ad = fabs(d);
-    const double x = -fmin(ad, 500.0);
+XP_HD void estep_read(const Tab& tab, double d, double& inv, double& rmin, double& h, bool& pos) {
+    const int dhi = hi32(d);
+    int ahi = dhi & 0x7fffffff;
+    ahi = ahi < 0x407f4000 ? ahi : 0x407f4000;  // |d| clipped at 500 (low word kept: [500, 500 + 2^-12))
+    const double ax = mk64(ahi, lo32(d));
     const double magic = XPT(kMisc)[5];
-    const double t0 = fma(x, XPT(kE32)[0], magic);
+    const double t0 = fma(-ax, XPT(kE32)[0], magic);
     const double kf = t0 - magic;
-    const int k = (int)(uint32_t)d2u(t0);  // low word of the magic sum = rint(32 x / ln 2), two's complement
-    double r = fma(-kf, XPT(kE32)[1], x);
+    const int k = lo32(t0);  // low word of the magic sum = rint(-32 |d| / ln 2), two's complement
+    double r = fma(-kf, XPT(kE32)[1], -ax);
     r = fma(-kf, XPT(kE32)[2], r);
-    double p = XPT(kE32)[3];                // r^6/720 ... Horner
-    p = fma(p, r, XPT(kE32)[4]);
+    double p = kExpC6;
+    p = fma(p, r, kExpC5);
     p = fma(p, r, XPT(kE32)[5]);
     p = fma(p, r, XPT(kE32)[6]);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     double t = tab.exp2(k & 31) * p;
-    t = u2d(d2u(t) + ((uint64_t)(int64_t)(k >> 5) << 52));  // * 2^m, result stays normal (x >= -500)
-    const double u = 1.0 + t;                               // [1, 2]
-    int i = (int)((d2u(u) - 0x3FF0000000000000ull) >> 47);  // top five mantissa bits; u == 2 gives 32
-    i = i > 31 ? 31 : i;
-    const double rr = fma(u, tab.invc(i), -1.0);
-    double q = XPT(kL1p)[0];
-    q = fma(q, rr, XPT(kL1p)[1]);
+    t = mk64(hi32(t) + (k >> 5) * (1 << 20), lo32(t));  // * 2^m, result stays normal (|d| <= 500)
+    const double u = 1.0 + t;                           // [1, 2]
+    const int i = (hi32(u) - 0x3ff00000) >> 15;         // top five mantissa bits; u == 2 gives 32
+    double ic, lc;
+    tab.logc(i, ic, lc);
+    const double rr = fma(u, ic, -1.0);
+    double q = kLogC7;
+    q = fma(q, rr, kLogC6);
     q = fma(q, rr, XPT(kL1p)[2]);
-    q = fma(q, rr, XPT(kL1p)[3]);
+    q = fma(q, rr, -0.25);
     q = fma(q, rr, XPT(kL1p)[4]);
-    q = fma(q, rr, XPT(kL1p)[5]);
+    q = fma(q, rr, -0.5);
     q = fma(q, rr, 1.0);
-    const double l1p = fma(q, rr, tab.logc(i));  // ln(1+t)
-    const double inv = xrcp(u);
-    const double rmin = t * inv;
-    const bool pos = d > 0.0;
-    r1 = pos ? inv : rmin;
-    r0 = pos ? rmin : inv;
-    hq = -fma(rmin, ad, l1p);
+    const double l1p = fma(q, rr, lc);  // ln(1+t)
+    inv = xrcp3(u);
+    rmin = t * inv;
+    pos = dhi >= 0;  // d == +-0 gives inv == rmin == 1/2 either way
+    h = fma(rmin, fabs(d), l1p);
 }
 
 // ---- M-step for one component (gmm.py:364-370 in centred moments) ------------------------

@@ -1,0 +1,643 @@
+// xp_fit.cuh — K3: variational EM of the two-component mixture (gmm.py:11-127) on sm_100a.
+//
+// Work unit = one position.  A *team* of TW warps owns one position at a time (TW = 1: one warp per
+// position, the common case; TW = 4: high-coverage positions whose reads would not leave room for
+// enough resident warps otherwise).  A CTA holds several teams; every team pulls tickets from a
+// global worklist (longest positions first), so ragged convergence (2...300+ sweeps) never idles an SM.
+//
+// Per position:
+//   1. one TMA bulk copy (cp.async.bulk + mbarrier) lands the position's reads in the team's slab;
+//      they are decoded / centred on the k-mer mean in place and stay resident for all sweeps;
+//   2. initial locations by an exact MSD radix select (np.percentile, gmm.py:39-44);
+//   3. sweeps.  The team leader (warp 0 of the team) runs the O(G) scalar phase — psi / lgamma of the
+//      2G+2 posterior parameters spread over lanes, ELBO from sufficient statistics, stopping rule
+//      (gmm.py:110-123), M-step — keeping component k in the lanes of parity k; all warps of the team
+//      run the E-step over their share of the resident reads (two reads per lane per trip).
+//
+// E-step bookkeeping: only component 0 is accumulated per read (N_g0, S1_0, S2_0 and the entropy);
+// component 1 follows from the per-position totals because r_n1 = 1 - r_n0 (gmm.py:242):
+//   N_g1 = n_g - N_g0,  S1_1 = sum y' - S1_0,  S2_1 = sum y'^2 - S2_0.
+// The 32/33-entry exp / log tables live in shared memory as table[entry][lane] (one column per lane:
+// any combination of per-lane indices is bank-conflict free).
+//
+// CTA shared memory:  [ exp2 table 32x32 f64 | {1/c, ln c} table 33x32 double2 | team 0 | team 1 | ... ]
+// team region (doubles unless noted):
+//   slab[cap+2]        centred reads y' (TMA destination; +2 = 16-byte alignment slack)
+//   scratch[R x RS]    R = G+3 rows (N_g0 per group, S1_0, S2_0, entropy), RS = 32 TW + 1 columns:
+//                      per-lane partials of the current sweep; doubles as the 256-bin select histogram
+//   tot[G+4]           row totals
+//   Asm[G]             per-group constant of d_n
+//   sc[8]              psi(alpha_k), lgamma(alpha_k), ln beta_k, ln lambda_k published by their lanes
+//   bc[8]              leader -> team broadcast: B, C, continue flag, ticket, reduction slots
+//   goff[G+1] (int), mbar (u64), gid[cap+2] (u8: group slot of every read)
+#pragma once
+#include <cuda_runtime.h>
+
+namespace xpk {
+
+struct FitArgs {
+    const void* y;
+    int y_format;
+    double y_scale;
+    const int64_t* read_off;
+    const int32_t* grp_len;
+    const double* kmer_mean;
+    const double* kmer_std;
+    const int32_t* worklist;   // null => identity
+    const uint32_t* w_begin;   // device: first worklist entry of this launch (null => 0)
+    const uint32_t* w_end;     // device: one past the last worklist entry of this launch
+    unsigned int* ticket;      // zeroed before launch
+    int G, max_iters, cap;
+    double stopping, conc0, lg_prior_w;  // lg_prior_w = lgamma(2 c0) - 2 lgamma(c0)
+    double* fit;
+    int32_t* n_iter;
+    uint32_t* status;
+};
+
+constexpr int kTabExpDoubles = 32 * 32;
+constexpr int kTabLogDoubles = 33 * 32 * 2;
+constexpr size_t kFitTableBytes = (size_t)(kTabExpDoubles + kTabLogDoubles) * 8;
+
+__host__ __device__ inline int fit_rows(int G) { return G + 3; }
+__host__ __device__ inline size_t fit_scratch_doubles(int G, int TW) {
+    const size_t s = (size_t)fit_rows(G) * (32 * TW + 1);
+    return s > 128 ? s : 128;  // >= 1 KB: the radix-select histogram lives here before the first sweep
+}
+__host__ __device__ inline size_t fit_team_smem_bytes(int cap, int G, int TW) {
+    const size_t doubles = (size_t)(cap + 2) + fit_scratch_doubles(G, TW) + (G + 4) + G + 8 + 8;
+    const size_t bytes = doubles * 8 + (size_t)((G + 2) & ~1) * 4 + 8 + (size_t)(cap + 2);
+    return (bytes + 15) & ~(size_t)15;
+}
+
+// shared-memory tables, one column per lane
+struct SmemTab {
+    const double* e2;
+    const double2* lg;
+    __device__ __forceinline__ double exp2(int j) const { return e2[j * 32]; }
+    __device__ __forceinline__ void logc(int i, double& ic, double& lc) const {
+        const double2 v = lg[i * 32];
+        ic = v.x;
+        lc = v.y;
+    }
+};
+
+template <int TW>
+__device__ __forceinline__ void team_sync(int team) {
+    if (TW == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TW * 32) : "memory");
+}
+
+// Order statistics sorted[r] and sorted[min(r+1, n-1)] of the n doubles in shared memory by an MSD
+// radix select over the order-preserving 64-bit keys: 8-bit digits, 256-bin histogram (shared-memory
+// integer atomics by the whole team), starting below the common prefix of the smallest and largest
+// key and stopping as soon as one candidate is left.  Exact for any input.  Every warp of the team
+// runs the (cheap) scan redundantly, so no broadcast is needed.
+template <int TW>
+__device__ void team_select2(const double* yv, int n, int r, uint64_t kmin, uint64_t kmax, int* hist, int lane,
+                             int tid, int team, double& a, double& b) {
+    const uint64_t diff = kmin ^ kmax;
+    int hi = diff ? 64 - __clzll((long long)diff) : 0;  // bits [hi,64) are common to every key
+    uint64_t pre = (hi >= 64) ? 0ull : (kmin >> hi);    // value of the fixed bits
+    int rank = r, cnt = n;
+    while (hi > 0 && cnt > 1) {
+        const int lo = hi > 8 ? hi - 8 : 0;
+        const unsigned mask = (1u << (hi - lo)) - 1u;
+        for (int j = tid; j < 256; j += TW * 32) hist[j] = 0;
+        team_sync<TW>(team);
+        for (int i = tid; i < n; i += TW * 32) {
+            const uint64_t k = dkey(yv[i]);
+            if (hi >= 64 || (k >> hi) == pre) atomicAdd(&hist[(unsigned)(k >> lo) & mask], 1);
+        }
+        team_sync<TW>(team);
+        int h[8], s = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            h[j] = hist[lane * 8 + j];
+            s += h[j];
+        }
+        int incl = s;
+#pragma unroll
+        for (int m = 1; m < 32; m <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, m);
+            if (lane >= m) incl += v;
+        }
+        const unsigned bal = __ballot_sync(kFull, incl > rank);
+        const int L = __ffs(bal) - 1;  // lane whose bins hold the wanted rank
+        int below = incl - s, d = 0, c = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (c == 0) {
+                if (below + h[j] > rank) {
+                    d = j;
+                    c = h[j];
+                } else below += h[j];
+            }
+        }
+        d = __shfl_sync(kFull, lane * 8 + d, L);
+        below = __shfl_sync(kFull, below, L);
+        cnt = __shfl_sync(kFull, c, L);
+        rank -= below;
+        pre = (hi >= 64) ? (uint64_t)d : ((pre << (hi - lo)) | (uint64_t)d);
+        hi = lo;
+        team_sync<TW>(team);  // everybody has read the histogram before it is cleared again
+    }
+    uint64_t ka;
+    if (hi == 0) ka = pre;
+    else {  // one candidate left: fetch it
+        uint64_t found = 0;
+        for (int i = lane; i < n; i += 32) {
+            const uint64_t k = dkey(yv[i]);
+            if ((k >> hi) == pre) found = k;
+        }
+        ka = warp_max_u64(found);
+    }
+    a = keyd(ka);
+    b = a;
+    if (r + 1 < n && !(hi == 0 && rank + 1 < cnt)) {
+        uint64_t mn = ~0ull;
+        for (int i = lane; i < n; i += 32) {
+            const uint64_t k = dkey(yv[i]);
+            if (k > ka && k < mn) mn = k;
+        }
+        b = keyd(warp_min_u64(mn));
+    }
+}
+
+template <int TW>
+__device__ double team_percentile(const double* yv, int n, double q, uint64_t kmin, uint64_t kmax, int* hist,
+                                  int lane, int tid, int team) {
+    int lo, hi;
+    double gamma;
+    percentile_index(n, q, lo, hi, gamma);
+    double a, b;
+    team_select2<TW>(yv, n, lo, kmin, kmax, hist, lane, tid, team, a, b);
+    return np_lerp(a, b, gamma);
+}
+
+// The constants of the E-step kept in registers across a sweep.
+struct EConst {
+    double a32, lhi, llo, c4, c3, l5, l3;
+    __device__ __forceinline__ void load() {
+        a32 = XPT(kE32)[0];
+        lhi = XPT(kE32)[1];
+        llo = XPT(kE32)[2];
+        c4 = XPT(kE32)[5];
+        c3 = XPT(kE32)[6];
+        l5 = XPT(kL1p)[2];
+        l3 = XPT(kL1p)[4];
+        // opaque to the optimiser: keeps them in registers instead of one constant load per use
+        asm volatile("" : "+d"(a32), "+d"(lhi), "+d"(llo), "+d"(c4), "+d"(c3), "+d"(l5), "+d"(l3));
+    }
+};
+
+// E-step of one read given d (device flavour of xpc::estep_read with the constants in registers).
+__device__ __forceinline__ void estep_dev(const SmemTab& tab, const EConst& K, double d, double& r0, double& h) {
+    const int dhi = __double2hiint(d);
+    int ahi = dhi & 0x7fffffff;
+    ahi = min(ahi, 0x407f4000);  // |d| clipped at 500 (gmm.py:240); low word kept: [500, 500 + 2^-12)
+    const double ax = __hiloint2double(ahi, __double2loint(d));
+    const double magic = 6755399441055744.0;
+    const double t0 = fma(-ax, K.a32, magic);
+    const double kf = t0 - magic;
+    const int k = __double2loint(t0);
+    double r = fma(-kf, K.lhi, -ax);
+    r = fma(-kf, K.llo, r);
+    double p = kExpC6;
+    p = fma(p, r, kExpC5);
+    p = fma(p, r, K.c4);
+    p = fma(p, r, K.c3);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    double t = tab.exp2(k & 31) * p;
+    t = __hiloint2double(__double2hiint(t) + ((k >> 5) << 20), __double2loint(t));
+    const double u = 1.0 + t;
+    const int i = (__double2hiint(u) - 0x3ff00000) >> 15;  // 0..32 (32 only for u == 2)
+    double ic, lc;
+    tab.logc(i, ic, lc);
+    const double rr = fma(u, ic, -1.0);
+    double q = kLogC7;
+    q = fma(q, rr, kLogC6);
+    q = fma(q, rr, K.l5);
+    q = fma(q, rr, -0.25);
+    q = fma(q, rr, K.l3);
+    q = fma(q, rr, -0.5);
+    q = fma(q, rr, 1.0);
+    const double l1p = fma(q, rr, lc);
+    const double inv = xrcp3(u);
+    const double rmin = t * inv;
+    r0 = (dhi >= 0) ? rmin : inv;
+    h = fma(rmin, fabs(d), l1p);
+}
+
+template <int TW, int MAXT>
+__global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int team = warp / TW, tw = warp % TW, tid = tw * 32 + lane;  // tid: thread index inside the team
+    const bool leader = (tw == 0);
+    const int G = a.G;
+    constexpr int RS = 32 * TW + 1;
+    const int R = fit_rows(G);
+
+    double* tab_e2 = reinterpret_cast<double*>(smem_raw);
+    double2* tab_lg = reinterpret_cast<double2*>(tab_e2 + kTabExpDoubles);
+    for (int i = threadIdx.x; i < kTabExpDoubles; i += blockDim.x) tab_e2[i] = XPT(kExp2)[i >> 5];
+    for (int i = threadIdx.x; i < 33 * 32; i += blockDim.x)
+        tab_lg[i] = make_double2(XPT(kInvC)[i >> 5], XPT(kLogC)[i >> 5]);
+    SmemTab tab;
+    tab.e2 = tab_e2 + lane;
+    tab.lg = tab_lg + lane;
+
+    unsigned char* wbase = smem_raw + kFitTableBytes + (size_t)team * fit_team_smem_bytes(a.cap, G, TW);
+    double* slab = reinterpret_cast<double*>(wbase);
+    double* scratch = slab + a.cap + 2;
+    double* tot = scratch + fit_scratch_doubles(G, TW);
+    double* Asm = tot + G + 4;
+    double* sc = Asm + G;
+    double* bc = sc + 8;
+    int* goff = reinterpret_cast<int*>(bc + 8);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(goff + ((G + 2) & ~1));
+    unsigned char* gid = reinterpret_cast<unsigned char*>(mbar + 1);
+
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    const unsigned w_begin = a.w_begin ? *a.w_begin : 0u;
+    const unsigned w_end = *a.w_end;
+    const double conc0 = a.conc0;
+    const int kpar = lane & 1;  // component owned by this lane in the scalar phase
+
+    for (;;) {
+        // ---- next ticket -----------------------------------------------------------------------
+        unsigned w = 0;
+        if (TW == 1) {
+            if (lane == 0) w = atomicAdd(a.ticket, 1u);
+            w = __shfl_sync(kFull, w, 0);
+        } else {
+            if (tid == 0) reinterpret_cast<unsigned*>(bc + 3)[0] = atomicAdd(a.ticket, 1u);
+            team_sync<TW>(team);
+            w = reinterpret_cast<const unsigned*>(bc + 3)[0];
+        }
+        w += w_begin;
+        if (w >= w_end) break;
+        const int p = a.worklist ? a.worklist[w] : (int)w;
+        const int64_t off = a.read_off[p];
+        const int n = (int)(a.read_off[p + 1] - off);
+        if (n > a.cap || n <= 0) {  // cannot happen when the host sized the slab from max_reads
+            if (tid == 0) {
+                a.status[p] |= STATUS_SELECTED;
+                a.n_iter[p] = -1;
+            }
+            continue;
+        }
+        // ---- stage the reads: one TMA bulk copy of the 16-byte aligned superset -------------------
+        const int fmt = a.y_format;
+        const int eb = y_elem_bytes(fmt);
+        const int per16 = 16 / eb;                         // elements per 16 bytes
+        const int sh = (int)(off & (per16 - 1));           // elements in front of this position
+        const uint32_t bytes = (uint32_t)(((n + sh) * eb + 15) & ~15);
+        fence_proxy_async();  // order this team's generic-proxy slab accesses before the async-proxy write
+        team_sync<TW>(team);
+        if (tid == 0) {
+            mbar_expect_tx(mbar, bytes);
+            tma_bulk_g2s(slab, reinterpret_cast<const char*>(a.y) + (off - sh) * eb, bytes, mbar);
+        }
+        const double m0 = a.kmer_mean[p];
+        const double sd = a.kmer_std[p];
+        const double tau = 1.0 / (sd * sd);          // diffmod.py:24
+        const double a0 = tau;                       // diffmod.py:40
+        const double b0 = 0.5 * (1.0 / tau);         // diffmod.py:41
+        for (int g = tid; g < G; g += TW * 32) goff[g + 1] = a.grp_len[(size_t)p * G + g];
+        team_sync<TW>(team);
+        if (tid == 0) {
+            int acc = 0;
+            goff[0] = 0;
+            for (int g = 0; g < G; ++g) {
+                acc += goff[g + 1];
+                goff[g + 1] = acc;
+            }
+        }
+        team_sync<TW>(team);
+        {
+            int g = 0, gend = goff[1];
+            for (int i = tid; i < n; i += TW * 32) {
+                while (i >= gend) {
+                    ++g;
+                    gend = goff[g + 1];
+                }
+                gid[i] = (unsigned char)g;
+            }
+        }
+        // per-position constants (leader): lgamma(sum_k c_gk) of the present groups, lgamma(a0)
+        double Kconst = 0.0, prior_gamma = 0.0;
+        if (leader) {
+            double kpart = 0.0, lga0 = 0.0;
+            for (int s = lane; s <= G; s += 32) {
+                double ps, lg;
+                if (s < G) {
+                    const int ng = goff[s + 1] - goff[s];
+                    psi_lgamma(2.0 * conc0 + (double)ng, &ps, &lg);
+                    if (ng > 0) kpart += a.lg_prior_w - lg;  // lnC(prior_g) - lgamma(sum_k c_gk)
+                } else {
+                    psi_lgamma(a0, &ps, &lg);
+                    lga0 = lg;
+                }
+            }
+            Kconst = warp_sum(kpart);
+            lga0 = __shfl_sync(kFull, lga0, G & 31);
+            prior_gamma = a0 * xlog(b0) - lga0;  // a0 ln b0 - lgamma(a0)   (gmm.py:334)
+        }
+
+        mbar_wait(mbar, parity);
+        parity ^= 1u;
+        // decode (scaled integers expand in place, last step first so no unread raw bytes are
+        // overwritten), centre on the k-mer mean; totals and min/max keys on the way
+        double* yv = slab + (fmt == kYF64 ? sh : 0);
+        const double rscale = 1.0 / a.y_scale;
+        uint64_t kmin = ~0ull, kmax = 0ull;
+        double T1 = 0.0, T2 = 0.0;
+        constexpr int TT = TW * 32;
+        for (int i0 = ((n - 1) / TT) * TT; i0 >= 0; i0 -= TT) {
+            const int i = i0 + tid;
+            double v = 0.0;
+            if (i < n) {
+                if (fmt == kYF64) v = yv[i];
+                else if (fmt == kYI32) v = y_decode((double)reinterpret_cast<const int*>(slab)[sh + i], a.y_scale, rscale);
+                else v = y_decode((double)reinterpret_cast<const unsigned short*>(slab)[sh + i], a.y_scale, rscale);
+                v -= m0;
+            }
+            team_sync<TW>(team);
+            if (i < n) {
+                yv[i] = v;
+                const uint64_t k = dkey(v);
+                kmin = k < kmin ? k : kmin;
+                kmax = k > kmax ? k : kmax;
+                T1 += v;
+                T2 = fma(v, v, T2);
+            }
+        }
+        kmin = warp_min_u64(kmin);
+        kmax = warp_max_u64(kmax);
+        T1 = warp_sum(T1);
+        T2 = warp_sum(T2);
+        if (TW > 1) {  // combine the warps of the team (fixed order: deterministic)
+            uint64_t* sk = reinterpret_cast<uint64_t*>(scratch);
+            if (lane == 0) {
+                sk[tw] = kmin;
+                sk[TW + tw] = kmax;
+                scratch[2 * TW + tw] = T1;
+                scratch[3 * TW + tw] = T2;
+            }
+            team_sync<TW>(team);
+            kmin = sk[0];
+            kmax = sk[TW];
+            T1 = scratch[2 * TW];
+            T2 = scratch[3 * TW];
+#pragma unroll
+            for (int j = 1; j < TW; ++j) {
+                kmin = sk[j] < kmin ? sk[j] : kmin;
+                kmax = sk[TW + j] > kmax ? sk[TW + j] : kmax;
+                T1 += scratch[2 * TW + j];
+                T2 += scratch[3 * TW + j];
+            }
+        }
+        team_sync<TW>(team);
+        // ---- initial locations (gmm.py:39-44) -------------------------------------------------------
+        int* hist = reinterpret_cast<int*>(scratch);  // scratch is idle until the first sweep
+        const double med = team_percentile<TW>(yv, n, 0.5, kmin, kmax, hist, lane, tid, team);
+        const double loc1 = team_percentile<TW>(yv, n, (0.0 < med) ? 0.75 : 0.25, kmin, kmax, hist, lane, tid, team);
+        team_sync<TW>(team);
+
+        // ---- leader state: lanes of parity k hold component k ---------------------------------------
+        Comp c = mstep(0.0, 0.0, 0.0, a0, b0);
+        if (kpar) c.mp = loc1;
+        double Nk = 0.0, S1k = 0.0, S2k = 0.0, Hent = 0.0;
+        double elbo_old = -INFINITY, elbo = -INFINITY;
+        int it = 0;
+        uint32_t st = STATUS_SELECTED;
+        if (leader)
+            for (int s = lane; s < G; s += 32) tot[s] = 0.0;  // N_g0 = 0: c_gk = c0 at the first scalar phase
+        // first sweep: component 1 has N = 0 too (q(w) starts at the prior, gmm.py:66) -> handled below
+        bool first = true;
+        __syncwarp();
+
+        for (;;) {
+            bool go = true;
+            if (leader) {
+                // ---- scalar phase: special functions spread over lanes, one uniform code path ----
+                // slots: [0,2G) c_gk -> psi, lgamma;  2G+k alpha_k -> psi, lgamma;
+                //        2G+2+k -> ln beta_k;  2G+4+k -> ln lambda_k       (slot parity = component)
+                double e_loc = 0.0;
+                for (int s0 = 0; s0 < 2 * G + 6; s0 += 32) {
+                    const int s = s0 + lane;
+                    const int role = (s < 2 * G) ? 0 : (s < 2 * G + 2) ? 1 : (s < 2 * G + 6) ? 2 : 3;
+                    double x = 16.0;
+                    bool present = false;
+                    if (role == 0) {
+                        const int g = s >> 1;
+                        const int ng = goff[g + 1] - goff[g];
+                        const double v = tot[g];
+                        present = ng > 0;
+                        x = conc0 + ((kpar && !first) ? ((double)ng - v) : v);
+                    } else if (role == 1) x = c.alpha;
+                    else if (role == 2) x = (s < 2 * G + 4) ? c.beta : c.lam;
+                    double z, num, den;
+                    shift_to_10(role == 2 ? 16.0 : x, z, num, den);
+                    if (role == 2) z = x;
+                    const double lz = xlog(z), lden = xlog(den);
+                    const double q = xrcp(z * den);
+                    double ps, lg;
+                    psi_lgamma_finish(z, lz, lden, q * den, num * (q * z), &ps, &lg);
+                    const double pso = __shfl_xor_sync(kFull, ps, 1);
+                    if (role == 0) {
+                        if (kpar) Asm[s >> 1] = ps - pso;  // psi(c_g1) - psi(c_g0)  (gmm.py:283-284)
+                        if (present) e_loc += lg;          // + sum_k lgamma(c_gk)
+                    } else if (role == 1) {
+                        sc[kpar] = ps;
+                        sc[2 + kpar] = lg;
+                    } else if (role == 2) {
+                        sc[4 + (s - 2 * G - 2)] = lz;
+                    }
+                }
+                __syncwarp();
+                double tb, lt;
+                const double ek = elbo_component(c, Nk, S1k, S2k, a0, b0, prior_gamma, sc[kpar], sc[2 + kpar],
+                                                 sc[4 + kpar], sc[6 + kpar], tb, lt);
+                if (lane < 2) e_loc += ek;
+                elbo = warp_sum(e_loc) + Kconst + Hent;
+                if (it >= 1) {
+                    const int rule = stop_rule(elbo, elbo_old, a.stopping);
+                    if (rule == 2) {
+                        st |= STATUS_ELBO_DECREASED;
+                        go = false;
+                    } else {
+                        elbo_old = elbo;
+                        if (rule == 1) {
+                            st |= STATUS_CONVERGED;
+                            go = false;
+                        }
+                    }
+                }
+                if (go && it >= a.max_iters - 1) {
+                    if (it >= 1) st |= STATUS_HIT_MAX;
+                    go = false;
+                }
+                if (go) {
+                    ++it;
+                    // coefficients of d_n = A_g + y'(B + C y'): every term is (component 1) - (component 0)
+                    const double u = tb * c.mp;
+                    const double wq = lt - c.il - u * c.mp;
+                    const double uo = __shfl_xor_sync(kFull, u, 1);
+                    const double tbo = __shfl_xor_sync(kFull, tb, 1);
+                    const double wo = __shfl_xor_sync(kFull, wq, 1);
+                    const double B = kpar ? (u - uo) : (uo - u);
+                    const double C = -0.5 * (kpar ? (tb - tbo) : (tbo - tb));
+                    const double base = 0.5 * (kpar ? (wq - wo) : (wo - wq));
+                    for (int g = lane; g < G; g += 32) Asm[g] += base;
+                    if (lane == 0) {
+                        bc[0] = B;
+                        bc[1] = C;
+                    }
+                }
+                if (lane == 0) bc[2] = go ? 1.0 : 0.0;
+            }
+            team_sync<TW>(team);
+            if (TW > 1) go = bc[2] != 0.0;
+            if (!go) break;
+            first = false;
+            const double B = bc[0], C = bc[1];
+            // ---- E-step + component-0 moments: one pass over the resident reads ------------------
+            const int col = tw * 32 + lane;
+            for (int g = 0; g < G; ++g) scratch[g * RS + col] = 0.0;
+            double accN = 0.0, S1 = 0.0, S2 = 0.0, Hh = 0.0;
+            {
+                EConst K;
+                K.load();
+                int gcur = gid[lane < n ? lane : 0];
+                const int nfull = n >> 6;
+                for (int trip = tw; trip < nfull; trip += TW) {
+                    const int i = (trip << 6) + lane;
+                    const int g0 = gid[i], g1 = gid[i + 32];
+                    const double ya = yv[i], yb = yv[i + 32];
+                    const double da = fma(ya, fma(C, ya, B), Asm[g0]);
+                    const double db = fma(yb, fma(C, yb, B), Asm[g1]);
+                    double ra, ha, rb, hb;
+                    estep_dev(tab, K, da, ra, ha);
+                    estep_dev(tab, K, db, rb, hb);
+                    if (g1 != gcur) {  // rare: this lane crosses into another group
+                        if (g0 != gcur) {
+                            scratch[gcur * RS + col] = accN;
+                            accN = 0.0;
+                        }
+                        accN += ra;
+                        if (g1 != g0) {
+                            scratch[g0 * RS + col] = accN;
+                            accN = 0.0;
+                        }
+                        accN += rb;
+                        gcur = g1;
+                    } else {
+                        accN += ra;
+                        accN += rb;
+                    }
+                    const double wa = ra * ya, wb = rb * yb;
+                    S1 += wa;
+                    S2 = fma(wa, ya, S2);
+                    S1 += wb;
+                    S2 = fma(wb, yb, S2);
+                    Hh += ha;
+                    Hh += hb;
+                }
+                if ((nfull % TW) == tw) {  // the reads past the last full trip (lanes may diverge here)
+                    for (int i = (nfull << 6) + lane; i < n; i += 32) {
+                        const int g0 = gid[i];
+                        const double ya = yv[i];
+                        const double da = fma(ya, fma(C, ya, B), Asm[g0]);
+                        double ra, ha;
+                        estep_dev(tab, K, da, ra, ha);
+                        if (g0 != gcur) {
+                            scratch[gcur * RS + col] = accN;
+                            accN = 0.0;
+                            gcur = g0;
+                        }
+                        accN += ra;
+                        const double wa = ra * ya;
+                        S1 += wa;
+                        S2 = fma(wa, ya, S2);
+                        Hh += ha;
+                    }
+                    __syncwarp();
+                }
+                scratch[gcur * RS + col] = accN;
+            }
+            scratch[G * RS + col] = S1;
+            scratch[(G + 1) * RS + col] = S2;
+            scratch[(G + 2) * RS + col] = Hh;
+            team_sync<TW>(team);
+            if (leader) {
+                // row sums: `parts` lanes share a row, then combine through shuffles
+                const int parts = (R <= 8) ? 4 : (R <= 16) ? 2 : 1;
+                const int rpp = 32 / parts;  // rows handled per pass
+                constexpr int NC = 32 * TW;
+                for (int r0 = 0; r0 < R; r0 += rpp) {
+                    const int row = r0 + lane % rpp, part = lane / rpp;
+                    double t0 = 0.0, t1 = 0.0;
+                    if (row < R) {
+                        const double* rp = scratch + (size_t)row * RS;
+                        const int len = NC / parts;
+                        const double* q = rp + part * len;
+                        for (int l = 0; l < len; l += 2) {
+                            t0 += q[l];
+                            t1 += q[l + 1];
+                        }
+                    }
+                    double t = t0 + t1;
+                    if (parts >= 2) t += __shfl_down_sync(kFull, t, rpp);
+                    if (parts >= 4) {
+                        // lanes [0,rpp) now hold parts 0+1, lanes [2rpp,3rpp) parts 2+3
+                        t += __shfl_down_sync(kFull, t, 2 * rpp);
+                    }
+                    if (row < R && part == 0) tot[row] = t;
+                }
+                __syncwarp();
+                double n0 = 0.0;
+                for (int g = lane; g < G; g += 32) n0 += tot[g];
+                n0 = warp_sum(n0);
+                const double s10 = tot[G], s20 = tot[G + 1];
+                Hent = tot[G + 2];
+                Nk = kpar ? ((double)n - n0) : n0;
+                S1k = kpar ? (T1 - s10) : s10;
+                S2k = kpar ? (T2 - s20) : s20;
+                // ---- M-step (gmm.py:292-294, 364-370) ---------------------------------------------
+                c = mstep(Nk, S1k, S2k, a0, b0);
+            }
+        }
+        // ---- write the fit record ------------------------------------------------------------------
+        if (leader) {
+            double* out = a.fit + (size_t)p * fit_width(G);
+            if (lane < 2) {
+                out[FIT_MU + kpar] = m0 + c.mp;
+                out[FIT_LAM + kpar] = c.lam;
+                out[FIT_ALPHA + kpar] = c.alpha;
+                out[FIT_BETA + kpar] = c.beta;
+            }
+            if (lane == 0) {
+                out[FIT_ELBO] = elbo;
+                a.n_iter[p] = it;
+                a.status[p] = (a.status[p] & STATUS_TTEST_VALID) | st;
+            }
+            for (int s = lane; s < 2 * G; s += 32) {
+                const int g = s >> 1;
+                const double v = tot[g];
+                out[FIT_N + s] = (it == 0) ? 0.0 : (kpar ? (double)(goff[g + 1] - goff[g]) - v : v);
+            }
+        }
+        team_sync<TW>(team);
+    }
+}
+
+}  // namespace xpk

@@ -3,9 +3,9 @@
 //   K1  xp_prefilter_kernel   two-sample t-test per position (statstest.py:4-18)  — HBM streaming
 //   W*  xp_worklist_*         selected positions, longest first (replaces the gene queue,
 //                             scripts/diffmod.py:152-175, helper.py:96-116)
-//   K3  xp_fit_kernel         VB-EM of the 2-component mixture (gmm.py:11-127), one warp per
-//                             position, reads resident in shared memory for all sweeps,
-//                             persistent CTAs pulling tickets from a global worklist
+//   K3  xp_fit_kernel         VB-EM of the 2-component mixture (gmm.py:11-127)  — xp_fit.cuh: one
+//                             warp (or a 4-warp team) per position, reads resident in shared memory
+//                             for all sweeps, persistent CTAs pulling tickets from a global worklist
 //   K4  xp_stats_kernel       cluster assignment, z-tests, overlap, row filter (io.py:255-367)
 //
 // FP64 throughout (the reference is float64 and its stopping rule rounds an ELBO difference at
@@ -48,20 +48,6 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
     }
     return v;
 }
-
-// The E-step lookup tables, one entry per lane, fetched with warp shuffles (every lane of the
-// warp must call together).
-struct LaneTab {
-    double e2, ic, lc;
-    __device__ __forceinline__ void load(int lane) {
-        e2 = XPT(kExp2)[lane];
-        ic = XPT(kInvC)[lane];
-        lc = XPT(kLogC)[lane];
-    }
-    __device__ __forceinline__ double exp2(int j) const { return __shfl_sync(kFull, e2, j); }
-    __device__ __forceinline__ double invc(int i) const { return __shfl_sync(kFull, ic, i); }
-    __device__ __forceinline__ double logc(int i) const { return __shfl_sync(kFull, lc, i); }
-};
 
 // order-preserving map double -> uint64
 __device__ __forceinline__ uint64_t dkey(double x) {
@@ -267,6 +253,8 @@ struct WorklistArgs {
     uint32_t* cursor;    // [kBuckets]
     uint32_t* n_work;    // [1]
     int32_t* worklist;   // [P]
+    uint32_t* n_large;   // [1] entries of the worklist with at least `split` reads (they come first)
+    int split;           // a bucket boundary (see cost_bucket), or 0: no large class
 };
 
 __global__ void xp_worklist_count(WorklistArgs a) {
@@ -295,6 +283,9 @@ __global__ void xp_worklist_scan(WorklistArgs a) {  // <<<1, kBuckets>>>
     }
     a.cursor[t] = s[t] - a.hist[t];  // exclusive start
     if (t == kBuckets - 1) *a.n_work = s[t];
+    if (t == 0) *a.n_large = 0;
+    __syncthreads();
+    if (a.split > 0 && t == cost_bucket(a.split)) *a.n_large = s[t];  // buckets 0..t hold n >= split
 }
 
 __global__ void xp_worklist_scatter(WorklistArgs a) {
@@ -306,496 +297,9 @@ __global__ void xp_worklist_scatter(WorklistArgs a) {
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// K3: variational EM.  One warp owns one position at a time.
-//
-// Per-warp shared memory (doubles unless noted):
-//   slab[cap+2]       centred reads y' (TMA bulk copy lands here; +2 for 16-byte alignment slack)
-//   scratch[2G+5][33] per-lane partials of the current sweep: N_gk rows, then S1_0 S1_1 S2_0 S2_1 Hq
-//                     (33: bank-conflict-free columns); lane s sums row s
-//   Nsm[2G+5]         the row totals: N_gk, then the five moments
-//   lw[2G]            E[ln w_gk] = psi(c_gk) - psi(c_g0 + c_g1)        (gmm.py:283-284)
-//   Asm[G]            per-group constant of d_n
-//   psis[G]           psi(2 c0 + n_g): sum_k c_gk = 2 c0 + n_g is constant over sweeps
-//   sc[8]             psi(alpha_k), lgamma(alpha_k), ln beta_k, ln lambda_k published by their lanes
-//   goff[G+1] (int)   group offsets inside the position
-//   mbar (u64)        TMA completion barrier
-//   gid[cap+2] (u8)   group slot of every read
-// ------------------------------------------------------------------------------------------
-struct FitArgs {
-    const void* y;
-    int y_format;
-    double y_scale;
-    const int64_t* read_off;
-    const int32_t* grp_len;
-    const double* kmer_mean;
-    const double* kmer_std;
-    const int32_t* worklist;   // null => identity
-    const uint32_t* n_work;    // device count of worklist entries
-    unsigned int* ticket;      // zeroed before launch
-    int G, max_iters, cap;
-    double stopping, conc0, lg_prior_w;  // lg_prior_w = lgamma(2 c0) - 2 lgamma(c0)
-    double* fit;
-    int32_t* n_iter;
-    uint32_t* status;
-};
-
-__host__ __device__ inline size_t fit_scratch_doubles(int G) {  // (2G N rows + 5 moment rows) x 33, >= 1 KB histogram
-    return 33 * (size_t)(2 * G + 5) > 128 ? 33 * (size_t)(2 * G + 5) : 128;
-}
-__host__ __device__ inline size_t fit_warp_smem_bytes(int cap, int G) {
-    size_t doubles = (size_t)(cap + 2) + fit_scratch_doubles(G) + (2 * G + 6) + 2 * G + G + G + 8;
-    size_t bytes = doubles * 8 + (size_t)((G + 2) & ~1) * 4 + 8 + (size_t)(cap + 2);  // + gid bytes
-    return (bytes + 15) & ~(size_t)15;
-}
-
-// Order statistics sorted[r] and sorted[min(r+1, n-1)] of the n doubles in shared memory by an
-// MSD radix select over the order-preserving 64-bit keys: 8-bit digits, per-warp 256-bin
-// histogram (shared-memory integer atomics), starting below the common prefix of the smallest
-// and largest key and stopping as soon as one candidate is left.  Exact for any input.
-__device__ void warp_select2(const double* yv, int n, int r, uint64_t kmin, uint64_t kmax, int* hist, int lane,
-                             double& a, double& b) {
-    const uint64_t diff = kmin ^ kmax;
-    int hi = diff ? 64 - __clzll((long long)diff) : 0;  // bits [hi,64) are common to every key
-    uint64_t pre = (hi >= 64) ? 0ull : (kmin >> hi);    // value of the fixed bits
-    int rank = r, cnt = n;
-    while (hi > 0 && cnt > 1) {
-        const int lo = hi > 8 ? hi - 8 : 0;
-        const unsigned mask = (1u << (hi - lo)) - 1u;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) hist[j * 32 + lane] = 0;
-        __syncwarp();
-        for (int i = lane; i < n; i += 32) {
-            const uint64_t k = dkey(yv[i]);
-            if (hi >= 64 || (k >> hi) == pre) atomicAdd(&hist[(unsigned)(k >> lo) & mask], 1);
-        }
-        __syncwarp();
-        int h[8], s = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            h[j] = hist[lane * 8 + j];
-            s += h[j];
-        }
-        int incl = s;
-#pragma unroll
-        for (int m = 1; m < 32; m <<= 1) {
-            const int v = __shfl_up_sync(kFull, incl, m);
-            if (lane >= m) incl += v;
-        }
-        const unsigned bal = __ballot_sync(kFull, incl > rank);
-        const int L = __ffs(bal) - 1;  // lane whose bins hold the wanted rank
-        int below = incl - s, d = 0, c = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (c == 0) {
-                if (below + h[j] > rank) {
-                    d = j;
-                    c = h[j];
-                } else below += h[j];
-            }
-        }
-        d = __shfl_sync(kFull, lane * 8 + d, L);
-        below = __shfl_sync(kFull, below, L);
-        cnt = __shfl_sync(kFull, c, L);
-        rank -= below;
-        pre = (hi >= 64) ? (uint64_t)d : ((pre << (hi - lo)) | (uint64_t)d);
-        hi = lo;
-        __syncwarp();
-    }
-    uint64_t ka;
-    if (hi == 0) ka = pre;
-    else {  // one candidate left: fetch it
-        uint64_t found = 0;
-        for (int i = lane; i < n; i += 32) {
-            const uint64_t k = dkey(yv[i]);
-            if ((k >> hi) == pre) found = k;
-        }
-        ka = warp_max_u64(found);
-    }
-    a = keyd(ka);
-    b = a;
-    if (r + 1 < n && !(hi == 0 && rank + 1 < cnt)) {
-        uint64_t mn = ~0ull;
-        for (int i = lane; i < n; i += 32) {
-            const uint64_t k = dkey(yv[i]);
-            if (k > ka && k < mn) mn = k;
-        }
-        b = keyd(warp_min_u64(mn));
-    }
-}
-
-__device__ double warp_percentile(const double* yv, int n, double q, uint64_t kmin, uint64_t kmax, int* hist,
-                                  int lane) {
-    int lo, hi;
-    double gamma;
-    percentile_index(n, q, lo, hi, gamma);
-    double a, b;
-    warp_select2(yv, n, lo, kmin, kmax, hist, lane, a, b);
-    return np_lerp(a, b, gamma);
-}
-
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) xp_fit_kernel(FitArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int G = a.G;
-    unsigned char* wbase = smem_raw + (size_t)warp * fit_warp_smem_bytes(a.cap, G);
-    double* slab = reinterpret_cast<double*>(wbase);
-    double* scratch = slab + a.cap + 2;
-    double* Nsm = scratch + fit_scratch_doubles(G);
-    double* lw = Nsm + 2 * G + 6;
-    double* Asm = lw + 2 * G;
-    double* psis = Asm + G;
-    double* sc = psis + G;
-    int* goff = reinterpret_cast<int*>(sc + 8);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(goff + ((G + 2) & ~1));
-    unsigned char* gid = reinterpret_cast<unsigned char*>(mbar + 1);  // group slot of every read
-
-    if (lane == 0) {
-        mbar_init(mbar, 1);
-        fence_mbar_init();
-    }
-    __syncwarp();
-    uint32_t parity = 0;
-    LaneTab tab;
-    tab.load(lane);
-    const unsigned n_work = *a.n_work;
-    const double conc0 = a.conc0;
-
-    for (;;) {
-        unsigned w = 0;
-        if (lane == 0) w = atomicAdd(a.ticket, 1u);
-        w = __shfl_sync(kFull, w, 0);
-        if (w >= n_work) break;
-        const int p = a.worklist ? a.worklist[w] : (int)w;
-        const int64_t off = a.read_off[p];
-        const int n = (int)(a.read_off[p + 1] - off);
-        if (n > a.cap || n <= 0) {  // cannot happen when the host sized the slab from max_reads
-            if (lane == 0) {
-                a.status[p] |= STATUS_SELECTED;
-                a.n_iter[p] = -1;
-            }
-            continue;
-        }
-        // ---- stage the reads: one TMA bulk copy of the 16-byte aligned superset -------------
-        const int fmt = a.y_format;
-        const int eb = y_elem_bytes(fmt);
-        const int per16 = 16 / eb;                         // elements per 16 bytes
-        const int sh = (int)(off & (per16 - 1));           // elements in front of this position
-        const uint32_t bytes = (uint32_t)(((n + sh) * eb + 15) & ~15);
-        fence_proxy_async();  // order this warp's generic-proxy slab accesses before the async-proxy write
-        __syncwarp();
-        if (lane == 0) {
-            mbar_expect_tx(mbar, bytes);
-            tma_bulk_g2s(slab, reinterpret_cast<const char*>(a.y) + (off - sh) * eb, bytes, mbar);
-        }
-        const double m0 = a.kmer_mean[p];
-        const double sd = a.kmer_std[p];
-        const double tau = 1.0 / (sd * sd);          // diffmod.py:24
-        const double a0 = tau;                       // diffmod.py:40
-        const double b0 = 0.5 * (1.0 / tau);         // diffmod.py:41
-        for (int g = lane; g < G; g += 32) goff[g + 1] = a.grp_len[(size_t)p * G + g];
-        __syncwarp();
-        if (lane == 0) {
-            int acc = 0;
-            goff[0] = 0;
-            for (int g = 0; g < G; ++g) {
-                acc += goff[g + 1];
-                goff[g + 1] = acc;
-            }
-        }
-        __syncwarp();
-        {
-            int g = 0, gend = goff[1];
-            for (int i = lane; i < n; i += 32) {
-                while (i >= gend) {
-                    ++g;
-                    gend = goff[g + 1];
-                }
-                gid[i] = (unsigned char)g;
-            }
-        }
-        // per-position constants: psi/lgamma of sum_k c_gk, lgamma(a0)   (lane-parallel)
-        double kpart = 0.0, lga0 = 0.0;
-        for (int s = lane; s <= G; s += 32) {
-            double ps, lg;
-            if (s < G) {
-                const int ng = goff[s + 1] - goff[s];
-                psi_lgamma(2.0 * conc0 + (double)ng, &ps, &lg);
-                psis[s] = ps;
-                if (ng > 0) kpart += a.lg_prior_w - lg;  // lnC(prior_g) - lgamma(sum_k c_gk)
-            } else {
-                psi_lgamma(a0, &ps, &lg);
-                lga0 = lg;
-            }
-        }
-        const double Kconst = warp_sum(kpart);
-        lga0 = __shfl_sync(kFull, lga0, G & 31);
-        const double prior_gamma = a0 * xlog(b0) - lga0;  // a0 ln b0 - lgamma(a0)   (gmm.py:334)
-
-        mbar_wait(mbar, parity);
-        parity ^= 1u;
-        // decode (scaled integers expand in place, last 32-read step first so no unread raw bytes
-        // are overwritten), centre on the k-mer mean, track min/max keys for the radix select
-        double* yv = slab + (fmt == kYF64 ? sh : 0);
-        const double rscale = 1.0 / a.y_scale;
-        uint64_t kmin = ~0ull, kmax = 0ull;
-        for (int i0 = ((n - 1) >> 5) << 5; i0 >= 0; i0 -= 32) {
-            const int i = i0 + lane;
-            double v = 0.0;
-            if (i < n) {
-                if (fmt == kYF64) v = yv[i];
-                else if (fmt == kYI32) v = y_decode((double)reinterpret_cast<const int*>(slab)[sh + i], a.y_scale, rscale);
-                else v = y_decode((double)reinterpret_cast<const unsigned short*>(slab)[sh + i], a.y_scale, rscale);
-                v -= m0;
-            }
-            __syncwarp();
-            if (i < n) {
-                yv[i] = v;
-                const uint64_t k = dkey(v);
-                kmin = k < kmin ? k : kmin;
-                kmax = k > kmax ? k : kmax;
-            }
-        }
-        kmin = warp_min_u64(kmin);
-        kmax = warp_max_u64(kmax);
-        __syncwarp();
-        // ---- initial locations (gmm.py:39-44) -------------------------------------------------
-        int* hist = reinterpret_cast<int*>(scratch);  // 256 ints; scratch is idle until the first sweep
-        const double med = warp_percentile(yv, n, 0.5, kmin, kmax, hist, lane);
-        const double loc1 = warp_percentile(yv, n, (0.0 < med) ? 0.75 : 0.25, kmin, kmax, hist, lane);
-
-        for (int s = lane; s < 2 * G; s += 32) Nsm[s] = 0.0;
-        Comp c0 = mstep(0.0, 0.0, 0.0, a0, b0);
-        Comp c1 = c0;
-        c1.mp = loc1;
-        double N0 = 0, N1 = 0, S10 = 0, S11 = 0, S20 = 0, S21 = 0, Hq = 0;
-        double elbo_old = -INFINITY, elbo = -INFINITY;
-        int it = 0;
-        uint32_t st = STATUS_SELECTED;
-        __syncwarp();
-
-        for (;;) {
-            // ---- scalar phase: special functions spread over lanes, one uniform code path --------
-            // slots: [0,2G) c_gk -> psi, lgamma;  2G+k alpha_k -> psi, lgamma;
-            //        2G+2+k -> ln beta_k;  2G+4+k -> ln lambda_k
-            double e_loc = 0.0;
-            for (int s0 = 0; s0 < 2 * G + 6; s0 += 32) {
-                const int s = s0 + lane;
-                const int role = (s < 2 * G) ? 0 : (s < 2 * G + 2) ? 1 : (s < 2 * G + 6) ? 2 : 3;
-                const int k = s & 1;
-                const Comp& c = k ? c1 : c0;
-                double x = 16.0;
-                if (role == 0) x = conc0 + Nsm[s];
-                else if (role == 1) x = c.alpha;
-                else if (role == 2) x = (s < 2 * G + 4) ? c.beta : c.lam;
-                double z, num, den;
-                shift_to_10(role == 2 ? 16.0 : x, z, num, den);
-                if (role == 2) z = x;
-                const double lz = xlog(z), lden = xlog(den);
-                const double q = xrcp(z * den);
-                double ps, lg;
-                psi_lgamma_finish(z, lz, lden, q * den, num * (q * z), &ps, &lg);
-                if (role == 0) {
-                    const int g = s >> 1;
-                    lw[s] = ps - psis[g];
-                    if (goff[g + 1] > goff[g]) e_loc += lg;  // + sum_k lgamma(c_gk)
-                } else if (role == 1) {
-                    sc[k] = ps;
-                    sc[2 + k] = lg;
-                } else if (role == 2) {
-                    sc[4 + (s - 2 * G - 2)] = lz;
-                }
-            }
-            __syncwarp();
-            double tb0, tb1, lt0, lt1;
-            {   // component terms: even lanes take k = 0, odd lanes k = 1
-                const int k = lane & 1;
-                const Comp& c = k ? c1 : c0;
-                double tb, lt;
-                const double ek = elbo_component(c, k ? N1 : N0, k ? S11 : S10, k ? S21 : S20, a0, b0, prior_gamma,
-                                                 sc[k], sc[2 + k], sc[4 + k], sc[6 + k], tb, lt);
-                if (lane < 2) e_loc += ek;
-                const double tbo = __shfl_xor_sync(kFull, tb, 1), lto = __shfl_xor_sync(kFull, lt, 1);
-                tb0 = k ? tbo : tb;
-                tb1 = k ? tb : tbo;
-                lt0 = k ? lto : lt;
-                lt1 = k ? lt : lto;
-            }
-            elbo = warp_sum(e_loc) + Kconst - Hq;
-            if (it >= 1) {
-                const int rule = stop_rule(elbo, elbo_old, a.stopping);
-                if (rule == 2) {
-                    st |= STATUS_ELBO_DECREASED;
-                    break;
-                }
-                elbo_old = elbo;
-                if (rule == 1) {
-                    st |= STATUS_CONVERGED;
-                    break;
-                }
-            }
-            if (it >= a.max_iters - 1) {
-                if (it >= 1) st |= STATUS_HIT_MAX;
-                break;
-            }
-            ++it;
-            // ---- coefficients of d_n = A_g + y'(B + C y') ------------------------------------
-            double base, B, C;
-            estep_coefficients(c0, c1, tb0, tb1, lt0, lt1, base, B, C);
-            for (int g = lane; g < G; g += 32) Asm[g] = base + (lw[2 * g + 1] - lw[2 * g]);
-            for (int s = 0; s < 2 * G; ++s) scratch[s * 33 + lane] = 0.0;
-            __syncwarp();
-            // ---- E-step + moments: one pass over the resident reads, two reads per lane per trip
-            // (two independent exp/log chains in flight).  Trip counts are warp-uniform because the
-            // table lookups are warp shuffles: n/64 full trips, then one masked trip for the rest.
-            double aN0 = 0, aN1 = 0, hq = 0;
-            S10 = S11 = S20 = S21 = 0.0;
-            {
-                int gcur = gid[lane < n ? lane : 0];
-                int i = lane;
-                const int nfull = n >> 6;
-                for (int trip = 0; trip < nfull; ++trip, i += 64) {
-                    const int g0 = gid[i], g1 = gid[i + 32];
-                    const double ya = yv[i], yb = yv[i + 32];
-                    const double da = fma(ya, fma(C, ya, B), Asm[g0]);
-                    const double db = fma(yb, fma(C, yb, B), Asm[g1]);
-                    double ra0, ra1, ha, rb0, rb1, hb;
-                    estep_read(tab, da, ra0, ra1, ha);
-                    estep_read(tab, db, rb0, rb1, hb);
-                    if (g0 != gcur) {
-                        scratch[(2 * gcur) * 33 + lane] = aN0;
-                        scratch[(2 * gcur + 1) * 33 + lane] = aN1;
-                        aN0 = aN1 = 0.0;
-                        gcur = g0;
-                    }
-                    aN0 += ra0;
-                    aN1 += ra1;
-                    if (g1 != gcur) {
-                        scratch[(2 * gcur) * 33 + lane] = aN0;
-                        scratch[(2 * gcur + 1) * 33 + lane] = aN1;
-                        aN0 = aN1 = 0.0;
-                        gcur = g1;
-                    }
-                    aN0 += rb0;
-                    aN1 += rb1;
-                    const double ya2 = ya * ya, yb2 = yb * yb;
-                    S10 = fma(ra0, ya, S10);
-                    S11 = fma(ra1, ya, S11);
-                    S20 = fma(ra0, ya2, S20);
-                    S21 = fma(ra1, ya2, S21);
-                    S10 = fma(rb0, yb, S10);
-                    S11 = fma(rb1, yb, S11);
-                    S20 = fma(rb0, yb2, S20);
-                    S21 = fma(rb1, yb2, S21);
-                    hq += ha + hb;
-                }
-                if (n & 63) {  // masked tail: reads i and i+32 where they exist
-                    const bool va = i < n, vb = i + 32 < n;
-                    const int ia = va ? i : 0, ib = vb ? i + 32 : 0;
-                    const int g0 = gid[ia], g1 = gid[ib];
-                    const double ya = yv[ia], yb = yv[ib];
-                    const double da = fma(ya, fma(C, ya, B), Asm[g0]);
-                    const double db = fma(yb, fma(C, yb, B), Asm[g1]);
-                    double ra0, ra1, ha, rb0, rb1, hb;
-                    estep_read(tab, da, ra0, ra1, ha);
-                    estep_read(tab, db, rb0, rb1, hb);
-                    if (va) {
-                        if (g0 != gcur) {
-                            scratch[(2 * gcur) * 33 + lane] = aN0;
-                            scratch[(2 * gcur + 1) * 33 + lane] = aN1;
-                            aN0 = aN1 = 0.0;
-                            gcur = g0;
-                        }
-                        aN0 += ra0;
-                        aN1 += ra1;
-                        const double ya2 = ya * ya;
-                        S10 = fma(ra0, ya, S10);
-                        S11 = fma(ra1, ya, S11);
-                        S20 = fma(ra0, ya2, S20);
-                        S21 = fma(ra1, ya2, S21);
-                        hq += ha;
-                    }
-                    if (vb) {
-                        if (g1 != gcur) {
-                            scratch[(2 * gcur) * 33 + lane] = aN0;
-                            scratch[(2 * gcur + 1) * 33 + lane] = aN1;
-                            aN0 = aN1 = 0.0;
-                            gcur = g1;
-                        }
-                        aN0 += rb0;
-                        aN1 += rb1;
-                        const double yb2 = yb * yb;
-                        S10 = fma(rb0, yb, S10);
-                        S11 = fma(rb1, yb, S11);
-                        S20 = fma(rb0, yb2, S20);
-                        S21 = fma(rb1, yb2, S21);
-                        hq += hb;
-                    }
-                }
-                scratch[(2 * gcur) * 33 + lane] = aN0;
-                scratch[(2 * gcur + 1) * 33 + lane] = aN1;
-            }
-            {
-                double* mrow = scratch + (size_t)(2 * G) * 33 + lane;
-                mrow[0] = S10;
-                mrow[33] = S11;
-                mrow[66] = S20;
-                mrow[99] = S21;
-                mrow[132] = hq;
-            }
-            __syncwarp();
-            // transpose-reduce through shared memory: lane s owns row s (2G rows of N_gk + 5 moments)
-            for (int s = lane; s < 2 * G + 5; s += 32) {
-                const double* row = scratch + (size_t)s * 33;
-                double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-#pragma unroll
-                for (int l = 0; l < 32; l += 4) {
-                    t0 += row[l];
-                    t1 += row[l + 1];
-                    t2 += row[l + 2];
-                    t3 += row[l + 3];
-                }
-                Nsm[s] = (t0 + t1) + (t2 + t3);
-            }
-            __syncwarp();
-            S10 = Nsm[2 * G];
-            S11 = Nsm[2 * G + 1];
-            S20 = Nsm[2 * G + 2];
-            S21 = Nsm[2 * G + 3];
-            Hq = Nsm[2 * G + 4];
-            {   // N_k = sum_g N_gk: slots of equal parity, butterfly over lane strides 2..16
-                double nk = 0.0;
-                for (int s = lane; s < 2 * G; s += 32) nk += Nsm[s];
-#pragma unroll
-                for (int m = 2; m < 32; m <<= 1) nk += __shfl_xor_sync(kFull, nk, m);
-                const double other = __shfl_xor_sync(kFull, nk, 1);
-                N0 = (lane & 1) ? other : nk;
-                N1 = (lane & 1) ? nk : other;
-            }
-            // ---- M-step (gmm.py:292-294, 364-370) -------------------------------------------
-            c0 = mstep(N0, S10, S20, a0, b0);
-            c1 = mstep(N1, S11, S21, a0, b0);
-        }
-        // ---- write the fit record ------------------------------------------------------------
-        double* out = a.fit + (size_t)p * fit_width(G);
-        if (lane == 0) {
-            out[FIT_MU] = m0 + c0.mp;
-            out[FIT_MU + 1] = m0 + c1.mp;
-            out[FIT_LAM] = c0.lam;
-            out[FIT_LAM + 1] = c1.lam;
-            out[FIT_ALPHA] = c0.alpha;
-            out[FIT_ALPHA + 1] = c1.alpha;
-            out[FIT_BETA] = c0.beta;
-            out[FIT_BETA + 1] = c1.beta;
-            out[FIT_ELBO] = elbo;
-            a.n_iter[p] = it;
-            a.status[p] = (a.status[p] & STATUS_TTEST_VALID) | st;
-        }
-        for (int s = lane; s < 2 * G; s += 32) out[FIT_N + s] = Nsm[s];
-        __syncwarp();
-    }
-}
+}  // namespace xpk
+#include "xp_fit.cuh"  // K3: variational EM
+namespace xpk {
 
 // ------------------------------------------------------------------------------------------
 // K4: statistics, one thread per fitted position.
@@ -886,15 +390,14 @@ __global__ void xp_dfma_peak_kernel(double* out, int iters, double seed) {
 // Special functions as the kernels evaluate them (accuracy tests).
 __global__ void xp_eval_special_kernel(int which, const double* x, const double* aux, double* out, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    LaneTab tab;
-    tab.load(threadIdx.x & 31);
-    const bool valid = i < n;  // whole warps stay alive: the E-step tables are fetched with shuffles
+    const bool valid = i < n;
     const double v = valid ? x[i] : 0.0;
     double r = NAN, ps, lg;
     if (which == 5 || which == 6) {
-        double r0, r1, h;
-        estep_read(tab, v, r0, r1, h);
-        r = (which == 5) ? r1 : h;
+        double inv, rmin, h;
+        bool pos;
+        estep_read(HostTab(), v, inv, rmin, h, pos);
+        r = (which == 5) ? (pos ? inv : rmin) : -h;  // r_n1 ; r0 ln r0 + r1 ln r1
     } else if (valid) {
         switch (which) {
             case 0: psi_lgamma(v, &ps, &lg); r = ps; break;

@@ -59,11 +59,20 @@ XP_TABLE(kMisc, 6, 6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.442
 
 #include "xp_tables.inc"
 // 32/ln2, ln2/32 split hi/lo (hi has 20 trailing zero bits), 1/6!, 1/5!, 1/4!, 1/3!
+// (entries 3, 4 are superseded by kExpC6 / kExpC5 below)
 XP_TABLE(kE32, 7, 46.16624130844683, 0.021660849390173098, 2.3251928472369475e-12,
          1.388888888888889e-03, 8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01)
 // log1p(r) = r (1 + r (c1 + r (c2 + ...))):  1/7 -1/6 1/5 -1/4 1/3 -1/2
 XP_TABLE(kL1p, 6, 1.4285714285714285e-01, -1.6666666666666666e-01, 2.0e-01, -2.5e-01, 3.3333333333333331e-01,
          -5.0e-01)
+
+// The two highest-order coefficients of each E-step series rounded to doubles whose low word is
+// zero: DFMA takes them as 32-bit immediates.  Their rounding (rel. 2^-22) is far below the weight
+// of the terms they multiply (r^5/120 <= 1.2e-12, rr^6/6 <= 2.4e-12 relative to the results).
+constexpr double kExpC6 = 0x1.6c16c00000000p-10;   // ~ 1/720
+constexpr double kExpC5 = 0x1.1111100000000p-7;    // ~ 1/120
+constexpr double kLogC7 = 0x1.2492500000000p-3;    // ~ 1/7
+constexpr double kLogC6 = -0x1.5555500000000p-3;   // ~ -1/6
 
 XP_HD uint64_t d2u(double x) {
 #if defined(__CUDA_ARCH__)
@@ -81,6 +90,29 @@ XP_HD double u2d(uint64_t u) {
     double x;
     memcpy(&x, &u, 8);
     return x;
+#endif
+}
+
+// high / low 32-bit words of a double
+XP_HD int hi32(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(x);
+#else
+    return (int)(uint32_t)(d2u(x) >> 32);
+#endif
+}
+XP_HD int lo32(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2loint(x);
+#else
+    return (int)(uint32_t)d2u(x);
+#endif
+}
+XP_HD double mk64(int hi, int lo) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, lo);
+#else
+    return u2d(((uint64_t)(uint32_t)hi << 32) | (uint64_t)(uint32_t)lo);
 #endif
 }
 
@@ -103,6 +135,20 @@ XP_HD double xrcp(double x) {
     e = fma(-x, y, 1.0);
     y = fma(y, e, y);
     return y;
+#else
+    return 1.0 / x;
+#endif
+}
+
+// 1/x for x in [1, 2].  Device: hardware seed (rel. error <= 2^-20) + one cubic step
+// y (1 + e + e^2), e = 1 - x y  (error e^3, <= 1 ulp).
+XP_HD double xrcp3(double x) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    const double g = fma(e, e, e);
+    return fma(y, g, y);
 #else
     return 1.0 / x;
 #endif
