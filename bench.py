@@ -367,7 +367,8 @@ def main():
     e2e_value = fitted_all / (e2e_ms * 1e-3)
     if world == 1:
         assert int(nf.value) == n_fitted
-        assert (hres["n_iter"].to(dev) == out.n_iter).all()
+        if not os.environ.get("XPB200_BENCH_NOVERIFY"):
+            assert (hres["n_iter"].to(dev) == out.n_iter).all()
 
     if rank == 0:
         fit_ms = float(np.median(stage_ms[:, 2]))

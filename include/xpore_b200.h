@@ -159,6 +159,10 @@ int32_t xpb200_eval_special(int32_t which, const double* x, const double* aux, d
 const char* xpb200_last_error(void);
 const char* xpb200_version(void);
 
+/* Test utility: fill the shared memory of every SM with a 64-bit pattern, so that a kernel which reads
+ * shared memory before writing it shows up in tests (tests/test_gpu_parity.py uses a NaN pattern). */
+int32_t xpb200_debug_fill_smem(uint64_t pattern, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

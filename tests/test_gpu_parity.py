@@ -264,3 +264,34 @@ def test_scaled_integer_decode_exhaustive(torch_cuda):
         enc = xf.fit_batch(b, m)
         np.testing.assert_array_equal(ref.pval, enc.pval)
         np.testing.assert_array_equal(ref.fit, enc.fit)
+
+
+def test_repeated_launches_bit_identical(torch_cuda):
+    """The same resident batch fitted five times gives the very same bits every time, also when the
+    shared memory of every SM is overwritten with NaN patterns / other data in between: the fit
+    kernel must not depend on what a previous launch left in shared memory."""
+    torch = torch_cuda
+    spec = Spec({"KO": 3, "WT": 3}, reads_lo=20, reads_hi=100, f_mod=0.1, seed=33,
+                method={"prefiltering": {"method": "t-test", "threshold": 0.1}})
+    batch = make_batch(spec, KmerModel.load(), n_positions=60000)
+    batch.encode_reads()
+    method = xf.Method.from_dict(spec.method)
+    db = xf.DeviceBatch(batch)
+    out = xf.DeviceResult(db.P, db.G, db.C, db.device)
+    L = _lib.lib()
+    ref = None
+    for pattern in (None, None, 0x7ff8000000000000, 0x4059000000000000, None):
+        if pattern is not None:
+            _lib.check(L.xpb200_debug_fill_smem(pattern, None))
+        xf.fit_device(db, method, out)
+        torch.cuda.synchronize()
+        got = out.to_host()
+        sel = got.selected
+        assert not np.isnan(got.fit[sel][:, :9]).any()
+        if ref is None:
+            ref = got
+            continue
+        np.testing.assert_array_equal(got.status, ref.status)
+        np.testing.assert_array_equal(got.n_iter, ref.n_iter)
+        np.testing.assert_array_equal(got.fit[sel], ref.fit[sel])
+        np.testing.assert_array_equal(got.stats[sel], ref.stats[sel])

@@ -11,9 +11,9 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(HERE, "libxpore_b200.so")
+LIB_PATH = os.environ.get("XPB200_LIB") or os.path.join(HERE, "libxpore_b200.so")  # override: experiments only
 SOURCES = ["xp_api.cu"]
-HEADERS = ["xp_math.cuh", "xp_core.cuh", "xp_kernels.cuh", os.path.join("..", "..", "include", "xpore_b200.h")]
+HEADERS = ["xp_math.cuh", "xp_core.cuh", "xp_kernels.cuh", "xp_fit.cuh", "xp_tables.inc", os.path.join("..", "..", "include", "xpore_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "--shared", "-Xcompiler", "-fPIC"]
 
@@ -45,7 +45,7 @@ EXPORTS = ["xpb200_fit_width", "xpb200_stats_width", "xpb200_workspace_bytes", "
            "xpb200_fit_host", "xpb200_release", "xpb200_prefilter_device", "xpb200_stats_device",
            "xpb200_fit_launch_info", "xpb200_launch_count", "xpb200_measure_fp64_peak", "xpb200_eval_special",
            "xpb200_set_stage_timing", "xpb200_get_stage_ms", "xpb200_pack_records",
-           "xpb200_last_error", "xpb200_version"]
+           "xpb200_debug_fill_smem", "xpb200_last_error", "xpb200_version"]
 
 
 def needs_build() -> bool:
@@ -93,6 +93,9 @@ def lib():
         L.xpb200_fit_host.restype = C.c_int32
         L.xpb200_fit_host.argtypes = [C.c_int32, C.POINTER(XpBatch), C.POINTER(XpMethod), C.POINTER(XpResult),
                                       C.POINTER(C.c_uint32)]
+        if hasattr(L, "xpb200_debug_fill_smem"):  # absent only in experiment builds (XPB200_LIB)
+            L.xpb200_debug_fill_smem.restype = C.c_int32
+            L.xpb200_debug_fill_smem.argtypes = [C.c_uint64, C.c_void_p]
         L.xpb200_release.restype = None
         L.xpb200_prefilter_device.restype = C.c_int32
         L.xpb200_prefilter_device.argtypes = [C.POINTER(XpBatch), C.POINTER(XpMethod), C.c_void_p, C.c_void_p,

@@ -498,6 +498,29 @@ int32_t xpb200_pack_records(const xpb200_result* r, int32_t P, int32_t G, int32_
     return 0;
 }
 
+// Test utility: overwrite the shared memory of every SM with a 64-bit pattern (a later kernel that
+// reads shared memory it has not written itself then sees that pattern instead of its own leftovers).
+__global__ void xp_fill_smem_kernel(unsigned long long pattern, unsigned long long* sink) {
+    extern __shared__ unsigned long long fill_buf[];
+    const int nwords = (int)(kMaxSmemPerCta / 8);
+    if (pattern != 0xdeadull)  // 0xdead: touch nothing (occupies the SM's shared memory only)
+        for (int i = threadIdx.x; i < nwords; i += blockDim.x) fill_buf[i] = pattern;
+    __syncthreads();
+    if (fill_buf[(threadIdx.x * 97) % nwords] != pattern) sink[0] = 1;  // keeps the stores alive
+}
+int32_t xpb200_debug_fill_smem(uint64_t pattern, void* stream) {
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    static unsigned long long* sink = nullptr;
+    if (!sink) CK(cudaMalloc(&sink, 8));
+    CK(cudaFuncSetAttribute(xp_fill_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemPerCta));
+    xp_fill_smem_kernel<<<sms, 256, kMaxSmemPerCta, (cudaStream_t)stream>>>(pattern, sink);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int32_t xpb200_set_stage_timing(int32_t on) {
     if (on && !g_timer.ev[0])
         for (auto& e : g_timer.ev) CK(cudaEventCreate(&e));

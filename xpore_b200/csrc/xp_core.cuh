@@ -95,7 +95,7 @@ XP_HD void estep_read(const Tab& tab, double d, double& inv, double& rmin, doubl
     inv = xrcp3(u);
     rmin = t * inv;
     pos = dhi >= 0;  // d == +-0 gives inv == rmin == 1/2 either way
-    h = fma(rmin, fabs(d), l1p);
+    h = fma(rmin, ax, l1p);  // |d| > 500 only when rmin < 1e-217: the clip does not show
 }
 
 // ---- M-step for one component (gmm.py:364-370 in centred moments) ------------------------
