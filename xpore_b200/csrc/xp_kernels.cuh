@@ -89,10 +89,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K1: prefilter t-test.  One warp per tile of 32 consecutive positions: the warp streams each
-// position's reads (coalesced 8-byte loads), reduces the centred moments of the two present
-// conditions, lane j keeps position j's moments; then all 32 lanes evaluate their Student-t
-// p-value in parallel.
+// K1: prefilter t-test (statstest.py:4-21; the gate is scripts/diffmod.py:52-58).
 // ------------------------------------------------------------------------------------------
 // Decode of the scaled-integer read formats: y = q / scale, correctly rounded, without a division
 // instruction sequence.  With rs = RN(1/scale):  a = q*rs;  r = fma(-a, scale, q) (exact residual);
@@ -126,96 +123,148 @@ struct PrefilterArgs {
     double* pval;      // [P]
 };
 
+// One warp owns a tile of 32 consecutive positions.  Four lanes share one position (8 positions in
+// flight per warp, four rounds per tile): they stream its reads in 8-read blocks (one aligned
+// 16-byte load per block for the u16 format, two blocks ahead), walk the group boundaries to know
+// which condition a read belongs to, and keep the centred moments (n, sum y', sum y'^2) of the two
+// conditions present.  A two-step shuffle reduction over the four lanes and one shuffle hand the
+// moments of position j to lane j; after the four rounds all 32 lanes evaluate their Student-t
+// p-value in parallel.  Fixed summation order: results are deterministic.
+constexpr int kPfLanes = 4;                 // lanes per position
+constexpr int kPfPerRound = 32 / kPfLanes;  // positions per round
+
+struct PfMoments {
+    double s1a, s2a, s1b, s2b;
+    int na, nb;
+};
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) xp_prefilter_kernel(PrefilterArgs a) {
-    __shared__ int s_off[WARPS][kMaxGroups + 1];
-    __shared__ signed char s_side[WARPS][kMaxGroups];  // 0 -> first condition, 1 -> second
+    __shared__ int s_cond[kMaxGroups];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = a.G;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) s_cond[g] = a.grp_cond[g];
+    __syncthreads();
     const int tile = blockIdx.x * WARPS + warp;
     const int p0 = tile * 32;
     if (p0 >= a.P) return;
-    const int G = a.G;
-    int* goff = s_off[warp];
-    signed char* side = s_side[warp];
+    const int sub = lane / kPfLanes, sl = lane % kPfLanes;
+    const double rscale = 1.0 / a.y_scale;
 
     double k_na = 0, k_s1a = 0, k_s2a = 0, k_nb = 0, k_s1b = 0, k_s2b = 0;
     bool k_valid = false;
-    const int pend = min(32, a.P - p0);
-    for (int j = 0; j < pend; ++j) {
-        const int p = p0 + j;
-        const int64_t off = a.read_off[p];
-        const int n = (int)(a.read_off[p + 1] - off);
-        const double m0 = a.kmer_mean[p];
-        // conditions present at this position
-        unsigned cmask = 0;
-        for (int g = lane; g < G; g += 32) {
-            const int len = a.grp_len[(size_t)p * G + g];
-            goff[g + 1] = len;
-            if (len > 0) cmask |= 1u << a.grp_cond[g];
-        }
-        cmask = __reduce_or_sync(kFull, cmask);
-        const bool valid = a.enabled && (__popc(cmask) == 2);
-        __syncwarp();
-        if (valid) {
-            const int ca = __ffs(cmask) - 1;
-            if (lane == 0) {
-                int acc = 0;
-                goff[0] = 0;
-                for (int g = 0; g < G; ++g) {
-                    acc += goff[g + 1];
-                    goff[g + 1] = acc;
-                }
-            }
-            for (int g = lane; g < G; g += 32) side[g] = (a.grp_cond[g] == ca) ? 0 : 1;
-            __syncwarp();
-            double s1a = 0, s2a = 0, s1b = 0, s2b = 0;
-            int na = 0, nb = 0;
-            int g = 0, gend = goff[1];
-            const double rscale = 1.0 / a.y_scale;
-            for (int base = 0; base < n; base += 128) {  // four loads in flight per lane
-                double v[4];
+    for (int round = 0; round < kPfLanes; ++round) {
+        const int p = p0 + round * kPfPerRound + sub;
+        PfMoments m = {0.0, 0.0, 0.0, 0.0, 0, 0};
+        bool valid = false;
+        if (p < a.P) {
+            const int64_t off = a.read_off[p];
+            const int n = (int)(a.read_off[p + 1] - off);
+            const double m0 = a.kmer_mean[p];
+            const int32_t* glen = a.grp_len + (size_t)p * G;
+            // conditions present at this position; the lower-numbered one is side 0
+            unsigned cmask = 0;
+            for (int g = 0; g < G; ++g)
+                if (glen[g] > 0) cmask |= 1u << s_cond[g];
+            valid = a.enabled && (__popc(cmask) == 2);
+            if (valid) {
+                const int ca = __ffs(cmask) - 1;
+                int g = 0, gend = glen[0];
+                auto add = [&](double v, int i) {  // read i of the position
+                    while (i >= gend) {
+                        ++g;
+                        gend += glen[g];
+                    }
+                    const double c = v - m0;
+                    if (s_cond[g] == ca) {
+                        m.s1a += c;
+                        m.s2a = fma(c, c, m.s2a);
+                        ++m.na;
+                    } else {
+                        m.s1b += c;
+                        m.s2b = fma(c, c, m.s2b);
+                        ++m.nb;
+                    }
+                };
+                // Lane sl takes the 8-read blocks sl, sl+4, ... of the position (position-local, so the
+                // moments depend neither on the read encoding nor on where the position sits in the
+                // buffer).
+                if (a.y_format == kYU16) {
+                    // One 16-byte load per lane and step.  The buffer's aligned 16-byte chunk c holds the
+                    // reads [8c - head, 8c - head + 8) of the position, so block b = the tail of chunk b
+                    // + the first `head` reads of chunk b+1, which the next lane of the quad has
+                    // (lane 0's prefetched chunk for lane 3).
+                    const unsigned quad = 0xFu << (lane & ~3);
+                    const int64_t e0 = off & ~(int64_t)7;
+                    const int head = (int)(off - e0), h2 = head >> 1, hs = (head & 1) * 16;
+                    const int nchunk = (head + n + 7) >> 3, nblock = (n + 7) >> 3;
+                    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(a.y) + e0);
+                    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+                    uint4 cur = (sl < nchunk) ? __ldg(src + sl) : zero4;
+                    uint4 nxt = (sl + kPfLanes < nchunk) ? __ldg(src + sl + kPfLanes) : zero4;
+                    for (int b0 = 0; b0 < nblock; b0 += kPfLanes) {
+                        const int bq = b0 + sl;
+                        const uint4 nn = (bq + 2 * kPfLanes < nchunk) ? __ldg(src + bq + 2 * kPfLanes) : zero4;
+                        const uint4 give = (sl == 0) ? nxt : cur;
+                        const int from = (lane & ~3) | ((sl + 1) & 3);
+                        uint4 got;
+                        got.x = __shfl_sync(quad, give.x, from);
+                        got.y = __shfl_sync(quad, give.y, from);
+                        got.z = __shfl_sync(quad, give.z, from);
+                        got.w = __shfl_sync(quad, give.w, from);
+                        // words [h2, h2 + 5) of {cur, got}, then a funnel shift by the odd half-word
+                        unsigned w0 = cur.x, w1 = cur.y, w2 = cur.z, w3 = cur.w, w4 = got.x, w5 = got.y, w6 = got.z,
+                                 w7 = got.w;
+                        if (h2 & 1) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6; w6 = w7; }
+                        if (h2 & 2) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; }
+                        const unsigned x[4] = {__funnelshift_r(w0, w1, hs), __funnelshift_r(w1, w2, hs),
+                                               __funnelshift_r(w2, w3, hs), __funnelshift_r(w3, w4, hs)};
+                        const int ibase = bq << 3;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int i = base + lane + 32 * k;
-                    v[k] = (i < n) ? y_load_global(a.y, a.y_format, a.y_scale, rscale, off + i) : 0.0;
-                }
+                        for (int k = 0; k < 8; ++k) {
+                            const unsigned q = (x[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                            if (ibase + k < n) add(y_decode((double)q, a.y_scale, rscale), ibase + k);
+                        }
+                        cur = nxt;
+                        nxt = nn;
+                    }
+                } else {
+                    for (int c = sl * 8; c < n; c += kPfLanes * 8) {  // 8 independent loads in flight
+                        double v[8];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int i = base + lane + 32 * k;
-                    if (i < n) {
-                        while (i >= gend) {
-                            ++g;
-                            gend = goff[g + 1];
-                        }
-                        const double c = v[k] - m0;
-                        if (side[g] == 0) {
-                            s1a += c;
-                            s2a = fma(c, c, s2a);
-                            ++na;
-                        } else {
-                            s1b += c;
-                            s2b = fma(c, c, s2b);
-                            ++nb;
-                        }
+                        for (int k = 0; k < 8; ++k)
+                            v[k] = (c + k < n) ? y_load_global(a.y, a.y_format, a.y_scale, rscale, off + c + k) : 0.0;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (c + k < n) add(v[k], c + k);
                     }
                 }
             }
-            s1a = warp_sum(s1a);
-            s2a = warp_sum(s2a);
-            s1b = warp_sum(s1b);
-            s2b = warp_sum(s2b);
-            na = __reduce_add_sync(kFull, na);
-            nb = __reduce_add_sync(kFull, nb);
-            if (lane == j) {
-                k_na = na; k_s1a = s1a; k_s2a = s2a;
-                k_nb = nb; k_s1b = s1b; k_s2b = s2b;
-                k_valid = true;
-            }
         }
-        __syncwarp();
+        // the four lanes of a position: fixed-order butterfly
+#pragma unroll
+        for (int d = 1; d < kPfLanes; d <<= 1) {
+            m.s1a += __shfl_xor_sync(kFull, m.s1a, d);
+            m.s2a += __shfl_xor_sync(kFull, m.s2a, d);
+            m.s1b += __shfl_xor_sync(kFull, m.s1b, d);
+            m.s2b += __shfl_xor_sync(kFull, m.s2b, d);
+            m.na += __shfl_xor_sync(kFull, m.na, d);
+            m.nb += __shfl_xor_sync(kFull, m.nb, d);
+        }
+        // position round * 8 + j goes to lane round * 8 + j
+        const int src = ((lane - round * kPfPerRound) & (kPfPerRound - 1)) * kPfLanes;
+        const double t1a = __shfl_sync(kFull, m.s1a, src), t2a = __shfl_sync(kFull, m.s2a, src);
+        const double t1b = __shfl_sync(kFull, m.s1b, src), t2b = __shfl_sync(kFull, m.s2b, src);
+        const int tna = __shfl_sync(kFull, m.na, src), tnb = __shfl_sync(kFull, m.nb, src);
+        const bool tv = __shfl_sync(kFull, (int)valid, src) != 0;
+        if ((lane / kPfPerRound) == round) {
+            k_na = tna; k_s1a = t1a; k_s2a = t2a;
+            k_nb = tnb; k_s1b = t1b; k_s2b = t2b;
+            k_valid = tv;
+        }
     }
-    if (lane < pend) {
-        const int p = p0 + lane;
+    const int p = p0 + lane;
+    if (p < a.P) {
         double pv = NAN;
         uint32_t st = 0;
         if (k_valid) {
