@@ -185,7 +185,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        n_cpu = args.cpu_positions or min(200000, 400 * cores)
+        n_cpu = args.cpu_positions or min(200000, 1600 * cores)  # ~10 s per step on the box's cores
         batch = make_batch(spec, km, n_positions=n_cpu)
         n_cpu = batch.n_positions
         vals = []
@@ -210,7 +210,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # before CUDA is initialised in this process (fork-based pool)
-        n_cpu = args.cpu_positions or min(200000, 800 * cores)
+        n_cpu = args.cpu_positions or min(200000, 2400 * cores)  # ~15 s of CPU work
         cb_batch = make_batch(spec, km, n_positions=n_cpu)
         cpu = cpu_baseline(cb_batch, spec, cb_batch.n_positions, cores)
         del cb_batch
@@ -377,6 +377,17 @@ def main():
         achieved = flops / (fit_ms * 1e-3) / 1e12
         ybytes = {0: 8, 1: 4, 2: 2}[yfmt]
         alg_bytes = sel_reads * ybytes + n_fitted * (8 + 4 * G + 16 + 4) + n_fitted * (fit_w * 8 + 8)
+        # DRAM traffic of the fit kernel per launch from the committed ncu capture of this very workload
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
+                                             "r1_fit_traffic.json"))).get(args.config)
+            yname = {0: "f64", 1: "i32 scaled by 100", 2: "u16 scaled by 100"}[yfmt]
+            if tr and tr["positions_per_gpu"] == db.P and tr["y_format"] == yname:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                traffic_src = "ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch (%s)" % tr["source"]
+        except Exception:
+            pass
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
@@ -412,7 +423,9 @@ def main():
                          "peak_source": "measured here: xpb200_measure_fp64_peak (8 independent DFMA chains per "
                                         "thread, 8 CTAs x 256 threads per SM, best of 5)",
                          "flop_model": "100 flop per read-sweep + (6G+4)*60 per position-sweep (SURVEY.md 8d)",
-                         "ms": fit_ms, "traffic": None,
+                         "ms": fit_ms, "traffic": traffic,
+                         "traffic_source": traffic_src,
+                         "algorithmic_bytes": alg_bytes,
                          "hbm": {"algorithmic_bytes": alg_bytes, "achieved": alg_bytes / (fit_ms * 1e-3) / 1e9,
                                  "peak": hbm_peak, "unit": "GB/s",
                                  "frac": alg_bytes / (fit_ms * 1e-3) / 1e9 / hbm_peak}},
