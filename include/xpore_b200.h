@@ -159,6 +159,32 @@ int32_t xpb200_eval_special(int32_t which, const double* x, const double* aux, d
 const char* xpb200_last_error(void);
 const char* xpb200_version(void);
 
+/* ---- native ingest of dataprep output (host code, no GPU involved) ---------------------------
+ * Replaces, for many genes per call and on several threads, the per-gene Python of the reference:
+ *   xpore/scripts/diffmod.py:156-169  seek / read / ujson.loads of one gene from every run's data.json
+ *   xpore/diffmod/io.py:21-90         load_data(): position selection and read concatenation
+ * and yields the arrays of an xpb200_batch directly.
+ *
+ * open:  one data.json per run (config order).  run_slot[r] = group slot of run r when not pooling,
+ *        run_cond[r] = condition index (rank among the sorted condition names); readcount_min/max are
+ *        the YAML `criteria`; `kmers` are the rows of model_kmer.csv (the output refers to them by row).
+ * genes: starts/ends are [n_genes, n_runs] byte spans from data.index, start = -1 where the run does
+ *        not have the gene.  Parses and selects on `n_threads` threads, keeps the result inside the
+ *        handle and reports its sizes.
+ * copy:  writes the result: y[n_reads] f64, read_off[n_positions+1], grp_len[n_positions*G],
+ *        kmer_row[n_positions], gene_of_position[n_positions] (index into the call's gene list),
+ *        strings = "<position>\0<kmer>\0" per position.  Any pointer but read_off may be NULL.
+ * Positions come out sorted by (int(position), kmer) inside a gene, genes in call order. */
+void* xpb200_ingest_open(int32_t n_runs, const char* const* json_paths, const int32_t* run_slot,
+                         const int32_t* run_cond, int32_t n_groups, int32_t n_conditions, int32_t pooling,
+                         int32_t readcount_min, int32_t readcount_max, int32_t n_kmers, const char* const* kmers);
+int32_t xpb200_ingest_genes(void* handle, int32_t n_genes, const int64_t* starts, const int64_t* ends,
+                            int32_t n_threads, int64_t* n_positions, int64_t* n_reads, int64_t* string_bytes);
+int32_t xpb200_ingest_copy(void* handle, double* y, int64_t* read_off, int32_t* grp_len, int32_t* kmer_row,
+                           int32_t* gene_of_position, char* strings);
+void xpb200_ingest_close(void* handle);
+const char* xpb200_ingest_last_error(void);
+
 /* Test utility: fill the shared memory of every SM with a 64-bit pattern, so that a kernel which reads
  * shared memory before writing it shows up in tests (tests/test_gpu_parity.py uses a NaN pattern). */
 int32_t xpb200_debug_fill_smem(uint64_t pattern, void* stream);

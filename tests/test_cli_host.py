@@ -22,7 +22,7 @@ def emul_fit_fn(batch, method):
 def run_cli(config_path, **kw):
     args = argparse.Namespace(config=config_path, n_processes=kw.get("n_processes", 1), save_models=False,
                               resume=kw.get("resume", False), ids=kw.get("ids", []),
-                              batch_positions=kw.get("batch_positions", 262144))
+                              batch_genes=kw.get("batch_genes", 8192), batch_bytes=kw.get("batch_bytes", 256 << 20))
     xd.diffmod(args, fit_fn=emul_fit_fn)
     out = Configurator(config_path).get_paths()["out_dir"]
     return os.path.join(out, "diffmod.table"), os.path.join(out, "diffmod.log")
@@ -61,7 +61,7 @@ def test_resume_ids_small_batches_and_pool(tmp_path):
     assert set(rows) == set(expected_rows(exp))
     assert len(open(table).read().splitlines()) == len(rows) + 1
     # tiny GPU batches and a 2-process ingest pool give the same table
-    table2, _ = run_cli(case["config_path"], batch_positions=7, n_processes=2)
+    table2, _ = run_cli(case["config_path"], batch_genes=1, n_processes=2)
     _, rows2 = read_table(table2)
     assert rows2 == rows
 

@@ -12,10 +12,10 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.environ.get("XPB200_LIB") or os.path.join(HERE, "libxpore_b200.so")  # override: experiments only
-SOURCES = ["xp_api.cu"]
+SOURCES = ["xp_api.cu", "xp_ingest.cpp"]
 HEADERS = ["xp_math.cuh", "xp_core.cuh", "xp_kernels.cuh", "xp_fit.cuh", "xp_tables.inc", os.path.join("..", "..", "include", "xpore_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-              "--shared", "-Xcompiler", "-fPIC"]
+              "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
 
 
 class XpBatch(C.Structure):
@@ -45,7 +45,9 @@ EXPORTS = ["xpb200_fit_width", "xpb200_stats_width", "xpb200_workspace_bytes", "
            "xpb200_fit_host", "xpb200_release", "xpb200_prefilter_device", "xpb200_stats_device",
            "xpb200_fit_launch_info", "xpb200_launch_count", "xpb200_measure_fp64_peak", "xpb200_eval_special",
            "xpb200_set_stage_timing", "xpb200_get_stage_ms", "xpb200_pack_records",
-           "xpb200_debug_fill_smem", "xpb200_last_error", "xpb200_version"]
+           "xpb200_debug_fill_smem", "xpb200_last_error", "xpb200_version",
+           "xpb200_ingest_open", "xpb200_ingest_genes", "xpb200_ingest_copy", "xpb200_ingest_close",
+           "xpb200_ingest_last_error"]
 
 
 def needs_build() -> bool:
@@ -96,6 +98,17 @@ def lib():
         if hasattr(L, "xpb200_debug_fill_smem"):  # absent only in experiment builds (XPB200_LIB)
             L.xpb200_debug_fill_smem.restype = C.c_int32
             L.xpb200_debug_fill_smem.argtypes = [C.c_uint64, C.c_void_p]
+        L.xpb200_ingest_open.restype = C.c_void_p
+        L.xpb200_ingest_open.argtypes = [C.c_int32, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_char_p)]
+        L.xpb200_ingest_genes.restype = C.c_int32
+        L.xpb200_ingest_genes.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                          C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.xpb200_ingest_copy.restype = C.c_int32
+        L.xpb200_ingest_copy.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.xpb200_ingest_close.restype = None
+        L.xpb200_ingest_close.argtypes = [C.c_void_p]
+        L.xpb200_ingest_last_error.restype = C.c_char_p
         L.xpb200_release.restype = None
         L.xpb200_prefilter_device.restype = C.c_int32
         L.xpb200_prefilter_device.argtypes = [C.POINTER(XpBatch), C.POINTER(XpMethod), C.c_void_p, C.c_void_p,

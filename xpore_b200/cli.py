@@ -22,8 +22,10 @@ def parse_options(argv):
     p.add_argument("--resume", dest="resume", default=False, action="store_true",
                    help="with this argument, the program will resume from the previous run.")
     p.add_argument("--ids", dest="ids", default=[], nargs="*", help="gene or transcript ids to model.")
-    p.add_argument("--batch_positions", dest="batch_positions", type=int, default=262144,
-                   help="positions packed per GPU call.")
+    p.add_argument("--batch_genes", dest="batch_genes", type=int, default=8192,
+                   help="at most this many ids are ingested and fitted per GPU call.")
+    p.add_argument("--batch_bytes", dest="batch_bytes", type=int, default=256 << 20,
+                   help="... or this many bytes of data.json text, whichever comes first.")
     return parser.parse_args(argv[1:])
 
 

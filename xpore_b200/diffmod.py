@@ -3,9 +3,10 @@
 Mirrors ``xpore/scripts/diffmod.py:79-189`` (``diffmod(args)``) at the file level — same YAML,
 same inputs, same ``diffmod.table`` / ``diffmod.log`` (header row, ``--- DIFFMOD ---``, one id per
 line, ``--- SUCCESSFULLY FINISHED ---``), same ``--resume`` / ``--ids`` semantics — but replaces
-the process pool of per-gene workers (``helper.py:96-116``) with "pack many genes -> one C-ABI
-call -> single writer".  ``--n_processes`` sizes the pool that parses JSON and applies the
-position selection on the host; the fit itself always runs on the GPU(s).
+the process pool of per-gene workers (``helper.py:96-116``) with "native ingest of many genes
+(``xpore_b200.ingest``, C++) -> one C-ABI fit call -> single writer".  ``--n_processes`` is the
+number of ingest threads that parse JSON and apply the position selection on the host; the fit
+itself always runs on the GPU(s).
 
 Multi-GPU: launch with ``torchrun``; ids are split into contiguous ranges balanced by their
 ``data.index`` byte spans, every rank fits its range, the fixed-width records of fitted
@@ -14,13 +15,12 @@ positions are gathered on rank 0 (NCCL ``gather``), which writes the table.
 from __future__ import annotations
 
 import csv
-import json
 import os
 from collections import OrderedDict
 
 import numpy as np
 
-from .batch import Batch, BatchBuilder, Layout
+from .batch import Layout
 from .config import Configurator
 from .kmer_model import KmerModel
 from .table import get_result_table_header, result_rows, write_rows
@@ -56,71 +56,6 @@ def get_ids(f_index, data_info):
         for i in ids:
             count[i] = count.get(i, 0) + 1
     return sorted(i for i, c in count.items() if c >= 2)
-
-
-class GeneReader:
-    """Seek + parse one gene from every run (diffmod.py:156-169)."""
-
-    def __init__(self, data_info, f_index):
-        self.data_info = data_info
-        self.f_index = f_index
-        self.handles = {}
-        for cond, runs in data_info.items():
-            for run, d in runs.items():
-                self.handles[run] = open(os.path.join(d, "data.json"), "r")
-
-    def read(self, idx):
-        dd = OrderedDict()
-        for cond, runs in self.data_info.items():
-            for run in runs:
-                span = self.f_index[run].get(idx)
-                if span is None:
-                    dd[(cond, run)] = None
-                else:
-                    fh = self.handles[run]
-                    fh.seek(span[0], 0)
-                    dd[(cond, run)] = json.loads(fh.read(span[1] - span[0]))
-        return dd
-
-    def close(self):
-        for fh in self.handles.values():
-            fh.close()
-
-
-# ---- host ingest workers (--n_processes) ----------------------------------------------------
-_W = {}
-
-
-def _worker_init(data_info, f_index, pooling, lo, hi, kmer_path):
-    _W["reader"] = GeneReader(data_info, f_index)
-    _W["layout"] = Layout.from_data_info(data_info, pooling)
-    _W["km"] = KmerModel.load(kmer_path)
-    _W["crit"] = (lo, hi)
-
-
-def _worker_pack(idx):
-    bb = BatchBuilder(_W["layout"], _W["km"], *_W["crit"])
-    bb.add_gene(idx, _W["reader"].read(idx))
-    b = bb.build()
-    return idx, b.y, b.grp_len, b.kmer_mean, b.kmer_std, b.positions, b.kmers
-
-
-def _concat(layout, parts) -> Batch:
-    ys, gl, km, ks, ids, pos, kmers = [], [], [], [], [], [], []
-    for idx, y, g, m, s, p, k in parts:
-        ys.append(y)
-        gl.append(g)
-        km.append(m)
-        ks.append(s)
-        ids += [idx] * len(p)
-        pos += p
-        kmers += k
-    G = layout.n_groups
-    grp_len = np.concatenate(gl) if gl else np.zeros((0, G), np.int32)
-    read_off = np.zeros(len(grp_len) + 1, np.int64)
-    np.cumsum(grp_len.sum(axis=1, dtype=np.int64), out=read_off[1:])
-    return Batch(layout, np.concatenate(ys) if ys else np.zeros(0), read_off, grp_len.astype(np.int32),
-                 np.concatenate(km) if km else np.zeros(0), np.concatenate(ks) if ks else np.zeros(0), ids, pos, kmers)
 
 
 def diffmod(args, fit_fn=None):
@@ -184,28 +119,22 @@ def diffmod(args, fit_fn=None):
     else:
         mine = todo
 
+    # ---- ingest (native, --n_processes threads) -> fit -> rows, chunk by chunk ----------------------
+    from .ingest import NativeIngest
     n_proc = max(1, int(args.n_processes))
-    pool = None
     lo, hi = criteria["readcount_min"], criteria["readcount_max"]
-    if n_proc > 1 and len(mine) > 1:
-        import multiprocessing as mp
-        pool = mp.get_context("fork").Pool(n_proc, initializer=_worker_init,
-                                           initargs=(data_info, f_index, method["pooling"], lo, hi, paths["model_kmer"]))
-        parts_iter = pool.imap(_worker_pack, mine, chunksize=4)
-    else:
-        _worker_init(data_info, f_index, method["pooling"], lo, hi, paths["model_kmer"])
-        parts_iter = map(_worker_pack, mine)
-
-    max_positions = int(getattr(args, "batch_positions", 0) or 262144)
+    reader = NativeIngest(data_info, layout, km, lo, hi)
+    max_bytes = int(getattr(args, "batch_bytes", 0) or (256 << 20))  # data.json text per chunk
+    max_genes = int(getattr(args, "batch_genes", 0) or 8192)      # and ids per chunk
     gene_rows = []  # (idx, rows) of this rank, in id order
 
-    def flush(parts):
-        if not parts:
+    def flush(chunk):
+        if not chunk:
             return
-        batch = _concat(layout, parts)
+        batch = reader.read(chunk, f_index, n_threads=n_proc)
         res = fit_fn(batch, m) if batch.n_positions else None
         rows = result_rows(batch, res, pm) if res is not None else []
-        by_gene = OrderedDict((p[0], []) for p in parts)
+        by_gene = OrderedDict((idx, []) for idx in chunk)
         for r in rows:
             by_gene[r[0]].append(r)
         if world == 1:
@@ -217,17 +146,15 @@ def diffmod(args, fit_fn=None):
         else:
             gene_rows.extend(by_gene.items())
 
-    parts, n_pos = [], 0
-    for part in parts_iter:
-        parts.append(part)
-        n_pos += len(part[5])
-        if n_pos >= max_positions:
-            flush(parts)
-            parts, n_pos = [], 0
-    flush(parts)
-    if pool is not None:
-        pool.close()
-        pool.join()
+    chunk, nbytes = [], 0
+    for idx in mine:
+        chunk.append(idx)
+        nbytes += sum(f_index[r][idx][1] - f_index[r][idx][0] for r in f_index if idx in f_index[r])
+        if nbytes >= max_bytes or len(chunk) >= max_genes:
+            flush(chunk)
+            chunk, nbytes = [], 0
+    flush(chunk)
+    reader.close()
 
     if world > 1:
         gathered = [None] * world if rank == 0 else None
