@@ -2,7 +2,8 @@
 
 Same sub-command and flags as the reference's ``xpore diffmod`` (``xpore/scripts/xpore.py:40-52``):
 ``--config`` (required), ``--n_processes``, ``--save_models``, ``--resume``, ``--ids``.
-``dataprep`` and ``postprocessing`` are outside this repository's scope.
+``postprocessing --diffmod_dir`` (``xpore.py:54-59``) is the majority-direction filter of
+``xpore_b200.postprocessing``.  ``dataprep`` is outside this repository's scope.
 """
 import argparse
 import sys
@@ -26,6 +27,11 @@ def parse_options(argv):
                    help="at most this many ids are ingested and fitted per GPU call.")
     p.add_argument("--batch_bytes", dest="batch_bytes", type=int, default=256 << 20,
                    help="... or this many bytes of data.json text, whichever comes first.")
+    q = sub.add_parser("postprocessing", help="run mode for post-processing diffmod.table, the result table from "
+                                              "differential modification analysis.")
+    qreq = q.add_argument_group("required arguments")
+    qreq.add_argument("--diffmod_dir", dest="diffmod_dir", required=True,
+                      help="diffmod directory path, the output from xpore-diffmod.")
     return parser.parse_args(argv[1:])
 
 
@@ -37,6 +43,9 @@ def main(argv=None):
         if options.save_models:
             print("warning: --save_models is accepted but not implemented in xpore_b200", file=sys.stderr)
         diffmod(options)
+    elif options.cmd == "postprocessing":
+        from .postprocessing import postprocessing
+        postprocessing(options)
 
 
 if __name__ == "__main__":

@@ -96,14 +96,16 @@ int prepare_kernel(Geometry* g) {
     return 0;
 }
 
+constexpr int kFitWarpsDefault = 28;
+
 int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
 }
 
-// Teams per CTA: as many as 227 KB of shared memory (after the 24.5 KB of tables) and the thread
-// limit of the flavour allow.  Single-warp teams run <= 16 warps with 128 registers per thread or up
-// to 20 warps with 96.
+// Teams per CTA: as many as 227 KB of shared memory (after the 24.5 KB of tables) allows, up to 28
+// single-warp teams (XPB200_FIT_WARPS overrides, <= 32).  The kernel is instantiated per thread limit
+// (640 / 768 / 896 / 1024 threads => 96 / 80 / 72 / 64 registers per thread) so that ptxas knows its budget.
 int fit_geometry(int G, int cap_reads, int tw, Geometry* g) {
     int dev = 0;
     CK(cudaGetDevice(&dev));
@@ -116,9 +118,9 @@ int fit_geometry(int G, int cap_reads, int tw, Geometry* g) {
                                        std::to_string(cap_reads) + ")");
     int teams = (int)((kMaxSmemPerCta - xpk::kFitTableBytes) / per_team);
     if (tw == 1) {
-        teams = std::min(teams, std::max(1, env_int("XPB200_FIT_WARPS", 20)));
-        teams = std::min(teams, 20);
-        g->maxt = teams <= 16 ? 512 : 640;
+        teams = std::min(teams, std::max(1, env_int("XPB200_FIT_WARPS", kFitWarpsDefault)));
+        teams = std::min(teams, 32);
+        g->maxt = teams <= 20 ? 640 : teams <= 24 ? 768 : teams <= 28 ? 896 : 1024;
     } else {
         teams = std::min(teams, 4);
         g->maxt = 512;
@@ -127,8 +129,14 @@ int fit_geometry(int G, int cap_reads, int tw, Geometry* g) {
     g->threads = teams * tw * 32;
     g->smem = xpk::kFitTableBytes + per_team * teams;
     int rc;
-    if (tw == 1) rc = (g->maxt == 512) ? prepare_kernel<1, 512>(g) : prepare_kernel<1, 640>(g);
-    else rc = prepare_kernel<4, 512>(g);
+    if (tw == 1) {
+        switch (g->maxt) {
+            case 640: rc = prepare_kernel<1, 640>(g); break;
+            case 768: rc = prepare_kernel<1, 768>(g); break;
+            case 896: rc = prepare_kernel<1, 896>(g); break;
+            default: rc = prepare_kernel<1, 1024>(g); break;
+        }
+    } else rc = prepare_kernel<4, 512>(g);
     if (rc) return rc;
     if (g->ctas_per_sm < 1) return fail(XPB200_ECUDA, "fit kernel does not fit on an SM");
     return 0;
@@ -137,9 +145,14 @@ int fit_geometry(int G, int cap_reads, int tw, Geometry* g) {
 int launch_fit(const Geometry& g, const xpk::FitArgs& fa, int max_teams_needed, cudaStream_t st) {
     const int need = (max_teams_needed + g.teams - 1) / g.teams;
     const int grid = std::max(1, std::min(g.sms * g.ctas_per_sm, need));
-    if (g.tw == 1 && g.maxt == 512) xpk::xp_fit_kernel<1, 512><<<grid, g.threads, g.smem, st>>>(fa);
-    else if (g.tw == 1) xpk::xp_fit_kernel<1, 640><<<grid, g.threads, g.smem, st>>>(fa);
-    else xpk::xp_fit_kernel<4, 512><<<grid, g.threads, g.smem, st>>>(fa);
+    if (g.tw == 1) {
+        switch (g.maxt) {
+            case 640: xpk::xp_fit_kernel<1, 640><<<grid, g.threads, g.smem, st>>>(fa); break;
+            case 768: xpk::xp_fit_kernel<1, 768><<<grid, g.threads, g.smem, st>>>(fa); break;
+            case 896: xpk::xp_fit_kernel<1, 896><<<grid, g.threads, g.smem, st>>>(fa); break;
+            default: xpk::xp_fit_kernel<1, 1024><<<grid, g.threads, g.smem, st>>>(fa); break;
+        }
+    } else xpk::xp_fit_kernel<4, 512><<<grid, g.threads, g.smem, st>>>(fa);
     ++g_launches;
     CK(cudaGetLastError());
     return 0;

@@ -23,15 +23,33 @@
 // CTA shared memory:  [ exp2 table 32x32 f64 | {1/c, ln c} table 33x32 double2 | team 0 | team 1 | ... ]
 // team region (doubles unless noted):
 //   slab[cap+2]        centred reads y' (TMA destination; +2 = 16-byte alignment slack)
-//   scratch[R x RS]    R = G+3 rows (N_g0 per group, S1_0, S2_0, entropy), RS = 32 TW + 1 columns:
-//                      per-lane partials of the current sweep; doubles as the 256-bin select histogram
+//   scratch[32 TW x RL] one row of RL = odd(G+3) doubles per thread of the team: its partial N_g0 per
+//                      group, S1_0, S2_0 and entropy of the current sweep (odd stride: conflict free);
+//                      doubles as the 256-bin select histogram before the first sweep
 //   tot[G+4]           row totals
 //   Asm[G]             per-group constant of d_n
 //   sc[8]              psi(alpha_k), lgamma(alpha_k), ln beta_k, ln lambda_k published by their lanes
 //   bc[8]              leader -> team broadcast: B, C, continue flag, ticket, reduction slots
+//   pc[8]              per-position values the leader needs once per sweep (m0, a0, b0, the two ELBO constants,
+//                      sum y', sum y'^2, previous ELBO): parked here so they hold no registers during the E-step
 //   goff[G+1] (int), mbar (u64), gid[cap+2] (u8: group slot of every read)
 #pragma once
 #include <cuda_runtime.h>
+
+#ifndef XP_FIT_NR
+#define XP_FIT_NR 2
+#endif
+#ifndef XP_FIT_FLOOR
+#define XP_FIT_FLOOR 0
+#endif
+#ifndef XP_FIT_PARK
+#define XP_FIT_PARK 1
+#endif
+#if XP_FIT_PARK
+#define XP_PK(i, var) parked(pc + (i))
+#else
+#define XP_PK(i, var) (var)
+#endif
 
 namespace xpk {
 
@@ -59,27 +77,51 @@ constexpr int kTabLogDoubles = 33 * 32 * 2;
 constexpr size_t kFitTableBytes = (size_t)(kTabExpDoubles + kTabLogDoubles) * 8;
 
 __host__ __device__ inline int fit_rows(int G) { return G + 3; }
+__host__ __device__ inline int fit_row_stride(int G) { return (G + 3) | 1; }
 __host__ __device__ inline size_t fit_scratch_doubles(int G, int TW) {
-    const size_t s = (size_t)fit_rows(G) * (32 * TW + 1);
+    const size_t s = (size_t)fit_row_stride(G) * (32 * TW);
     return s > 128 ? s : 128;  // >= 1 KB: the radix-select histogram lives here before the first sweep
 }
 __host__ __device__ inline size_t fit_team_smem_bytes(int cap, int G, int TW) {
-    const size_t doubles = (size_t)(cap + 2) + fit_scratch_doubles(G, TW) + (G + 4) + G + 8 + 8;
+    const size_t doubles = (size_t)(cap + 2) + fit_scratch_doubles(G, TW) + (G + 4) + G + 8 + 8 + 8;
     const size_t bytes = doubles * 8 + (size_t)((G + 2) & ~1) * 4 + 8 + (size_t)(cap + 2);
     return (bytes + 15) & ~(size_t)15;
 }
 
-// shared-memory tables, one column per lane
+// shared-memory tables, one column per lane, addressed through the 32-bit shared window
 struct SmemTab {
-    const double* e2;
-    const double2* lg;
-    __device__ __forceinline__ double exp2(int j) const { return e2[j * 32]; }
-    __device__ __forceinline__ void logc(int i, double& ic, double& lc) const {
-        const double2 v = lg[i * 32];
-        ic = v.x;
-        lc = v.y;
-    }
+    uint32_t e2;  // this lane's column of the 2^(j/32) table; entries 256 bytes apart
+    uint32_t lg;  // this lane's column of the {1/c, ln c} table (entries 512 bytes apart), biased so that
+                  // entry i is found at lg + 512 * (hi32(u) >> 15) for u = 1 + t in [1, 2]
 };
+__device__ __forceinline__ double lds_tab(uint32_t a) {  // tables are immutable after the prologue
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void lds_tab2(uint32_t a, double& x, double& y) {
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+}
+// a * b + c as one IMAD (written in C, the compiler turns a * 2^s into shift + mask + add)
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {  // mutable shared data: ordered like a volatile access
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+// a value parked in shared memory: re-read where it is used instead of living in a register pair
+__device__ __forceinline__ double parked(const double* p) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
 
 template <int TW>
 __device__ __forceinline__ void team_sync(int team) {
@@ -175,18 +217,22 @@ __device__ double team_percentile(const double* yv, int n, double q, uint64_t km
 }
 
 // The constants of the E-step kept in registers across a sweep.
+// The series coefficients of the E-step.  They are left in the constant bank on purpose: ptxas feeds
+// them to DFMA through uniform registers, which costs a few LDCU per trip but no vector registers - and
+// this kernel is bound by the number of independent FP64 chains in flight (DFMA latency is ~23 cycles on
+// B200, tools/microbench/dfma_lat.cu), not by issue slots, so registers go to reads in flight instead.
 struct EConst {
-    double a32, lhi, llo, c4, c3, l5, l3;
+    double a32, lhi, llo, c6, c4, c3, l7, l5, l3;
     __device__ __forceinline__ void load() {
         a32 = XPT(kE32)[0];
         lhi = XPT(kE32)[1];
         llo = XPT(kE32)[2];
+        c6 = kExpC6;
         c4 = XPT(kE32)[5];
         c3 = XPT(kE32)[6];
+        l7 = kLogC7;
         l5 = XPT(kL1p)[2];
         l3 = XPT(kL1p)[4];
-        // opaque to the optimiser: keeps them in registers instead of one constant load per use
-        asm volatile("" : "+d"(a32), "+d"(lhi), "+d"(llo), "+d"(c4), "+d"(c3), "+d"(l5), "+d"(l3));
     }
 };
 
@@ -199,24 +245,23 @@ __device__ __forceinline__ void estep_dev(const SmemTab& tab, const EConst& K, d
     const double magic = 6755399441055744.0;
     const double t0 = fma(-ax, K.a32, magic);
     const double kf = t0 - magic;
-    const int k = __double2loint(t0);
+    const unsigned k = (unsigned)__double2loint(t0);
     double r = fma(-kf, K.lhi, -ax);
     r = fma(-kf, K.llo, r);
-    double p = kExpC6;
+    double p = K.c6;
     p = fma(p, r, kExpC5);
     p = fma(p, r, K.c4);
     p = fma(p, r, K.c3);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    double t = tab.exp2(k & 31) * p;
-    t = __hiloint2double(__double2hiint(t) + ((k >> 5) << 20), __double2loint(t));
+    double t = lds_tab(mad_u32(k & 31u, 256u, tab.e2)) * p;
+    t = __hiloint2double((int)mad_u32(k & ~31u, 32768u, (unsigned)__double2hiint(t)), __double2loint(t));  // * 2^(k >> 5)
     const double u = 1.0 + t;
-    const int i = (__double2hiint(u) - 0x3ff00000) >> 15;  // 0..32 (32 only for u == 2)
     double ic, lc;
-    tab.logc(i, ic, lc);
+    lds_tab2(mad_u32((unsigned)__double2hiint(u) >> 15, 512u, tab.lg), ic, lc);  // top five mantissa bits; u == 2 -> entry 32
     const double rr = fma(u, ic, -1.0);
-    double q = kLogC7;
+    double q = K.l7;
     q = fma(q, rr, kLogC6);
     q = fma(q, rr, K.l5);
     q = fma(q, rr, -0.25);
@@ -227,7 +272,95 @@ __device__ __forceinline__ void estep_dev(const SmemTab& tab, const EConst& K, d
     const double inv = xrcp3(u);
     const double rmin = t * inv;
     r0 = (dhi >= 0) ? rmin : inv;
-    h = fma(rmin, fabs(d), l1p);
+    h = fma(rmin, ax, l1p);  // |d| > 500 only when rmin < 1e-217: the clip does not show
+}
+
+// The same arithmetic for NR independent reads, written step by step across the reads so that the
+// NR dependency chains are interleaved in program order (ptxas keeps this order; left to itself it
+// runs the chains of separately inlined calls almost back to back).
+template <int NR>
+__device__ __forceinline__ void estep_dev_n(const SmemTab& tab, const EConst& K, const double (&d)[NR], double (&r0)[NR],
+                                            double (&h)[NR]) {
+    const double magic = 6755399441055744.0;
+    double ax[NR], t0[NR], kf[NR], r[NR], p[NR], t[NR], u[NR], ic[NR], lc[NR], rr[NR], q[NR], y0[NR], e[NR];
+    unsigned k[NR];
+    bool pos[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        const int dhi = __double2hiint(d[i]);
+        pos[i] = dhi >= 0;
+        const int ahi = min(dhi & 0x7fffffff, 0x407f4000);
+        ax[i] = __hiloint2double(ahi, __double2loint(d[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) t0[i] = fma(-ax[i], K.a32, magic);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        kf[i] = t0[i] - magic;
+        k[i] = (unsigned)__double2loint(t0[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) r[i] = fma(-kf[i], K.lhi, -ax[i]);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) r[i] = fma(-kf[i], K.llo, r[i]);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) t[i] = lds_tab(mad_u32(k[i] & 31u, 256u, tab.e2));
+#pragma unroll
+    for (int i = 0; i < NR; ++i) p[i] = fma(K.c6, r[i], kExpC5);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) p[i] = fma(p[i], r[i], K.c4);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) p[i] = fma(p[i], r[i], K.c3);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) p[i] = fma(p[i], r[i], 0.5);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) p[i] = fma(p[i], r[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) p[i] = fma(p[i], r[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        t[i] = t[i] * p[i];
+        t[i] = __hiloint2double((int)mad_u32(k[i] & ~31u, 32768u, (unsigned)__double2hiint(t[i])), __double2loint(t[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) u[i] = 1.0 + t[i];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        lds_tab2(mad_u32((unsigned)__double2hiint(u[i]) >> 15, 512u, tab.lg), ic[i], lc[i]);
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0[i]) : "d"(u[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        rr[i] = fma(u[i], ic[i], -1.0);
+        e[i] = fma(-u[i], y0[i], 1.0);
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        q[i] = fma(K.l7, rr[i], kLogC6);
+        e[i] = fma(e[i], e[i], e[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        q[i] = fma(q[i], rr[i], K.l5);
+        y0[i] = fma(y0[i], e[i], y0[i]);  // 1/u (xrcp3)
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        q[i] = fma(q[i], rr[i], -0.25);
+        t[i] = t[i] * y0[i];  // rmin
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) q[i] = fma(q[i], rr[i], K.l3);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) q[i] = fma(q[i], rr[i], -0.5);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) q[i] = fma(q[i], rr[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        const double l1p = fma(q[i], rr[i], lc[i]);
+        r0[i] = pos[i] ? t[i] : y0[i];
+        h[i] = fma(t[i], ax[i], l1p);
+    }
 }
 
 template <int TW, int MAXT>
@@ -237,8 +370,7 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
     const int team = warp / TW, tw = warp % TW, tid = tw * 32 + lane;  // tid: thread index inside the team
     const bool leader = (tw == 0);
     const int G = a.G;
-    constexpr int RS = 32 * TW + 1;
-    const int R = fit_rows(G);
+    const int R = fit_rows(G), RL = fit_row_stride(G);
 
     double* tab_e2 = reinterpret_cast<double*>(smem_raw);
     double2* tab_lg = reinterpret_cast<double2*>(tab_e2 + kTabExpDoubles);
@@ -246,8 +378,8 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
     for (int i = threadIdx.x; i < 33 * 32; i += blockDim.x)
         tab_lg[i] = make_double2(XPT(kInvC)[i >> 5], XPT(kLogC)[i >> 5]);
     SmemTab tab;
-    tab.e2 = tab_e2 + lane;
-    tab.lg = tab_lg + lane;
+    tab.e2 = smem_u32(tab_e2 + lane);
+    tab.lg = smem_u32(tab_lg + lane) - 0x7fe0u * 512u;
 
     unsigned char* wbase = smem_raw + kFitTableBytes + (size_t)team * fit_team_smem_bytes(a.cap, G, TW);
     double* slab = reinterpret_cast<double*>(wbase);
@@ -256,7 +388,8 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
     double* Asm = tot + G + 4;
     double* sc = Asm + G;
     double* bc = sc + 8;
-    int* goff = reinterpret_cast<int*>(bc + 8);
+    double* pc = bc + 8;
+    int* goff = reinterpret_cast<int*>(pc + 8);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(goff + ((G + 2) & ~1));
     unsigned char* gid = reinterpret_cast<unsigned char*>(mbar + 1);
 
@@ -354,31 +487,38 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
 
         mbar_wait(mbar, parity);
         parity ^= 1u;
-        // decode (scaled integers expand in place, last step first so no unread raw bytes are
-        // overwritten), centre on the k-mer mean; totals and min/max keys on the way
-        double* yv = slab + (fmt == kYF64 ? sh : 0);
+        // decode in place and centre on the k-mer mean.  Scaled integers expand (last step first, so no
+        // unread raw bytes are overwritten); doubles move down by the `sh` leading elements of the aligned
+        // superset (first step first), so the reads start 16-byte aligned in either case.
+        double* yv = slab;
         const double rscale = 1.0 / a.y_scale;
+        constexpr int TT = TW * 32;
+        {
+            const int last = ((n - 1) / TT) * TT;
+            const int step = (fmt == kYF64) ? TT : -TT;
+            for (int i0 = (fmt == kYF64) ? 0 : last; i0 >= 0 && i0 <= last; i0 += step) {
+                const int i = i0 + tid;
+                double v = 0.0;
+                if (i < n) {
+                    if (fmt == kYF64) v = slab[sh + i];
+                    else if (fmt == kYI32) v = y_decode((double)reinterpret_cast<const int*>(slab)[sh + i], a.y_scale, rscale);
+                    else v = y_decode((double)reinterpret_cast<const unsigned short*>(slab)[sh + i], a.y_scale, rscale);
+                    v -= m0;
+                }
+                team_sync<TW>(team);
+                if (i < n) yv[i] = v;
+            }
+        }
+        // totals and min/max keys in one fixed order, whatever the encoding was
         uint64_t kmin = ~0ull, kmax = 0ull;
         double T1 = 0.0, T2 = 0.0;
-        constexpr int TT = TW * 32;
-        for (int i0 = ((n - 1) / TT) * TT; i0 >= 0; i0 -= TT) {
-            const int i = i0 + tid;
-            double v = 0.0;
-            if (i < n) {
-                if (fmt == kYF64) v = yv[i];
-                else if (fmt == kYI32) v = y_decode((double)reinterpret_cast<const int*>(slab)[sh + i], a.y_scale, rscale);
-                else v = y_decode((double)reinterpret_cast<const unsigned short*>(slab)[sh + i], a.y_scale, rscale);
-                v -= m0;
-            }
-            team_sync<TW>(team);
-            if (i < n) {
-                yv[i] = v;
-                const uint64_t k = dkey(v);
-                kmin = k < kmin ? k : kmin;
-                kmax = k > kmax ? k : kmax;
-                T1 += v;
-                T2 = fma(v, v, T2);
-            }
+        for (int i = tid; i < n; i += TT) {
+            const double v = yv[i];
+            const uint64_t k = dkey(v);
+            kmin = k < kmin ? k : kmin;
+            kmax = k > kmax ? k : kmax;
+            T1 += v;
+            T2 = fma(v, v, T2);
         }
         kmin = warp_min_u64(kmin);
         kmax = warp_max_u64(kmax);
@@ -411,12 +551,27 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
         const double med = team_percentile<TW>(yv, n, 0.5, kmin, kmax, hist, lane, tid, team);
         const double loc1 = team_percentile<TW>(yv, n, (0.0 < med) ? 0.75 : 0.25, kmin, kmax, hist, lane, tid, team);
         team_sync<TW>(team);
+        // this thread's row of partial sums.  The groups a thread meets are the same in every sweep, so the
+        // entries it never writes are cleared once per position.
+        double* srow = scratch + (size_t)tid * RL;
+        for (int g = 0; g < G; ++g) srow[g] = 0.0;
+        const int g_first = gid[0];
 
         // ---- leader state: lanes of parity k hold component k ---------------------------------------
         Comp c = mstep(0.0, 0.0, 0.0, a0, b0);
         if (kpar) c.mp = loc1;
         double Nk = 0.0, S1k = 0.0, S2k = 0.0, Hent = 0.0;
-        double elbo_old = -INFINITY, elbo = -INFINITY;
+        double elbo = -INFINITY, elbo_old = -INFINITY;
+        if (XP_FIT_PARK && leader && lane == 0) {
+            pc[0] = m0;
+            pc[1] = a0;
+            pc[2] = b0;
+            pc[3] = Kconst;
+            pc[4] = prior_gamma;
+            pc[5] = T1;
+            pc[6] = T2;
+            pc[7] = -INFINITY;  // ELBO of the previous sweep
+        }
         int it = 0;
         uint32_t st = STATUS_SELECTED;
         if (leader)
@@ -424,6 +579,16 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
         // first sweep: component 1 has N = 0 too (q(w) starts at the prior, gmm.py:66) -> handled below
         bool first = true;
         __syncwarp();
+#if XP_FIT_FLOOR
+        // Register floor.  ptxas picks its register budget from occupancy levels (.., 72, 80, 96, 128) and, once
+        // the minimal pressure fits a level, spends only that level's slack on interleaving the E-step chains:
+        // a kernel that *could* run in 96 registers gets its NR chains serialised to stay there, although this
+        // kernel's occupancy is set by shared memory, not registers.  A few values held across the sweep loop
+        // push the minimum over that level, and the next level's slack goes to instruction-level parallelism.
+        double floor_[XP_FIT_FLOOR];
+#pragma unroll
+        for (int q = 0; q < XP_FIT_FLOOR; ++q) floor_[q] = *reinterpret_cast<const volatile double*>(bc + (q & 7));
+#endif
 
         for (;;) {
             bool go = true;
@@ -465,17 +630,18 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
                 }
                 __syncwarp();
                 double tb, lt;
-                const double ek = elbo_component(c, Nk, S1k, S2k, a0, b0, prior_gamma, sc[kpar], sc[2 + kpar],
+                const double ek = elbo_component(c, Nk, S1k, S2k, XP_PK(1, a0), XP_PK(2, b0), XP_PK(4, prior_gamma), sc[kpar], sc[2 + kpar],
                                                  sc[4 + kpar], sc[6 + kpar], tb, lt);
                 if (lane < 2) e_loc += ek;
-                elbo = warp_sum(e_loc) + Kconst + Hent;
+                elbo = warp_sum(e_loc) + XP_PK(3, Kconst) + Hent;
                 if (it >= 1) {
-                    const int rule = stop_rule(elbo, elbo_old, a.stopping);
+                    const int rule = stop_rule(elbo, XP_PK(7, elbo_old), a.stopping);
                     if (rule == 2) {
                         st |= STATUS_ELBO_DECREASED;
                         go = false;
                     } else {
                         elbo_old = elbo;
+                        if (XP_FIT_PARK && lane == 0) pc[7] = elbo;
                         if (rule == 1) {
                             st |= STATUS_CONVERGED;
                             go = false;
@@ -511,72 +677,78 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
             first = false;
             const double B = bc[0], C = bc[1];
             // ---- E-step + component-0 moments: one pass over the resident reads ------------------
-            const int col = tw * 32 + lane;
-            for (int g = 0; g < G; ++g) scratch[g * RS + col] = 0.0;
+            // A thread takes the adjacent reads 2j, 2j+1 (j = 32 trip + lane: one 16-byte load) of every
+            // full trip of 64 reads, then single reads of the tail, so the groups it meets never decrease;
+            // its N_g0 partial goes to srow[g] whenever the group changes.  The loop body is branch free.
             double accN = 0.0, S1 = 0.0, S2 = 0.0, Hh = 0.0;
             {
                 EConst K;
                 K.load();
-                int gcur = gid[lane < n ? lane : 0];
-                const int nfull = n >> 6;
+                unsigned pg = g_first;  // group of this thread's last read; accN goes to srow[pg] on leaving it
+                constexpr int NR = XP_FIT_NR;   // adjacent reads per thread and trip
+                const int nfull = n / (32 * NR);
+#define XP_READ(yy, gg)                              \
+    {                                                \
+        const double d_ = fma((yy), fma(C, (yy), B), Asm[gg]); \
+        double r_, h_;                               \
+        estep_dev(tab, K, d_, r_, h_);               \
+        if ((gg) != pg) {                            \
+            srow[pg] = accN;                         \
+            accN = 0.0;                              \
+        }                                            \
+        pg = (gg);                                   \
+        accN += r_;                                  \
+        const double w_ = r_ * (yy);                 \
+        S1 += w_;                                    \
+        S2 = fma(w_, (yy), S2);                      \
+        Hh += h_;                                    \
+    }
                 for (int trip = tw; trip < nfull; trip += TW) {
-                    const int i = (trip << 6) + lane;
-                    const int g0 = gid[i], g1 = gid[i + 32];
-                    const double ya = yv[i], yb = yv[i + 32];
-                    const double da = fma(ya, fma(C, ya, B), Asm[g0]);
-                    const double db = fma(yb, fma(C, yb, B), Asm[g1]);
-                    double ra, ha, rb, hb;
-                    estep_dev(tab, K, da, ra, ha);
-                    estep_dev(tab, K, db, rb, hb);
-                    if (g1 != gcur) {  // rare: this lane crosses into another group
-                        if (g0 != gcur) {
-                            scratch[gcur * RS + col] = accN;
-                            accN = 0.0;
-                        }
-                        accN += ra;
-                        if (g1 != g0) {
-                            scratch[g0 * RS + col] = accN;
-                            accN = 0.0;
-                        }
-                        accN += rb;
-                        gcur = g1;
-                    } else {
-                        accN += ra;
-                        accN += rb;
+                    const int i0 = trip * (32 * NR) + lane;
+                    double y4[NR], d4[NR], r4[NR], h4[NR];
+                    unsigned gg[NR];
+                    // one load per read (not one wide load per thread): ptxas interleaves the NR dependency
+                    // chains only when they start from separate loads
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        gg[i] = gid[i0 + 32 * i];
+                        y4[i] = yv[i0 + 32 * i];
                     }
-                    const double wa = ra * ya, wb = rb * yb;
-                    S1 += wa;
-                    S2 = fma(wa, ya, S2);
-                    S1 += wb;
-                    S2 = fma(wb, yb, S2);
-                    Hh += ha;
-                    Hh += hb;
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) d4[i] = fma(y4[i], fma(C, y4[i], B), Asm[gg[i]]);
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) estep_dev(tab, K, d4[i], r4[i], h4[i]);
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        if (gg[i] != pg) {
+                            srow[pg] = accN;
+                            accN = 0.0;
+                        }
+                        pg = gg[i];
+                        accN += r4[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        const double w_ = r4[i] * y4[i];
+                        S1 += w_;
+                        S2 = fma(w_, y4[i], S2);
+                        Hh += h4[i];
+                    }
                 }
                 if ((nfull % TW) == tw) {  // the reads past the last full trip (lanes may diverge here)
-                    for (int i = (nfull << 6) + lane; i < n; i += 32) {
-                        const int g0 = gid[i];
+                    for (int i = nfull * (32 * NR) + lane; i < n; i += 32) {
                         const double ya = yv[i];
-                        const double da = fma(ya, fma(C, ya, B), Asm[g0]);
-                        double ra, ha;
-                        estep_dev(tab, K, da, ra, ha);
-                        if (g0 != gcur) {
-                            scratch[gcur * RS + col] = accN;
-                            accN = 0.0;
-                            gcur = g0;
-                        }
-                        accN += ra;
-                        const double wa = ra * ya;
-                        S1 += wa;
-                        S2 = fma(wa, ya, S2);
-                        Hh += ha;
+                        const unsigned ga = gid[i];
+                        XP_READ(ya, ga)
                     }
                     __syncwarp();
                 }
-                scratch[gcur * RS + col] = accN;
+#undef XP_READ
+                srow[pg] = accN;
             }
-            scratch[G * RS + col] = S1;
-            scratch[(G + 1) * RS + col] = S2;
-            scratch[(G + 2) * RS + col] = Hh;
+            srow[G] = S1;
+            srow[G + 1] = S2;
+            srow[G + 2] = Hh;
             team_sync<TW>(team);
             if (leader) {
                 // row sums: `parts` lanes share a row, then combine through shuffles
@@ -587,12 +759,11 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
                     const int row = r0 + lane % rpp, part = lane / rpp;
                     double t0 = 0.0, t1 = 0.0;
                     if (row < R) {
-                        const double* rp = scratch + (size_t)row * RS;
                         const int len = NC / parts;
-                        const double* q = rp + part * len;
-                        for (int l = 0; l < len; l += 2) {
-                            t0 += q[l];
-                            t1 += q[l + 1];
+                        const double* q = scratch + (size_t)(part * len) * RL + row;
+                        for (int l = 0; l < len; l += 2, q += 2 * RL) {
+                            t0 += q[0];
+                            t1 += q[RL];
                         }
                     }
                     double t = t0 + t1;
@@ -610,17 +781,22 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
                 const double s10 = tot[G], s20 = tot[G + 1];
                 Hent = tot[G + 2];
                 Nk = kpar ? ((double)n - n0) : n0;
-                S1k = kpar ? (T1 - s10) : s10;
-                S2k = kpar ? (T2 - s20) : s20;
+                S1k = kpar ? (XP_PK(5, T1) - s10) : s10;
+                S2k = kpar ? (XP_PK(6, T2) - s20) : s20;
                 // ---- M-step (gmm.py:292-294, 364-370) ---------------------------------------------
-                c = mstep(Nk, S1k, S2k, a0, b0);
+                c = mstep(Nk, S1k, S2k, XP_PK(1, a0), XP_PK(2, b0));
             }
         }
+#if XP_FIT_FLOOR
+#pragma unroll
+        for (int q = 0; q < XP_FIT_FLOOR; ++q)
+            if (floor_[q] == 1.2345e-300) *reinterpret_cast<volatile double*>(bc + (q & 7)) = floor_[q];
+#endif
         // ---- write the fit record ------------------------------------------------------------------
         if (leader) {
             double* out = a.fit + (size_t)p * fit_width(G);
             if (lane < 2) {
-                out[FIT_MU + kpar] = m0 + c.mp;
+                out[FIT_MU + kpar] = XP_PK(0, m0) + c.mp;
                 out[FIT_LAM + kpar] = c.lam;
                 out[FIT_ALPHA + kpar] = c.alpha;
                 out[FIT_BETA + kpar] = c.beta;
