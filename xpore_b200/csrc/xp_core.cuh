@@ -45,11 +45,11 @@ struct Comp {
 // `pos` (d > 0) says component 1 is the likelier one.  h = -(r0 ln r0 + r1 ln r1) = rmin |d| + log1p(t)
 // is this read's share of -E[ln q(z)] (gmm.py:217-219).
 //
-// Table-driven: exp(x) = 2^m 2^(j/32) e^r with |r| <= ln2/64 (degree-6 series), and
-// ln(1+t) = ln1p(u/c_i - 1) + ln c_i with u = 1+t in [1,2] and c_i the centre of its 1/32-wide
-// interval (degree-7 series, |u/c_i - 1| <= 1/64; entry 32 = {1/2, ln 2} serves u == 2).  `Tab`
-// supplies the tables: constant arrays here, [entry][lane] shared-memory columns in xp_fit.cuh
-// (xpk::estep_dev is the same arithmetic with the coefficients held in registers).
+// Table-driven: exp(x) = 2^m 2^(j/256) e^r with |r| <= ln2/512 (degree-4 series), and
+// ln(1+t) = ln1p(u/c_i - 1) + ln c_i with u = 1+t in [1,2] and c_i the centre of its 1/128-wide
+// interval (degree-5 series, |u/c_i - 1| <= 1/256; entry 128 = {1/2, ln 2} serves u == 2).  `Tab`
+// supplies the tables: constant arrays here, shared-memory copies in xp_fit.cuh
+// (xpk::estep_dev is the same arithmetic).
 struct HostTab {
     XP_HD double exp2(int j) const { return XPT(kExp2)[j]; }
     XP_HD void logc(int i, double& ic, double& lc) const {
@@ -65,30 +65,24 @@ XP_HD void estep_read(const Tab& tab, double d, double& inv, double& rmin, doubl
     ahi = ahi < 0x407f4000 ? ahi : 0x407f4000;  // |d| clipped at 500 (low word kept: [500, 500 + 2^-12))
     const double ax = mk64(ahi, lo32(d));
     const double magic = XPT(kMisc)[5];
-    const double t0 = fma(-ax, XPT(kE32)[0], magic);
+    const double t0 = fma(-ax, XPT(kE256)[0], magic);
     const double kf = t0 - magic;
-    const int k = lo32(t0);  // low word of the magic sum = rint(-32 |d| / ln 2), two's complement
-    double r = fma(-kf, XPT(kE32)[1], -ax);
-    r = fma(-kf, XPT(kE32)[2], r);
-    double p = kExpC6;
-    p = fma(p, r, kExpC5);
-    p = fma(p, r, XPT(kE32)[5]);
-    p = fma(p, r, XPT(kE32)[6]);
+    const int k = lo32(t0);  // low word of the magic sum = rint(-256 |d| / ln 2), two's complement
+    double r = fma(-kf, XPT(kE256)[1], -ax);
+    r = fma(-kf, XPT(kE256)[2], r);
+    double p = fma(kExpC4, r, XPT(kE3)[0]);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    double t = tab.exp2(k & 31) * p;
-    t = mk64(hi32(t) + (k >> 5) * (1 << 20), lo32(t));  // * 2^m, result stays normal (|d| <= 500)
+    double t = tab.exp2(k & 255) * p;
+    t = mk64(hi32(t) + (k >> 8) * (1 << 20), lo32(t));  // * 2^m, result stays normal (|d| <= 500)
     const double u = 1.0 + t;                           // [1, 2]
-    const int i = (hi32(u) - 0x3ff00000) >> 15;         // top five mantissa bits; u == 2 gives 32
+    const int i = (hi32(u) - 0x3ff00000) >> 13;         // top seven mantissa bits; u == 2 gives 128
     double ic, lc;
     tab.logc(i, ic, lc);
     const double rr = fma(u, ic, -1.0);
-    double q = kLogC7;
-    q = fma(q, rr, kLogC6);
-    q = fma(q, rr, XPT(kL1p)[2]);
-    q = fma(q, rr, -0.25);
-    q = fma(q, rr, XPT(kL1p)[4]);
+    double q = fma(kLogC5, rr, -0.25);
+    q = fma(q, rr, XPT(kE3)[1]);
     q = fma(q, rr, -0.5);
     q = fma(q, rr, 1.0);
     const double l1p = fma(q, rr, lc);  // ln(1+t)

@@ -17,10 +17,9 @@
 // E-step bookkeeping: only component 0 is accumulated per read (N_g0, S1_0, S2_0 and the entropy);
 // component 1 follows from the per-position totals because r_n1 = 1 - r_n0 (gmm.py:242):
 //   N_g1 = n_g - N_g0,  S1_1 = sum y' - S1_0,  S2_1 = sum y'^2 - S2_0.
-// The 32/33-entry exp / log tables live in shared memory as table[entry][lane] (one column per lane:
-// any combination of per-lane indices is bank-conflict free).
+// The 256-entry 2^(j/256) table and the 129-entry {1/c, ln c} table live in shared memory (4 KB per CTA).
 //
-// CTA shared memory:  [ exp2 table 32x32 f64 | {1/c, ln c} table 33x32 double2 | team 0 | team 1 | ... ]
+// CTA shared memory:  [ exp2 table 256 f64 | {1/c, ln c} table 129 double2 (+pad) | team 0 | team 1 | ... ]
 // team region (doubles unless noted):
 //   slab[cap+2]        centred reads y' (TMA destination; +2 = 16-byte alignment slack)
 //   scratch[32 TW x RL] one row of RL = odd(G+3) doubles per thread of the team: its partial N_g0 per
@@ -72,8 +71,8 @@ struct FitArgs {
     uint32_t* status;
 };
 
-constexpr int kTabExpDoubles = 32 * 32;
-constexpr int kTabLogDoubles = 33 * 32 * 2;
+constexpr int kTabExpDoubles = 256;
+constexpr int kTabLogDoubles = 130 * 2;
 constexpr size_t kFitTableBytes = (size_t)(kTabExpDoubles + kTabLogDoubles) * 8;
 
 __host__ __device__ inline int fit_rows(int G) { return G + 3; }
@@ -88,11 +87,11 @@ __host__ __device__ inline size_t fit_team_smem_bytes(int cap, int G, int TW) {
     return (bytes + 15) & ~(size_t)15;
 }
 
-// shared-memory tables, one column per lane, addressed through the 32-bit shared window
+// shared-memory tables, addressed through the 32-bit shared window
 struct SmemTab {
-    uint32_t e2;  // this lane's column of the 2^(j/32) table; entries 256 bytes apart
-    uint32_t lg;  // this lane's column of the {1/c, ln c} table (entries 512 bytes apart), biased so that
-                  // entry i is found at lg + 512 * (hi32(u) >> 15) for u = 1 + t in [1, 2]
+    uint32_t e2;  // 2^(j/256), 8 bytes per entry
+    uint32_t lg;  // {1/c, ln c}, 16 bytes per entry, biased so that entry i of u = 1 + t in [1, 2] is found
+                  // at lg + 16 * (hi32(u) >> 13)
 };
 __device__ __forceinline__ double lds_tab(uint32_t a) {  // tables are immutable after the prologue
     double v;
@@ -222,49 +221,39 @@ __device__ double team_percentile(const double* yv, int n, double q, uint64_t km
 // this kernel is bound by the number of independent FP64 chains in flight (DFMA latency is ~23 cycles on
 // B200, tools/microbench/dfma_lat.cu), not by issue slots, so registers go to reads in flight instead.
 struct EConst {
-    double a32, lhi, llo, c6, c4, c3, l7, l5, l3;
+    double a256, lhi, llo, c3, l3;
     __device__ __forceinline__ void load() {
-        a32 = XPT(kE32)[0];
-        lhi = XPT(kE32)[1];
-        llo = XPT(kE32)[2];
-        c6 = kExpC6;
-        c4 = XPT(kE32)[5];
-        c3 = XPT(kE32)[6];
-        l7 = kLogC7;
-        l5 = XPT(kL1p)[2];
-        l3 = XPT(kL1p)[4];
+        a256 = XPT(kE256)[0];
+        lhi = XPT(kE256)[1];
+        llo = XPT(kE256)[2];
+        c3 = XPT(kE3)[0];
+        l3 = XPT(kE3)[1];
     }
 };
 
-// E-step of one read given d (device flavour of xpc::estep_read with the constants in registers).
+// E-step of one read given d (device flavour of xpc::estep_read: same operations, same order).
 __device__ __forceinline__ void estep_dev(const SmemTab& tab, const EConst& K, double d, double& r0, double& h) {
     const int dhi = __double2hiint(d);
     int ahi = dhi & 0x7fffffff;
     ahi = min(ahi, 0x407f4000);  // |d| clipped at 500 (gmm.py:240); low word kept: [500, 500 + 2^-12)
     const double ax = __hiloint2double(ahi, __double2loint(d));
     const double magic = 6755399441055744.0;
-    const double t0 = fma(-ax, K.a32, magic);
+    const double t0 = fma(-ax, K.a256, magic);
     const double kf = t0 - magic;
     const unsigned k = (unsigned)__double2loint(t0);
     double r = fma(-kf, K.lhi, -ax);
     r = fma(-kf, K.llo, r);
-    double p = K.c6;
-    p = fma(p, r, kExpC5);
-    p = fma(p, r, K.c4);
-    p = fma(p, r, K.c3);
+    double p = fma(kExpC4, r, K.c3);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    double t = lds_tab(mad_u32(k & 31u, 256u, tab.e2)) * p;
-    t = __hiloint2double((int)mad_u32(k & ~31u, 32768u, (unsigned)__double2hiint(t)), __double2loint(t));  // * 2^(k >> 5)
+    double t = lds_tab(mad_u32(k & 255u, 8u, tab.e2)) * p;
+    t = __hiloint2double((int)mad_u32(k & ~255u, 4096u, (unsigned)__double2hiint(t)), __double2loint(t));  // * 2^(k >> 8)
     const double u = 1.0 + t;
     double ic, lc;
-    lds_tab2(mad_u32((unsigned)__double2hiint(u) >> 15, 512u, tab.lg), ic, lc);  // top five mantissa bits; u == 2 -> entry 32
+    lds_tab2(mad_u32((unsigned)__double2hiint(u) >> 13, 16u, tab.lg), ic, lc);  // top seven mantissa bits; u == 2 -> entry 128
     const double rr = fma(u, ic, -1.0);
-    double q = K.l7;
-    q = fma(q, rr, kLogC6);
-    q = fma(q, rr, K.l5);
-    q = fma(q, rr, -0.25);
+    double q = fma(kLogC5, rr, -0.25);
     q = fma(q, rr, K.l3);
     q = fma(q, rr, -0.5);
     q = fma(q, rr, 1.0);
@@ -273,94 +262,6 @@ __device__ __forceinline__ void estep_dev(const SmemTab& tab, const EConst& K, d
     const double rmin = t * inv;
     r0 = (dhi >= 0) ? rmin : inv;
     h = fma(rmin, ax, l1p);  // |d| > 500 only when rmin < 1e-217: the clip does not show
-}
-
-// The same arithmetic for NR independent reads, written step by step across the reads so that the
-// NR dependency chains are interleaved in program order (ptxas keeps this order; left to itself it
-// runs the chains of separately inlined calls almost back to back).
-template <int NR>
-__device__ __forceinline__ void estep_dev_n(const SmemTab& tab, const EConst& K, const double (&d)[NR], double (&r0)[NR],
-                                            double (&h)[NR]) {
-    const double magic = 6755399441055744.0;
-    double ax[NR], t0[NR], kf[NR], r[NR], p[NR], t[NR], u[NR], ic[NR], lc[NR], rr[NR], q[NR], y0[NR], e[NR];
-    unsigned k[NR];
-    bool pos[NR];
-#pragma unroll
-    for (int i = 0; i < NR; ++i) {
-        const int dhi = __double2hiint(d[i]);
-        pos[i] = dhi >= 0;
-        const int ahi = min(dhi & 0x7fffffff, 0x407f4000);
-        ax[i] = __hiloint2double(ahi, __double2loint(d[i]));
-    }
-#pragma unroll
-    for (int i = 0; i < NR; ++i) t0[i] = fma(-ax[i], K.a32, magic);
-#pragma unroll
-    for (int i = 0; i < NR; ++i) {
-        kf[i] = t0[i] - magic;
-        k[i] = (unsigned)__double2loint(t0[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < NR; ++i) r[i] = fma(-kf[i], K.lhi, -ax[i]);
-#pragma unroll
-    for (int i = 0; i < NR; ++i) r[i] = fma(-kf[i], K.llo, r[i]);
-#pragma unroll
-    for (int i = 0; i < NR; ++i) t[i] = lds_tab(mad_u32(k[i] & 31u, 256u, tab.e2));
-#pragma unroll
-    for (int i = 0; i < NR; ++i) p[i] = fma(K.c6, r[i], kExpC5);
-#pragma unroll
-    for (int i = 0; i < NR; ++i) p[i] = fma(p[i], r[i], K.c4);
-#pragma unroll
-    for (int i = 0; i < NR; ++i) p[i] = fma(p[i], r[i], K.c3);
-#pragma unroll
-    for (int i = 0; i < NR; ++i) p[i] = fma(p[i], r[i], 0.5);
-#pragma unroll
-    for (int i = 0; i < NR; ++i) p[i] = fma(p[i], r[i], 1.0);
-#pragma unroll
-    for (int i = 0; i < NR; ++i) p[i] = fma(p[i], r[i], 1.0);
-#pragma unroll
-    for (int i = 0; i < NR; ++i) {
-        t[i] = t[i] * p[i];
-        t[i] = __hiloint2double((int)mad_u32(k[i] & ~31u, 32768u, (unsigned)__double2hiint(t[i])), __double2loint(t[i]));
-    }
-#pragma unroll
-    for (int i = 0; i < NR; ++i) u[i] = 1.0 + t[i];
-#pragma unroll
-    for (int i = 0; i < NR; ++i) {
-        lds_tab2(mad_u32((unsigned)__double2hiint(u[i]) >> 15, 512u, tab.lg), ic[i], lc[i]);
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0[i]) : "d"(u[i]));
-    }
-#pragma unroll
-    for (int i = 0; i < NR; ++i) {
-        rr[i] = fma(u[i], ic[i], -1.0);
-        e[i] = fma(-u[i], y0[i], 1.0);
-    }
-#pragma unroll
-    for (int i = 0; i < NR; ++i) {
-        q[i] = fma(K.l7, rr[i], kLogC6);
-        e[i] = fma(e[i], e[i], e[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < NR; ++i) {
-        q[i] = fma(q[i], rr[i], K.l5);
-        y0[i] = fma(y0[i], e[i], y0[i]);  // 1/u (xrcp3)
-    }
-#pragma unroll
-    for (int i = 0; i < NR; ++i) {
-        q[i] = fma(q[i], rr[i], -0.25);
-        t[i] = t[i] * y0[i];  // rmin
-    }
-#pragma unroll
-    for (int i = 0; i < NR; ++i) q[i] = fma(q[i], rr[i], K.l3);
-#pragma unroll
-    for (int i = 0; i < NR; ++i) q[i] = fma(q[i], rr[i], -0.5);
-#pragma unroll
-    for (int i = 0; i < NR; ++i) q[i] = fma(q[i], rr[i], 1.0);
-#pragma unroll
-    for (int i = 0; i < NR; ++i) {
-        const double l1p = fma(q[i], rr[i], lc[i]);
-        r0[i] = pos[i] ? t[i] : y0[i];
-        h[i] = fma(t[i], ax[i], l1p);
-    }
 }
 
 template <int TW, int MAXT>
@@ -374,12 +275,11 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
 
     double* tab_e2 = reinterpret_cast<double*>(smem_raw);
     double2* tab_lg = reinterpret_cast<double2*>(tab_e2 + kTabExpDoubles);
-    for (int i = threadIdx.x; i < kTabExpDoubles; i += blockDim.x) tab_e2[i] = XPT(kExp2)[i >> 5];
-    for (int i = threadIdx.x; i < 33 * 32; i += blockDim.x)
-        tab_lg[i] = make_double2(XPT(kInvC)[i >> 5], XPT(kLogC)[i >> 5]);
+    for (int i = threadIdx.x; i < kTabExpDoubles; i += blockDim.x) tab_e2[i] = XPT(kExp2)[i];
+    for (int i = threadIdx.x; i < 129; i += blockDim.x) tab_lg[i] = make_double2(XPT(kInvC)[i], XPT(kLogC)[i]);
     SmemTab tab;
-    tab.e2 = smem_u32(tab_e2 + lane);
-    tab.lg = smem_u32(tab_lg + lane) - 0x7fe0u * 512u;
+    tab.e2 = smem_u32(tab_e2);
+    tab.lg = smem_u32(tab_lg) - (0x3ff00000u >> 13) * 16u;
 
     unsigned char* wbase = smem_raw + kFitTableBytes + (size_t)team * fit_team_smem_bytes(a.cap, G, TW);
     double* slab = reinterpret_cast<double*>(wbase);

@@ -57,22 +57,15 @@ XP_TABLE(kLgam, 7, 6.41025641025641025641e-3, -1.91752691752691752692e-3, 8.4175
 XP_TABLE(kMisc, 6, 6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.44269504088896338700e+00,
          6.931471805599453094e-01, 1.41421356237309504880e+00, 6755399441055744.0)
 
-#include "xp_tables.inc"
-// 32/ln2, ln2/32 split hi/lo (hi has 20 trailing zero bits), 1/6!, 1/5!, 1/4!, 1/3!
-// (entries 3, 4 are superseded by kExpC6 / kExpC5 below)
-XP_TABLE(kE32, 7, 46.16624130844683, 0.021660849390173098, 2.3251928472369475e-12,
-         1.388888888888889e-03, 8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01)
-// log1p(r) = r (1 + r (c1 + r (c2 + ...))):  1/7 -1/6 1/5 -1/4 1/3 -1/2
-XP_TABLE(kL1p, 6, 1.4285714285714285e-01, -1.6666666666666666e-01, 2.0e-01, -2.5e-01, 3.3333333333333331e-01,
-         -5.0e-01)
+#include "xp_tables.inc"  // kExp2[256], kInvC[129], kLogC[129], kE256[3] (tools/make_tables.py)
+// full-precision series coefficients of the E-step: 1/3! (exp) and 1/3 (log1p)
+XP_TABLE(kE3, 2, 1.6666666666666666e-01, 3.3333333333333331e-01)
 
-// The two highest-order coefficients of each E-step series rounded to doubles whose low word is
-// zero: DFMA takes them as 32-bit immediates.  Their rounding (rel. 2^-22) is far below the weight
-// of the terms they multiply (r^5/120 <= 1.2e-12, rr^6/6 <= 2.4e-12 relative to the results).
-constexpr double kExpC6 = 0x1.6c16c00000000p-10;   // ~ 1/720
-constexpr double kExpC5 = 0x1.1111100000000p-7;    // ~ 1/120
-constexpr double kLogC7 = 0x1.2492500000000p-3;    // ~ 1/7
-constexpr double kLogC6 = -0x1.5555500000000p-3;   // ~ -1/6
+// The highest-order coefficient of each E-step series rounded to a double whose low word is zero: DFMA
+// takes it as a 32-bit immediate.  Its rounding (rel. 2^-21) is far below the weight of the term it
+// multiplies (r^4/24 <= 1.4e-13, rr^5/5 <= 1.9e-13 relative to the results).
+constexpr double kExpC4 = 0x1.5555500000000p-5;   // ~ 1/24
+constexpr double kLogC5 = 0x1.9999900000000p-3;   // ~ 1/5
 
 XP_HD uint64_t d2u(double x) {
 #if defined(__CUDA_ARCH__)
