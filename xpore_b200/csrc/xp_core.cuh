@@ -92,11 +92,24 @@ XP_HD void estep_read(const Tab& tab, double d, double& inv, double& rmin, doubl
     h = fma(rmin, ax, l1p);  // |d| > 500 only when rmin < 1e-217: the clip does not show
 }
 
+// ---- psi / lgamma of one posterior parameter inside the sweeps (xp_math.cuh: shift10, xlog_tab) -------
+// Returns psi(x), lgamma(x) + ln den and den, where den is the shift product (1 for x >= 10): the caller
+// multiplies the den of all its parameters and subtracts one logarithm of the product from the ELBO.
+template <class Tab>
+XP_HD void psi_lgamma_parts(const Tab& tab, double x, double* psi, double* lgam_plus_lden, double* den_out) {
+    double z, num, den;
+    shift10(x, z, num, den);
+    const double lz = xlog_tab(tab, z);
+    const double q = xrcp3(z * den);
+    psi_lgamma_shifted(z, lz, q * den, num * (q * z), psi, lgam_plus_lden);
+    *den_out = den;
+}
+
 // ---- M-step for one component (gmm.py:364-370 in centred moments) ------------------------
 XP_HD Comp mstep(double Nk, double S1, double S2, double a0, double b0) {
     Comp c;
     c.lam = 1.0 + Nk;
-    c.il = xdiv(1.0, c.lam);
+    c.il = xdiv3(1.0, c.lam);
     c.mp = S1 * c.il;
     c.alpha = a0 + 0.5 * Nk;
     c.beta = b0 + 0.5 * (S2 - S1 * S1 * c.il);
@@ -110,7 +123,7 @@ XP_HD Comp mstep(double Nk, double S1, double S2, double a0, double b0) {
 XP_HD double elbo_component(const Comp& c, double Nk, double S1, double S2, double a0, double b0,
                             double prior_gamma, double psi_a, double lg_a, double ln_b, double ln_lam,
                             double& tbar, double& ltau) {
-    tbar = xdiv(c.alpha, c.beta);
+    tbar = xdiv3(c.alpha, c.beta);
     ltau = psi_a - ln_b;
     const double il = c.il;
     const double m2 = c.mp * c.mp;
@@ -140,7 +153,7 @@ XP_HD int stop_rule(double elbo_new, double elbo_old, double stopping) {
     const double delta = elbo_new - elbo_old;
     if (rint(delta * 1e8) < 0.0) return 2;
     if (elbo_old == -INFINITY) return 0;  // first sweep: the reference compares with the ELBO of a random q(z)
-    const double diff = xdiv(delta, fabs(elbo_old));
+    const double diff = xdiv3(delta, fabs(elbo_old));
     return (diff < stopping) ? 1 : 0;
 }
 

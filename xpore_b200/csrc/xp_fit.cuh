@@ -88,10 +88,15 @@ __host__ __device__ inline size_t fit_team_smem_bytes(int cap, int G, int TW) {
 }
 
 // shared-memory tables, addressed through the 32-bit shared window
+struct SmemTab;
+__device__ __forceinline__ void lds_tab2(uint32_t a, double& x, double& y);
 struct SmemTab {
     uint32_t e2;  // 2^(j/256), 8 bytes per entry
     uint32_t lg;  // {1/c, ln c}, 16 bytes per entry, biased so that entry i of u = 1 + t in [1, 2] is found
                   // at lg + 16 * (hi32(u) >> 13)
+    __device__ __forceinline__ void logc(int i, double& ic, double& lc) const {  // entry i (xlog_tab)
+        lds_tab2(lg + ((0x3ff00000u >> 13) + (unsigned)i) * 16u, ic, lc);
+    }
 };
 __device__ __forceinline__ double lds_tab(uint32_t a) {  // tables are immutable after the prologue
     double v;
@@ -501,32 +506,41 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
                     const int s = s0 + lane;
                     const int role = (s < 2 * G) ? 0 : (s < 2 * G + 2) ? 1 : (s < 2 * G + 6) ? 2 : 3;
                     double x = 16.0;
-                    bool present = false;
+                    bool counted = false;  // lgamma of this slot enters the ELBO
                     if (role == 0) {
                         const int g = s >> 1;
                         const int ng = goff[g + 1] - goff[g];
                         const double v = tot[g];
-                        present = ng > 0;
+                        counted = ng > 0;
                         x = conc0 + ((kpar && !first) ? ((double)ng - v) : v);
-                    } else if (role == 1) x = c.alpha;
-                    else if (role == 2) x = (s < 2 * G + 4) ? c.beta : c.lam;
+                    } else if (role == 1) {
+                        x = c.alpha;
+                        counted = true;
+                    } else if (role == 2) x = (s < 2 * G + 4) ? c.beta : c.lam;
                     double z, num, den;
-                    shift_to_10(role == 2 ? 16.0 : x, z, num, den);
+                    shift10(role == 2 ? 16.0 : x, z, num, den);
                     if (role == 2) z = x;
-                    const double lz = xlog(z), lden = xlog(den);
-                    const double q = xrcp(z * den);
+                    // one logarithm serves the ln den of every counted slot of this pass: ln of their product
+                    // (den <= 10!, at most 32 factors)
+                    double dp = counted ? den : 1.0;
+#pragma unroll
+                    for (int m = 16; m > 0; m >>= 1) dp *= __shfl_xor_sync(kFull, dp, m);
+                    const double lz = xlog_tab(tab, z);
+                    const double q = xrcp3(z * den);
                     double ps, lg;
-                    psi_lgamma_finish(z, lz, lden, q * den, num * (q * z), &ps, &lg);
+                    psi_lgamma_shifted(z, lz, q * den, num * (q * z), &ps, &lg);
+                    const double ldp = xlog_tab(tab, dp);
                     const double pso = __shfl_xor_sync(kFull, ps, 1);
                     if (role == 0) {
                         if (kpar) Asm[s >> 1] = ps - pso;  // psi(c_g1) - psi(c_g0)  (gmm.py:283-284)
-                        if (present) e_loc += lg;          // + sum_k lgamma(c_gk)
+                        if (counted) e_loc += lg;          // + sum_k lgamma(c_gk) (+ ln den, taken off below)
                     } else if (role == 1) {
                         sc[kpar] = ps;
-                        sc[2 + kpar] = lg;
+                        sc[2 + kpar] = lg;                 // lgamma(alpha_k) + ln den
                     } else if (role == 2) {
                         sc[4 + (s - 2 * G - 2)] = lz;
                     }
+                    if (lane == 0) e_loc -= ldp;
                 }
                 __syncwarp();
                 double tb, lt;

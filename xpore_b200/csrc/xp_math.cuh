@@ -133,7 +133,7 @@ XP_HD double xrcp(double x) {
 #endif
 }
 
-// 1/x for x in [1, 2].  Device: hardware seed (rel. error <= 2^-20) + one cubic step
+// 1/x for normal positive x (the E-step calls it with x in [1, 2]).  Device: hardware seed (rel. error <= 2^-20) + one cubic step
 // y (1 + e + e^2), e = 1 - x y  (error e^3, <= 1 ulp).
 XP_HD double xrcp3(double x) {
 #if defined(__CUDA_ARCH__)
@@ -151,6 +151,15 @@ XP_HD double xrcp3(double x) {
 XP_HD double xdiv(double a, double b) {
 #if defined(__CUDA_ARCH__)
     return a * xrcp(b);
+#else
+    return a / b;
+#endif
+}
+// the same with the one-step cubic reciprocal (the hardware seed is good to 2^-20 for every normal
+// operand, so the cubic step leaves <= 2^-60): one DFMA less, used once per sweep and call site.
+XP_HD double xdiv3(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return a * xrcp3(b);
 #else
     return a / b;
 #endif
@@ -229,6 +238,71 @@ XP_HD void shift_to_10(double x, double& z, double& num, double& den) {
         z += 1.0;
     }
 }
+// The same shift for the sweeps' scalar phase, without a data-dependent loop: every x < 10 moves up by
+// exactly ten, z = x + 10, and the two products are the fixed polynomials
+//   den = P(x) = x (x+1) ... (x+9) = sum_k [10 k] x^k      (unsigned Stirling numbers of the first kind)
+//   num = P'(x)                                            (so num/den = sum_j 1/(x+j))
+// evaluated by two independent Horner chains (all coefficients are small integers, x > 0: no cancellation).
+XP_HD void shift10(double x, double& z, double& num, double& den) {
+    double p = x + 45.0;
+    double d = fma(10.0, x, 405.0);
+    p = fma(p, x, 870.0);
+    d = fma(d, x, 6960.0);
+    p = fma(p, x, 9450.0);
+    d = fma(d, x, 66150.0);
+    p = fma(p, x, 63273.0);
+    d = fma(d, x, 379638.0);
+    p = fma(p, x, 269325.0);
+    d = fma(d, x, 1346625.0);
+    p = fma(p, x, 723680.0);
+    d = fma(d, x, 2894720.0);
+    p = fma(p, x, 1172700.0);
+    d = fma(d, x, 3518100.0);
+    p = fma(p, x, 1026576.0);
+    d = fma(d, x, 2053152.0);
+    p = fma(p, x, 362880.0);
+    d = fma(d, x, 362880.0);
+    p = p * x;
+    const bool sh = x < 10.0;
+    z = sh ? x + 10.0 : x;
+    num = sh ? d : 0.0;
+    den = sh ? p : 1.0;
+}
+
+// ln x of a positive normal double through the E-step's {1/c, ln c} table: x = 2^e u, u in [1, 2),
+// ln u = ln c_i + ln1p(u / c_i - 1) with the degree-5 series (absolute error < 1e-15).
+template <class Tab>
+XP_HD double xlog_tab(const Tab& tab, double x) {
+    const int hx = hi32(x);
+    const int i = (hx >> 13) & 127;
+    const double u = mk64((hx & 0x000fffff) | 0x3ff00000, lo32(x));
+    const double e = (double)((hx >> 20) - 1023);
+    double ic, lc;
+    tab.logc(i, ic, lc);
+    const double rr = fma(u, ic, -1.0);
+    double q = fma(kLogC5, rr, -0.25);
+    q = fma(q, rr, XPT(kE3)[1]);
+    q = fma(q, rr, -0.5);
+    q = fma(q, rr, 1.0);
+    const double lu = fma(q, rr, lc);
+    return fma(e, XPT(kMisc)[0], fma(e, XPT(kMisc)[1], lu));
+}
+
+// psi and lgamma + ln den from the shifted argument: lz = ln z, iz = 1/z, sden = num/den.  The caller
+// subtracts ln den itself (the scalar phase takes one logarithm of the product of all its den).
+XP_HD void psi_lgamma_shifted(double z, double lz, double iz, double sden, double* psi, double* lgam_plus_lden) {
+    const double w = iz * iz;
+    double a = XPT(kPsi)[0];
+    double b = XPT(kLgam)[0];
+#pragma unroll
+    for (int i = 1; i < 7; ++i) {
+        a = fma(a, w, XPT(kPsi)[i]);
+        b = fma(b, w, XPT(kLgam)[i]);
+    }
+    *psi = lz - 0.5 * iz - a * w - sden;
+    *lgam_plus_lden = fma(z - 0.5, lz, -z) + kHalfLn2Pi + b * iz;
+}
+
 // lz = ln z, lden = ln den, iz = 1/z, sden = num/den
 XP_HD void psi_lgamma_finish(double z, double lz, double lden, double iz, double sden, double* psi, double* lgam) {
     const double w = iz * iz;
