@@ -299,11 +299,13 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
 // records come back on the copy-out stream, so PCIe (full duplex) and the SMs work concurrently.
 namespace {
 constexpr int kMaxChunks = 64;
-constexpr size_t kChunkBytes = 192u << 20;
+constexpr size_t kChunkBytes = 112u << 20;
+
+constexpr int kComputeStreams = 3;
 
 struct DevCache {
     int device = -1;
-    cudaStream_t s_in = nullptr, s_c = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_c[kComputeStreams] = {nullptr, nullptr, nullptr}, s_out = nullptr;
     cudaEvent_t e_in[kMaxChunks], e_done[kMaxChunks];
     void* buf = nullptr;
     size_t cap = 0;
@@ -328,7 +330,7 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
         dc = new DevCache();
         dc->device = device;
         CK(cudaStreamCreateWithFlags(&dc->s_in, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&dc->s_c, cudaStreamNonBlocking));
+        for (int i = 0; i < kComputeStreams; ++i) CK(cudaStreamCreateWithFlags(&dc->s_c[i], cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&dc->s_out, cudaStreamNonBlocking));
         for (int i = 0; i < kMaxChunks; ++i) {
             CK(cudaEventCreateWithFlags(&dc->e_in[i], cudaEventDisableTiming));
@@ -342,16 +344,38 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
     const size_t eb = b->y_format == XPB200_Y_F64 ? 8 : (b->y_format == XPB200_Y_I32 ? 4 : 2);
     const int FW = xpc::fit_width(G), SW = xpc::stats_width(G, C);
 
-    // chunk boundaries (positions), cut where the read offsets cross multiples of the chunk size
+    // chunk boundaries (positions), cut where the read offsets cross the chunk targets.  The first chunks are
+    // small (1/8, 1/4, 1/2 of a full chunk) so the SMs start early, and so is the last one, whose result copy
+    // is the only one nothing overlaps with.
     const int64_t* roff = b->read_off;
-    int nchunks = (int)std::min<size_t>(kMaxChunks, std::max<size_t>(1, ((size_t)b->n_reads * eb + kChunkBytes - 1) / kChunkBytes));
-    std::vector<int> cut(nchunks + 1, 0);
-    cut[nchunks] = P;
-    for (int c = 1; c < nchunks; ++c) {
-        const int64_t target = (int64_t)((double)b->n_reads * c / nchunks);
-        cut[c] = (int)(std::lower_bound(roff, roff + P + 1, target) - roff);
-        cut[c] = std::min(std::max(cut[c], cut[c - 1]), P);
+    const size_t chunk_bytes = (size_t)std::max(1, env_int("XPB200_CHUNK_MB", (int)(kChunkBytes >> 20))) << 20;
+    const size_t total_bytes = (size_t)b->n_reads * eb;
+    std::vector<int> cut(1, 0);
+    {
+        std::vector<size_t> ends;  // byte targets of the chunk ends
+        size_t pos = 0;
+        const size_t ramp[3] = {chunk_bytes / 8, chunk_bytes / 4, chunk_bytes / 2};
+        const size_t tail = chunk_bytes / 4;
+        for (int i = 0; i < 3 && total_bytes > 2 * chunk_bytes && pos + ramp[i] + tail < total_bytes; ++i) {
+            pos += ramp[i];
+            ends.push_back(pos);
+        }
+        const size_t last_start = (total_bytes > 2 * chunk_bytes) ? total_bytes - tail : total_bytes;
+        while (pos + chunk_bytes < last_start && (int)ends.size() < kMaxChunks - 2) {
+            pos += chunk_bytes;
+            ends.push_back(pos);
+        }
+        if (last_start < total_bytes && pos < last_start) ends.push_back(last_start);
+        for (size_t e : ends) {
+            const int64_t target = (int64_t)(e / eb);
+            int p = (int)(std::lower_bound(roff, roff + P + 1, target) - roff);
+            p = std::min(std::max(p, cut.back()), P);
+            if (p > cut.back() && p < P) cut.push_back(p);
+        }
+        cut.push_back(P);
     }
+    const int nchunks = (int)cut.size() - 1;
+    const int n_streams = std::min(kComputeStreams, std::max(1, env_int("XPB200_STREAMS", 2)));
 
     // device layout
     size_t o = 0;
@@ -411,7 +435,8 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
         CK(cudaMemcpyAsync(d_ks + p0, b->kmer_std + p0, (size_t)pc * 8, cudaMemcpyDefault, dc->s_in));
         CK(cudaEventRecord(dc->e_in[c], dc->s_in));
         // compute
-        CK(cudaStreamWaitEvent(dc->s_c, dc->e_in[c], 0));
+        cudaStream_t sc = dc->s_c[c % n_streams];
+        CK(cudaStreamWaitEvent(sc, dc->e_in[c], 0));
         xpb200_batch db = *b;
         db.n_positions = pc;
         db.n_reads = r1 - r0;
@@ -420,12 +445,12 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
         xpb200_result dr;
         dr.status = d_status + p0; dr.n_iter = d_niter + p0; dr.pval = d_pval + p0;
         dr.fit = d_fit + (size_t)p0 * FW; dr.stats = d_stats + (size_t)p0 * SW;
-        CK(cudaMemsetAsync(dr.n_iter, 0, (size_t)pc * 4, dc->s_c));
-        CK(cudaMemsetAsync(dr.fit, 0xFF, (size_t)pc * FW * 8, dc->s_c));
-        CK(cudaMemsetAsync(dr.stats, 0xFF, (size_t)pc * SW * 8, dc->s_c));
-        if (int rc = xpb200_fit_device(&db, m, &dr, d + o_ws[c], xpb200_workspace_bytes(pc), d_nf + c, dc->s_c))
+        CK(cudaMemsetAsync(dr.n_iter, 0, (size_t)pc * 4, sc));
+        CK(cudaMemsetAsync(dr.fit, 0xFF, (size_t)pc * FW * 8, sc));
+        CK(cudaMemsetAsync(dr.stats, 0xFF, (size_t)pc * SW * 8, sc));
+        if (int rc = xpb200_fit_device(&db, m, &dr, d + o_ws[c], xpb200_workspace_bytes(pc), d_nf + c, sc))
             return rc;
-        CK(cudaEventRecord(dc->e_done[c], dc->s_c));
+        CK(cudaEventRecord(dc->e_done[c], sc));
         // copy-out
         CK(cudaStreamWaitEvent(dc->s_out, dc->e_done[c], 0));
         CK(cudaMemcpyAsync(r->status + p0, dr.status, (size_t)pc * 4, cudaMemcpyDefault, dc->s_out));
@@ -437,7 +462,7 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
     uint32_t nf[kMaxChunks];
     CK(cudaMemcpyAsync(nf, d_nf, sizeof(nf), cudaMemcpyDefault, dc->s_out));
     CK(cudaStreamSynchronize(dc->s_out));
-    CK(cudaStreamSynchronize(dc->s_c));
+    for (int i = 0; i < kComputeStreams; ++i) CK(cudaStreamSynchronize(dc->s_c[i]));
     CK(cudaStreamSynchronize(dc->s_in));
     uint32_t total = 0;
     for (int c = 0; c < nchunks; ++c) total += nf[c];
@@ -450,7 +475,7 @@ void xpb200_release(void) {
     for (auto* c : g_cache) {
         cudaSetDevice(c->device);
         if (c->buf) cudaFree(c->buf);
-        for (cudaStream_t st : {c->s_in, c->s_c, c->s_out})
+        for (cudaStream_t st : {c->s_in, c->s_c[0], c->s_c[1], c->s_c[2], c->s_out})
             if (st) cudaStreamDestroy(st);
         for (int i = 0; i < kMaxChunks; ++i) {
             cudaEventDestroy(c->e_in[i]);
