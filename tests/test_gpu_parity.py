@@ -149,8 +149,11 @@ def test_device_path_vs_oracle(torch_cuda, shape):
 
 @pytest.mark.parametrize("shift,expect", [(0.0, 2), (-200.0, 1), (1e-9, 0)])
 def test_encoded_reads_bit_identical(torch_cuda, shift, expect):
-    """u16 / i32 scaled-integer read buffers decode to the very same doubles: every record must be
-    bit-identical to the f64 path, through both entry points; non-representable data stays f64."""
+    """u16 / i32 scaled-integer read buffers decode to the very same doubles: every fit / statistics
+    record must be bit-identical to the f64 path, through both entry points; non-representable data
+    stays f64.  The prefilter of the u16 format works on exact integer sums (its t statistic carries
+    only the final roundings), so its p-values agree with the f64 path to rounding, not bit for bit;
+    the selection must be identical."""
     torch = torch_cuda
     spec = Spec({"KO": 2, "WT": 3}, reads_lo=10, reads_hi=70, f_mod=0.4, seed=41,
                 method={"prefiltering": {"method": "t-test", "threshold": 0.2}})
@@ -166,7 +169,10 @@ def test_encoded_reads_bit_identical(torch_cuda, shift, expect):
     for r in (enc, dev):
         np.testing.assert_array_equal(r.status, ref.status)
         np.testing.assert_array_equal(r.n_iter, ref.n_iter)
-        np.testing.assert_array_equal(r.pval, ref.pval)
+        if expect == 2:
+            np.testing.assert_allclose(r.pval, ref.pval, rtol=1e-11, atol=0, equal_nan=True)
+        else:
+            np.testing.assert_array_equal(r.pval, ref.pval)
         sel = ref.selected
         np.testing.assert_array_equal(r.fit[sel], ref.fit[sel])
         np.testing.assert_array_equal(r.stats[sel], ref.stats[sel])
@@ -262,7 +268,10 @@ def test_scaled_integer_decode_exhaustive(torch_cuda):
         ref = xf.fit_batch(b, m)
         assert b.encode_reads() == fmt
         enc = xf.fit_batch(b, m)
-        np.testing.assert_array_equal(ref.pval, enc.pval)
+        if fmt == 2:  # the u16 prefilter sums integers exactly: equal to rounding; the fit decodes every read
+            np.testing.assert_allclose(enc.pval, ref.pval, rtol=1e-11, atol=0, equal_nan=True)
+        else:
+            np.testing.assert_array_equal(ref.pval, enc.pval)
         np.testing.assert_array_equal(ref.fit, enc.fit)
 
 

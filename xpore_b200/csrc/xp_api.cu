@@ -170,7 +170,11 @@ int launch_prefilter(const xpb200_batch* b, const xpb200_method* m, uint32_t* st
     a.status = status; a.pval = pval;
     constexpr int W = 4;
     const int tiles = (b->n_positions + 31) / 32;
-    xpk::xp_prefilter_kernel<W><<<(tiles + W - 1) / W, W * 32, 0, st>>>(a);
+    const int grid = (tiles + W - 1) / W;
+    if (b->y_format == XPB200_Y_U16 && b->max_reads <= xpk::kPfIntMaxReads)
+        xpk::xp_prefilter_kernel<W, true><<<grid, W * 32, 0, st>>>(a);
+    else
+        xpk::xp_prefilter_kernel<W, false><<<grid, W * 32, 0, st>>>(a);
     ++g_launches;
     CK(cudaGetLastError());
     return 0;

@@ -186,6 +186,21 @@ XP_HD void ttest_from_moments(double na, double s1a, double s2a, double nb, doub
     t = (ma - mb) / denom;
 }
 
+// The same statistic from exact integer sums of a scaled-integer encoding: s1 = sum q (exact),
+// nss = n sum q^2 - (sum q)^2 (exact; = n times the side's sum of squared deviations).  t is invariant
+// under the common scale and origin of q, so neither enters.
+XP_HD void ttest_from_exact_sums(double na, double s1a, double nssa, double nb, double s1b, double nssb,
+                                 double& t, double& df) {
+    df = na + nb - 2.0;
+    if (na < 2.0 || nb < 2.0) {
+        t = NAN;
+        return;
+    }
+    const double svar = (nssa / na + nssb / nb) / df;
+    const double denom = sqrt(svar * (1.0 / na + 1.0 / nb));
+    t = ((s1a * nb - s1b * na) / (na * nb)) / denom;  // s1a nb - s1b na < 2^47: exact
+}
+
 // ---- statistics + row filter (io.py:255-367, utils/stats.py) -------------------------------
 XP_HD double norm_cdf(double x, double mu, double sigma) {  // stats.py:35-36
     return 0.5 * (1.0 + xerf((x - mu) / (sigma * sqrt(2.0))));

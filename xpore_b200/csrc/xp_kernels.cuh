@@ -137,8 +137,19 @@ struct PfMoments {
     double s1a, s2a, s1b, s2b;
     int na, nb;
 };
+// The u16 read format carries integers q = 100 y, so its moments are kept as exact integer sums
+// (sum q <= 2^31 and sum q^2 <= 2^47 for up to 32767 reads): three integer instructions per read instead of
+// a decode and four FP64 operations, and a t statistic that carries only the final roundings.
+struct PfIntMoments {
+    unsigned s1a, s1b;
+    unsigned long long s2a, s2b;
+    int na, nb;
+};
+constexpr int kPfIntMaxReads = 32767;
 
-template <int WARPS>
+// U16X: the batch is u16-encoded and no position has more than kPfIntMaxReads reads (the host checks
+// max_reads), so every position takes the exact-integer path and the FP accumulation is compiled out.
+template <int WARPS, bool U16X>
 __global__ void __launch_bounds__(WARPS * 32) xp_prefilter_kernel(PrefilterArgs a) {
     __shared__ int s_cond[kMaxGroups];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -152,14 +163,17 @@ __global__ void __launch_bounds__(WARPS * 32) xp_prefilter_kernel(PrefilterArgs 
     const double rscale = 1.0 / a.y_scale;
 
     double k_na = 0, k_s1a = 0, k_s2a = 0, k_nb = 0, k_s1b = 0, k_s2b = 0;
-    bool k_valid = false;
+    bool k_valid = false, k_exact = false;
     for (int round = 0; round < kPfLanes; ++round) {
         const int p = p0 + round * kPfPerRound + sub;
         PfMoments m = {0.0, 0.0, 0.0, 0.0, 0, 0};
-        bool valid = false;
+        PfIntMoments mi = {0u, 0u, 0ull, 0ull, 0, 0};
+        bool valid = false, exact = false;
+        int n_pos = 0;
         if (p < a.P) {
             const int64_t off = a.read_off[p];
             const int n = (int)(a.read_off[p + 1] - off);
+            n_pos = n;
             const double m0 = a.kmer_mean[p];
             const int32_t* glen = a.grp_len + (size_t)p * G;
             // conditions present at this position; the lower-numbered one is side 0
@@ -189,7 +203,22 @@ __global__ void __launch_bounds__(WARPS * 32) xp_prefilter_kernel(PrefilterArgs 
                 // Lane sl takes the 8-read blocks sl, sl+4, ... of the position (position-local, so the
                 // moments depend neither on the read encoding nor on where the position sits in the
                 // buffer).
-                if (a.y_format == kYU16) {
+                bool side_a = (s_cond[0] == ca);  // side of the current group; looked up only at a boundary
+                auto addq = [&](unsigned q, int i) {  // read i of the position, raw integer
+                    while (i >= gend) {
+                        ++g;
+                        gend += glen[g];
+                        side_a = (s_cond[g] == ca);
+                    }
+                    const unsigned long long qq = (unsigned long long)q * q;
+                    mi.s1a += side_a ? q : 0u;
+                    mi.s1b += side_a ? 0u : q;
+                    mi.s2a += side_a ? qq : 0ull;
+                    mi.s2b += side_a ? 0ull : qq;
+                    mi.na += side_a ? 1 : 0;
+                };
+                exact = U16X;
+                if (U16X || a.y_format == kYU16) {
                     // One 16-byte load per lane and step.  The buffer's aligned 16-byte chunk c holds the
                     // reads [8c - head, 8c - head + 8) of the position, so block b = the tail of chunk b
                     // + the first `head` reads of chunk b+1, which the next lane of the quad has
@@ -220,10 +249,18 @@ __global__ void __launch_bounds__(WARPS * 32) xp_prefilter_kernel(PrefilterArgs 
                         const unsigned x[4] = {__funnelshift_r(w0, w1, hs), __funnelshift_r(w1, w2, hs),
                                                __funnelshift_r(w2, w3, hs), __funnelshift_r(w3, w4, hs)};
                         const int ibase = bq << 3;
+                        if (U16X && ibase + 8 <= n) {  // a full block: no per-read bound checks
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const unsigned q = (x[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-                            if (ibase + k < n) add(y_decode((double)q, a.y_scale, rscale), ibase + k);
+                            for (int k = 0; k < 8; ++k) addq((x[k >> 1] >> ((k & 1) * 16)) & 0xffffu, ibase + k);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const unsigned q = (x[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                                if (ibase + k < n) {
+                                    if (U16X) addq(q, ibase + k);
+                                    else add(y_decode((double)q, a.y_scale, rscale), ibase + k);
+                                }
+                            }
                         }
                         cur = nxt;
                         nxt = nn;
@@ -244,13 +281,34 @@ __global__ void __launch_bounds__(WARPS * 32) xp_prefilter_kernel(PrefilterArgs 
         // the four lanes of a position: fixed-order butterfly
 #pragma unroll
         for (int d = 1; d < kPfLanes; d <<= 1) {
-            m.s1a += __shfl_xor_sync(kFull, m.s1a, d);
-            m.s2a += __shfl_xor_sync(kFull, m.s2a, d);
-            m.s1b += __shfl_xor_sync(kFull, m.s1b, d);
-            m.s2b += __shfl_xor_sync(kFull, m.s2b, d);
-            m.na += __shfl_xor_sync(kFull, m.na, d);
-            m.nb += __shfl_xor_sync(kFull, m.nb, d);
+            if (!U16X) {
+                m.s1a += __shfl_xor_sync(kFull, m.s1a, d);
+                m.s2a += __shfl_xor_sync(kFull, m.s2a, d);
+                m.s1b += __shfl_xor_sync(kFull, m.s1b, d);
+                m.s2b += __shfl_xor_sync(kFull, m.s2b, d);
+                m.na += __shfl_xor_sync(kFull, m.na, d);
+                m.nb += __shfl_xor_sync(kFull, m.nb, d);
+                continue;
+            }
+            mi.s1a += __shfl_xor_sync(kFull, mi.s1a, d);
+            mi.s1b += __shfl_xor_sync(kFull, mi.s1b, d);
+            mi.s2a += __shfl_xor_sync(kFull, mi.s2a, d);
+            mi.s2b += __shfl_xor_sync(kFull, mi.s2b, d);
+            mi.na += __shfl_xor_sync(kFull, mi.na, d);
+            mi.nb += __shfl_xor_sync(kFull, mi.nb, d);
         }
+        if (U16X) mi.nb = n_pos - mi.na;
+        if (U16X) {  // exact sums -> the same six doubles (n, sum, sum of squares about the side's own origin)
+            m.na = mi.na;
+            m.nb = mi.nb;
+            m.s1a = (double)mi.s1a;
+            m.s1b = (double)mi.s1b;
+            // n S2 - S1^2 is exact in 64 bits (< 2^62); stored through s2 as "S2 - S1^2/n + S1^2/n" would
+            // round, so the t statistic below takes the exact numerators instead: s2 carries N = n S2 - S1^2.
+            m.s2a = (double)((unsigned long long)mi.na * mi.s2a - (unsigned long long)mi.s1a * mi.s1a);
+            m.s2b = (double)((unsigned long long)mi.nb * mi.s2b - (unsigned long long)mi.s1b * mi.s1b);
+        }
+        const bool t_exact = __shfl_sync(kFull, (int)exact, ((lane - round * kPfPerRound) & (kPfPerRound - 1)) * kPfLanes) != 0;
         // position round * 8 + j goes to lane round * 8 + j
         const int src = ((lane - round * kPfPerRound) & (kPfPerRound - 1)) * kPfLanes;
         const double t1a = __shfl_sync(kFull, m.s1a, src), t2a = __shfl_sync(kFull, m.s2a, src);
@@ -261,6 +319,7 @@ __global__ void __launch_bounds__(WARPS * 32) xp_prefilter_kernel(PrefilterArgs 
             k_na = tna; k_s1a = t1a; k_s2a = t2a;
             k_nb = tnb; k_s1b = t1b; k_s2b = t2b;
             k_valid = tv;
+            k_exact = t_exact;
         }
     }
     const int p = p0 + lane;
@@ -269,7 +328,8 @@ __global__ void __launch_bounds__(WARPS * 32) xp_prefilter_kernel(PrefilterArgs 
         uint32_t st = 0;
         if (k_valid) {
             double t, df;
-            ttest_from_moments(k_na, k_s1a, k_s2a, k_nb, k_s1b, k_s2b, t, df);
+            if (k_exact) ttest_from_exact_sums(k_na, k_s1a, k_s2a, k_nb, k_s1b, k_s2b, t, df);
+            else ttest_from_moments(k_na, k_s1a, k_s2a, k_nb, k_s1b, k_s2b, t, df);
             pv = student_t_two_sided(t, df);
             st |= STATUS_TTEST_VALID;
         }

@@ -338,28 +338,28 @@ XP_HD double betacf(double a, double b, double x) {
     const double tiny = 1e-300;
     const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
     double c = 1.0;
-    double d = 1.0 - qab * x / qap;
+    double d = 1.0 - xdiv3(qab * x, qap);
     if (fabs(d) < tiny) d = tiny;
-    d = 1.0 / d;
+    d = xdiv3(1.0, d);
     double h = d;
     for (int m = 1; m <= 500; ++m) {
         const double m2 = 2.0 * m;
-        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        double aa = xdiv3(m * (b - m) * x, (qam + m2) * (a + m2));
         d = 1.0 + aa * d;
         if (fabs(d) < tiny) d = tiny;
-        c = 1.0 + aa / c;
+        c = 1.0 + xdiv3(aa, c);
         if (fabs(c) < tiny) c = tiny;
-        d = 1.0 / d;
+        d = xdiv3(1.0, d);
         h *= d * c;
-        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        aa = -xdiv3((a + m) * (qab + m) * x, (a + m2) * (qap + m2));
         d = 1.0 + aa * d;
         if (fabs(d) < tiny) d = tiny;
-        c = 1.0 + aa / c;
+        c = 1.0 + xdiv3(aa, c);
         if (fabs(c) < tiny) c = tiny;
-        d = 1.0 / d;
+        d = xdiv3(1.0, d);
         const double del = d * c;
         h *= del;
-        if (fabs(del - 1.0) < 2e-16) break;
+        if (fabs(del - 1.0) < 4e-16) break;
     }
     return h;
 }
