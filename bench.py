@@ -339,9 +339,9 @@ def main():
             _lib.check(L.xpb200_fit_host(local_rank, C.byref(cb), C.byref(cm), C.byref(cr), C.byref(nf)))
             d2h_box[0] = sum(v.numel() * v.element_size() for v in hres.values()) + 4
         else:
-            # pinned host -> HBM, fit, compact, NCCL gather to rank 0, rank 0 copies the records to its host
-            db.upload()
-            xf.fit_device(db, method, out)
+            # pinned host -> HBM and fit, pipelined chunk by chunk inside xpb200_fit_host (result arrays
+            # are device memory here), compact, NCCL gather to rank 0, rank 0 copies the records to its host
+            _lib.check(L.xpb200_fit_host(local_rank, C.byref(cb), C.byref(cm), C.byref(cr), C.byref(nf)))
             rec, recbuf[0] = xf.pack_records_device(out, index_offset=rank * db.P, buf=recbuf[0])
             allrec = gather_records(rec, rank, world)
             if rank == 0:
@@ -414,8 +414,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "positions fitted/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_box[0],
                     "api": "xpb200_fit_host (C ABI, pinned host buffers)" if world == 1 else
-                           "pinned host -> DeviceBatch.upload -> xpb200_fit_device -> xpb200_pack_records -> "
-                           "NCCL gather -> rank-0 host"},
+                           "xpb200_fit_host (pinned host buffers in, device records out) -> "
+                           "xpb200_pack_records -> NCCL gather -> rank-0 host"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "xp_fit_kernel", "bound": "fp64", "achieved": achieved, "peak": peak.value,

@@ -27,6 +27,9 @@ def parse_options(argv):
                    help="at most this many ids are ingested and fitted per GPU call.")
     p.add_argument("--batch_bytes", dest="batch_bytes", type=int, default=256 << 20,
                    help="... or this many bytes of data.json text, whichever comes first.")
+    p.add_argument("--csr_cache", dest="csr_cache", default=None,
+                   help="binary CSR cache of the inputs (xpore_b200.csrcache): read instead of data.json when it "
+                        "matches the inputs, written on first use otherwise.")
     q = sub.add_parser("postprocessing", help="run mode for post-processing diffmod.table, the result table from "
                                               "differential modification analysis.")
     qreq = q.add_argument_group("required arguments")
