@@ -304,3 +304,37 @@ def test_repeated_launches_bit_identical(torch_cuda):
         np.testing.assert_array_equal(got.n_iter, ref.n_iter)
         np.testing.assert_array_equal(got.fit[sel], ref.fit[sel])
         np.testing.assert_array_equal(got.stats[sel], ref.stats[sel])
+
+
+def test_cli_writes_reference_table(torch_cuda, golden_case, tmp_path):
+    """The drop-in CLI end to end on the GPU: data.json/data.index -> native ingest -> CUDA path ->
+    diffmod.table/diffmod.log, against the rows the unmodified reference emitted (north-star tolerances);
+    again through the binary CSR hand-off, which must give the very same file; then `postprocessing`."""
+    import os
+
+    from xpore_b200 import cli
+    from xpore_b200.batch import Layout
+    from xpore_b200.config import Configurator
+
+    from helpers import compare_tables, read_table
+    exp = golden_case["expected"]
+    cfg = Configurator(golden_case["config_path"])
+    out = cfg.get_paths()["out_dir"]
+    method = cfg.get_method()
+    lay = Layout.from_data_info(cfg.get_data_info(), method["pooling"])
+    pm = method["prefiltering"]["method"] if method["prefiltering"] else None
+    cli.main(["xpore", "diffmod", "--config", golden_case["config_path"], "--n_processes", "2"])
+    table = os.path.join(out, "diffmod.table")
+    header, rows = read_table(table)
+    assert header == exp["header"]
+    compare_tables(rows, {tuple(r[:3]): r for r in exp["rows"]}, header, lay, pm, rtol_param=1e-5, rtol_p=1e-4)
+    lines = open(os.path.join(out, "diffmod.log")).read().splitlines()
+    assert lines[0] == "--- DIFFMOD ---" and lines[-1] == "--- SUCCESSFULLY FINISHED ---" and lines[1:-1] == exp["ids"]
+    first = open(table).read()
+    cache = str(tmp_path / "inputs.xpb")
+    for _ in range(2):  # builds the cache, then reuses it
+        cli.main(["xpore", "diffmod", "--config", golden_case["config_path"], "--csr_cache", cache])
+        assert open(table).read() == first
+    cli.main(["xpore", "postprocessing", "--diffmod_dir", out])
+    kept = open(os.path.join(out, "majority_direction_kmer_diffmod.table")).read().splitlines()
+    assert kept[0] == first.splitlines()[0] and set(kept[1:]) <= set(first.splitlines()[1:])
