@@ -338,3 +338,50 @@ def test_cli_writes_reference_table(torch_cuda, golden_case, tmp_path):
     cli.main(["xpore", "postprocessing", "--diffmod_dir", out])
     kept = open(os.path.join(out, "majority_direction_kmer_diffmod.table")).read().splitlines()
     assert kept[0] == first.splitlines()[0] and set(kept[1:]) <= set(first.splitlines()[1:])
+
+
+def test_edge_case_positions_vs_oracle(torch_cuda):
+    """Hand-made positions at the corners of the input space, one batch, every position against the
+    oracle: identical reads (zero variance), two far-apart clusters (|d| beyond the +-500 clip of
+    gmm.py:240), reads far from the k-mer mean, the smallest groups the selection lets through, a run
+    missing at a position, and read counts on both sides of the 1-warp / 4-warp split (1023 / 1024)."""
+    from xpore_b200.batch import Batch, Layout
+    rng = np.random.default_rng(11)
+    lay = Layout(["KO", "WT"], ["KO-r1", "KO-r2", "WT-r1", "WT-r2"], [0, 0, 1, 1], False)
+    km, ks = 100.0, 3.0
+    cases = []
+
+    def add(groups, kmean=km, kstd=ks):
+        cases.append(([np.round(np.asarray(g, dtype=np.float64), 2) for g in groups], kmean, kstd))
+
+    add([np.full(20, 101.37)] * 4)                                               # zero variance
+    add([np.r_[np.full(15, 60.0), np.full(15, 140.0)]] * 4)                        # two point masses, 80 apart
+    add([rng.normal(100, 3, 40), rng.normal(100, 3, 40), rng.normal(160, 1, 40), rng.normal(160, 1, 40)])
+    add([rng.normal(30, 2, 25) for _ in range(4)], kmean=120.0, kstd=2.0)        # all reads 45 sigma off the prior
+    add([rng.normal(100, 3, 2), rng.normal(100, 3, 2), rng.normal(108, 4, 2), rng.normal(108, 4, 2)])   # 2 reads per run
+    add([rng.normal(100, 3, 30), [], rng.normal(106, 4, 30), rng.normal(106, 4, 31)])                    # a run absent
+    for n in (1023, 1024, 1025):                                                  # single-warp / 4-warp team split
+        per = [n // 4 + (1 if j < n % 4 else 0) for j in range(4)]
+        add([np.r_[rng.normal(100, 3, m - m // 3), rng.normal(109, 4, m // 3)] if j >= 2 else rng.normal(100, 3, m)
+             for j, m in enumerate(per)])
+    add([np.r_[rng.normal(95, 2.5, 50), rng.normal(104, 2.5, 50)] for _ in range(4)])                    # both clusters everywhere
+
+    y = np.concatenate([np.concatenate(g) for g, _, _ in cases])
+    glen = np.asarray([[len(x) for x in g] for g, _, _ in cases], dtype=np.int32)
+    off = np.zeros(len(cases) + 1, dtype=np.int64)
+    np.cumsum(glen.sum(axis=1), out=off[1:])
+    batch = Batch(lay, y, off, glen, np.asarray([c[1] for c in cases]), np.asarray([c[2] for c in cases]))
+    method = xf.Method()  # no prefilter: every position is fitted
+    for encode in (False, True):
+        if encode:
+            assert batch.encode_reads() == 2
+        res = xf.fit_batch(batch, method)
+        assert res.n_fitted == len(cases)
+        for p in range(len(cases)):
+            f, present = _oracle_fit(batch, p, method)
+            assert res.n_iter[p] == f["n_iterations"], (p, res.n_iter[p], f["n_iterations"])
+            assert bool(res.status[p] & xf.CONVERGED) == f["converged"], p
+            np.testing.assert_allclose(res.mu[p], f["location"], rtol=1e-5, err_msg=str(p))
+            np.testing.assert_allclose(res.alpha[p], f["alpha"], rtol=1e-5, err_msg=str(p))
+            np.testing.assert_allclose(res.beta[p], f["beta"], rtol=1e-5, err_msg=str(p))
+            np.testing.assert_allclose(res.N[p][present], f["N"], rtol=1e-5, atol=1e-9, err_msg=str(p))
