@@ -311,38 +311,36 @@ def main():
     value = fitted_all / (ms_per_step * 1e-3)
 
     # ---- e2e: host buffers through the C ABI ----------------------------------------------
-    hres = {
-        "status": torch.zeros(db.P, dtype=torch.int32).pin_memory(),
-        "n_iter": torch.zeros(db.P, dtype=torch.int32).pin_memory(),
-        "pval": torch.zeros(db.P, dtype=torch.float64).pin_memory(),
-        "fit": torch.zeros((db.P, fit_w), dtype=torch.float64).pin_memory(),
-        "stats": torch.zeros((db.P, stats_w), dtype=torch.float64).pin_memory(),
-    }
     hb = db.host
     cb = _lib.XpBatch(db.P, db.G, db.C, db.max_reads, db.R, hb["y"].data_ptr(), hb["read_off"].data_ptr(),
                       hb["grp_len"].data_ptr(), hb["kmer_mean"].data_ptr(), hb["kmer_std"].data_ptr(),
                       hb["grp_cond"].data_ptr(), db.y_format, 0, db.y_scale)
     cm = method.c_struct()
-    # N = 1: results land in pinned host memory.  N > 1: results stay on the device of each rank,
-    # fitted records are gathered to rank 0 over NCCL and copied to its host there.
-    tgt = hres if world == 1 else {"status": out.status, "n_iter": out.n_iter, "pval": out.pval, "fit": out.fit,
-                                   "stats": out.stats}
-    cr = _lib.XpResult(tgt["status"].data_ptr(), tgt["n_iter"].data_ptr(), tgt["pval"].data_ptr(),
-                       tgt["fit"].data_ptr(), tgt["stats"].data_ptr())
+    cr = _lib.XpResult(out.status.data_ptr(), out.n_iter.data_ptr(), out.pval.data_ptr(), out.fit.data_ptr(),
+                       out.stats.data_ptr())  # N > 1: the dense results stay on the device of each rank
     nf = C.c_uint32(0)
     h2d = db.h2d_bytes
     d2h_box = [0]
     pinned_out = [None]
 
+    # N = 1: xpb200_fit_host_rows - pinned host buffers in, the records of diffmod.table's rows (fitted positions
+    # that pass the reference's row filter, io.py:363-367) out to pinned host memory: what `execute()` hands to
+    # the table writer.  N > 1: xpb200_fit_host with device result arrays, the same rows compacted on the
+    # device, gathered to rank 0 over NCCL and copied to its host there (the CLI gathers the same rows).
+    rec_w = 4 + fit_w + stats_w
+    rows_cap = max(1, n_fitted)
+    hrows = torch.empty((rows_cap, rec_w), dtype=torch.float64).pin_memory() if world == 1 else None
+    nrows = C.c_int64(0)
+
     def step_e2e():
         if world == 1:
-            _lib.check(L.xpb200_fit_host(local_rank, C.byref(cb), C.byref(cm), C.byref(cr), C.byref(nf)))
-            d2h_box[0] = sum(v.numel() * v.element_size() for v in hres.values()) + 4
+            _lib.check(L.xpb200_fit_host_rows(local_rank, C.byref(cb), C.byref(cm), hrows.data_ptr(), rows_cap,
+                                              C.byref(nrows), C.byref(nf)))
+            d2h_box[0] = int(nrows.value) * rec_w * 8 + 4 * 16
         else:
-            # pinned host -> HBM and fit, pipelined chunk by chunk inside xpb200_fit_host (result arrays
-            # are device memory here), compact, NCCL gather to rank 0, rank 0 copies the records to its host
             _lib.check(L.xpb200_fit_host(local_rank, C.byref(cb), C.byref(cm), C.byref(cr), C.byref(nf)))
             rec, recbuf[0] = xf.pack_records_device(out, index_offset=rank * db.P, buf=recbuf[0])
+            rec = rec[(rec[:, 1].to(torch.int64) & xf.KEEP_ROW) != 0]
             allrec = gather_records(rec, rank, world)
             if rank == 0:
                 if pinned_out[0] is None or pinned_out[0].shape[0] < allrec.shape[0]:
@@ -368,7 +366,13 @@ def main():
     if world == 1:
         assert int(nf.value) == n_fitted
         if not os.environ.get("XPB200_BENCH_NOVERIFY"):
-            assert (hres["n_iter"].to(dev) == out.n_iter).all()
+            # the rows that came back are the device-resident run's rows, record for record
+            keep = ((out.status.to(torch.int64) & (xf.SELECTED | xf.KEEP_ROW)) == (xf.SELECTED | xf.KEEP_ROW)).nonzero().flatten()
+            got = hrows[:int(nrows.value)].to(dev)
+            assert got.shape[0] == keep.numel()
+            assert (got[:, 0].to(torch.int64) == keep).all()
+            assert (got[:, 2].to(torch.int32) == out.n_iter[keep]).all()
+            assert torch.equal(got[:, 4:4 + fit_w], out.fit[keep])
 
     if rank == 0:
         fit_ms = float(np.median(stage_ms[:, 2]))
@@ -413,9 +417,10 @@ def main():
                        "read_sweeps_per_s": read_iters * world / (ms_per_step * 1e-3)},
             "e2e": {"value": e2e_value, "unit": "positions fitted/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_box[0],
-                    "api": "xpb200_fit_host (C ABI, pinned host buffers)" if world == 1 else
+                    "api": "xpb200_fit_host_rows (C ABI, pinned host buffers in, records of the rows of diffmod.table out)"
+                           if world == 1 else
                            "xpb200_fit_host (pinned host buffers in, device records out) -> "
-                           "xpb200_pack_records -> NCCL gather -> rank-0 host"},
+                           "xpb200_pack_records -> rows that pass the row filter -> NCCL gather -> rank-0 host"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "xp_fit_kernel", "bound": "fp64", "achieved": achieved, "peak": peak.value,

@@ -114,6 +114,15 @@ int32_t xpb200_fit_device(const xpb200_batch* batch, const xpb200_method* method
 int32_t xpb200_fit_host(int32_t device, const xpb200_batch* batch, const xpb200_method* method,
                         const xpb200_result* result, uint32_t* n_fitted);
 
+/* Same path on HOST pointers when only diffmod.table matters: nothing but the records of the table's rows
+ * comes back - the positions that were fitted AND pass the reference's row filter (io.py:363-367) - as
+ * rows[n_rows][4+FW+SW] f64 = [position, status, n_iter, pval, fit[FW], stats[SW]] (the record of
+ * xpb200_pack_records), ascending by position.  This is what `execute()` (scripts/diffmod.py:15-77) hands to
+ * the table writer.  `rows` holds `capacity_rows` rows (XPB200_ENOMEM and *n_rows = rows needed if more);
+ * copies the batch up in chunks like xpb200_fit_host, synchronises. */
+int32_t xpb200_fit_host_rows(int32_t device, const xpb200_batch* batch, const xpb200_method* method, double* rows,
+                             int64_t capacity_rows, int64_t* n_rows, uint32_t* n_fitted);
+
 /* Release the cached device buffers of xpb200_fit_host (all devices). */
 void xpb200_release(void);
 

@@ -385,3 +385,30 @@ def test_edge_case_positions_vs_oracle(torch_cuda):
             np.testing.assert_allclose(res.alpha[p], f["alpha"], rtol=1e-5, err_msg=str(p))
             np.testing.assert_allclose(res.beta[p], f["beta"], rtol=1e-5, err_msg=str(p))
             np.testing.assert_allclose(res.N[p][present], f["N"], rtol=1e-5, atol=1e-9, err_msg=str(p))
+
+
+def test_fit_host_rows_equals_dense_records(torch_cuda):
+    """xpb200_fit_host_rows returns exactly the records of the table's rows (fitted + row filter) that the
+    dense xpb200_fit_host arrays hold, ascending by position; too small a buffer is an error, not a truncation."""
+    from xpore_b200.dist import unpack_records
+    spec = Spec({"KO": 3, "WT": 3}, reads_lo=20, reads_hi=100, f_mod=0.3, seed=19,
+                method={"prefiltering": {"method": "t-test", "threshold": 0.1}})
+    batch = make_batch(spec, KmerModel.load(), n_positions=150000)  # several chunks of the host pipeline
+    batch.encode_reads()
+    method = xf.Method.from_dict(spec.method)
+    dense = xf.fit_batch(batch, method)
+    rows, n_fitted = xf.fit_rows(batch, method)
+    assert n_fitted == dense.n_fitted
+    keep = np.nonzero(dense.keep_row)[0]
+    assert 100 < len(keep) < dense.n_fitted
+    idx, status, n_iter, pval, fit, stats = unpack_records(rows, xf.fit_width(6), xf.stats_width(6, 2))
+    np.testing.assert_array_equal(idx, keep)
+    np.testing.assert_array_equal(status, dense.status[keep])
+    np.testing.assert_array_equal(n_iter, dense.n_iter[keep])
+    np.testing.assert_array_equal(pval, dense.pval[keep])
+    np.testing.assert_array_equal(fit, dense.fit[keep])
+    np.testing.assert_array_equal(stats, dense.stats[keep])
+    with pytest.raises(RuntimeError, match="rows buffer too small"):
+        xf.fit_rows(batch, method, capacity_rows=len(keep) - 1)
+    rows2, _ = xf.fit_rows(batch, method, capacity_rows=len(keep))
+    np.testing.assert_array_equal(rows2, rows)

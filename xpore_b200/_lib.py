@@ -42,7 +42,7 @@ class XpLaunchInfo(C.Structure):
 
 
 EXPORTS = ["xpb200_fit_width", "xpb200_stats_width", "xpb200_workspace_bytes", "xpb200_fit_device",
-           "xpb200_fit_host", "xpb200_release", "xpb200_prefilter_device", "xpb200_stats_device",
+           "xpb200_fit_host", "xpb200_fit_host_rows", "xpb200_release", "xpb200_prefilter_device", "xpb200_stats_device",
            "xpb200_fit_launch_info", "xpb200_launch_count", "xpb200_measure_fp64_peak", "xpb200_eval_special",
            "xpb200_set_stage_timing", "xpb200_get_stage_ms", "xpb200_pack_records",
            "xpb200_debug_fill_smem", "xpb200_last_error", "xpb200_version",
@@ -95,6 +95,9 @@ def lib():
         L.xpb200_fit_host.restype = C.c_int32
         L.xpb200_fit_host.argtypes = [C.c_int32, C.POINTER(XpBatch), C.POINTER(XpMethod), C.POINTER(XpResult),
                                       C.POINTER(C.c_uint32)]
+        L.xpb200_fit_host_rows.restype = C.c_int32
+        L.xpb200_fit_host_rows.argtypes = [C.c_int32, C.POINTER(XpBatch), C.POINTER(XpMethod), C.c_void_p, C.c_int64,
+                                           C.POINTER(C.c_int64), C.POINTER(C.c_uint32)]
         if hasattr(L, "xpb200_debug_fill_smem"):  # absent only in experiment builds (XPB200_LIB)
             L.xpb200_debug_fill_smem.restype = C.c_int32
             L.xpb200_debug_fill_smem.argtypes = [C.c_uint64, C.c_void_p]

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -306,6 +307,7 @@ constexpr int kMaxChunks = 64;
 constexpr size_t kChunkBytes = 112u << 20;
 
 constexpr int kComputeStreams = 3;
+constexpr int kPackWarps = 2048;  // warps of the row-compaction launches of one chunk
 
 struct DevCache {
     int device = -1;
@@ -320,11 +322,31 @@ std::vector<DevCache*> g_cache;
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 }  // namespace
 
+namespace {
+// r != null: dense result arrays come back (xpb200_fit_host).  rows != null: only the records of the table's
+// rows come back, compacted (xpb200_fit_host_rows).
+int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m, const xpb200_result* r,
+                  double* rows, int64_t rows_capacity, int64_t* n_rows, uint32_t* n_fitted);
+}  // namespace
+
 int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_method* m, const xpb200_result* r,
                         uint32_t* n_fitted) {
     if (int rc = check_batch(b, m)) return rc;
     if (!r || !r->status || !r->n_iter || !r->pval || !r->fit || !r->stats)
         return fail(XPB200_EINVAL, "null result array");
+    return fit_host_impl(device, b, m, r, nullptr, 0, nullptr, n_fitted);
+}
+
+int32_t xpb200_fit_host_rows(int32_t device, const xpb200_batch* b, const xpb200_method* m, double* rows,
+                             int64_t capacity_rows, int64_t* n_rows, uint32_t* n_fitted) {
+    if (int rc = check_batch(b, m)) return rc;
+    if (!rows || capacity_rows < 0 || !n_rows) return fail(XPB200_EINVAL, "null rows / n_rows");
+    return fit_host_impl(device, b, m, nullptr, rows, capacity_rows, n_rows, n_fitted);
+}
+
+namespace {
+int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m, const xpb200_result* r,
+                  double* rows, int64_t rows_capacity, int64_t* n_rows, uint32_t* n_fitted) {
     CK(cudaSetDevice(device));
     std::lock_guard<std::mutex> lk(g_cache_mu);
     DevCache* dc = nullptr;
@@ -344,6 +366,7 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
     }
     const int P = b->n_positions, G = b->n_groups, C = b->n_conditions;
     if (n_fitted) *n_fitted = 0;
+    if (n_rows) *n_rows = 0;
     if (P == 0) return 0;
     const size_t eb = b->y_format == XPB200_Y_F64 ? 8 : (b->y_format == XPB200_Y_I32 ? 4 : 2);
     const int FW = xpc::fit_width(G), SW = xpc::stats_width(G, C);
@@ -395,6 +418,10 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
     const size_t o_fit = o; o += align_up((size_t)P * FW * 8);
     const size_t o_stats = o; o += align_up((size_t)P * SW * 8);
     const size_t o_nf = o; o += align_up((size_t)kMaxChunks * 4);
+    const size_t o_nr = o; o += align_up((size_t)kMaxChunks * 4);
+    const size_t o_cnt = o; o += rows ? align_up((size_t)kMaxChunks * kPackWarps * 4) : 0;
+    const int RW = 4 + FW + SW;  // record width
+    const size_t o_rows = o; o += rows ? align_up((size_t)P * RW * 8) : 0;  // chunk c's rows start at row cut[c]
     std::vector<size_t> o_ws(nchunks);
     for (int c = 0; c < nchunks; ++c) {
         o_ws[c] = o;
@@ -423,9 +450,13 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
     double* d_fit = (double*)(d + o_fit);
     double* d_stats = (double*)(d + o_stats);
     uint32_t* d_nf = (uint32_t*)(d + o_nf);
+    uint32_t* d_nr = (uint32_t*)(d + o_nr);
+    uint32_t* d_cnt = (uint32_t*)(d + o_cnt);
+    double* d_rows = (double*)(d + o_rows);
 
     CK(cudaMemcpyAsync(d + o_gc, b->grp_cond, (size_t)G * 4, cudaMemcpyDefault, dc->s_in));
     CK(cudaMemsetAsync(d_nf, 0, (size_t)kMaxChunks * 4, dc->s_in));
+    CK(cudaMemsetAsync(d_nr, 0, (size_t)kMaxChunks * 4, dc->s_in));
     for (int c = 0; c < nchunks; ++c) {
         const int p0 = cut[c], p1 = cut[c + 1], pc = p1 - p0;
         if (pc == 0) continue;
@@ -454,7 +485,23 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
         CK(cudaMemsetAsync(dr.stats, 0xFF, (size_t)pc * SW * 8, sc));
         if (int rc = xpb200_fit_device(&db, m, &dr, d + o_ws[c], xpb200_workspace_bytes(pc), d_nf + c, sc))
             return rc;
+        if (rows) {  // compact the table's rows of this chunk
+            xpk::PackRowsArgs pa;
+            pa.status = dr.status; pa.n_iter = dr.n_iter; pa.pval = dr.pval; pa.fit = dr.fit; pa.stats = dr.stats;
+            pa.P = pc; pa.FW = FW; pa.SW = SW; pa.need = xpc::STATUS_SELECTED | xpc::STATUS_KEEP_ROW;
+            pa.index_offset = p0; pa.capacity = pc; pa.n_rows = d_nr + c; pa.out = d_rows + (size_t)p0 * RW;
+            const int threads = 256, wpb = threads / 32;
+            pa.n_warps = std::max(1, std::min(kPackWarps, (pc + 255) / 256));
+            pa.span = ((pc + pa.n_warps - 1) / pa.n_warps + 31) & ~31;
+            pa.counts = d_cnt + (size_t)c * kPackWarps;
+            const int blocks = (pa.n_warps + wpb - 1) / wpb;
+            xpk::xp_count_rows_kernel<<<blocks, threads, 0, sc>>>(pa);
+            xpk::xp_pack_rows_kernel<<<blocks, threads, 0, sc>>>(pa);
+            g_launches += 2;
+            CK(cudaGetLastError());
+        }
         CK(cudaEventRecord(dc->e_done[c], sc));
+        if (rows) continue;  // the rows are fetched below, once their counts are known
         // copy-out
         CK(cudaStreamWaitEvent(dc->s_out, dc->e_done[c], 0));
         CK(cudaMemcpyAsync(r->status + p0, dr.status, (size_t)pc * 4, cudaMemcpyDefault, dc->s_out));
@@ -462,6 +509,35 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
         CK(cudaMemcpyAsync(r->pval + p0, dr.pval, (size_t)pc * 8, cudaMemcpyDefault, dc->s_out));
         CK(cudaMemcpyAsync(r->fit + (size_t)p0 * FW, dr.fit, (size_t)pc * FW * 8, cudaMemcpyDefault, dc->s_out));
         CK(cudaMemcpyAsync(r->stats + (size_t)p0 * SW, dr.stats, (size_t)pc * SW * 8, cudaMemcpyDefault, dc->s_out));
+    }
+    if (rows) {
+        // every chunk is enqueued; fetch each chunk's rows as soon as it is done (count first, then the rows)
+        int64_t total_rows = 0;
+        bool overflow = false;
+        for (int c = 0; c < nchunks; ++c) {
+            const int p0 = cut[c], pc = cut[c + 1] - cut[c];
+            if (pc == 0) continue;
+            uint32_t cnt = 0;
+            CK(cudaStreamWaitEvent(dc->s_out, dc->e_done[c], 0));
+            CK(cudaMemcpyAsync(&cnt, d_nr + c, 4, cudaMemcpyDefault, dc->s_out));
+            CK(cudaStreamSynchronize(dc->s_out));
+            if (total_rows + cnt > rows_capacity) {
+                overflow = true;
+                total_rows += cnt;
+                continue;
+            }
+            if (cnt)
+                CK(cudaMemcpyAsync(rows + (size_t)total_rows * RW, d_rows + (size_t)p0 * RW, (size_t)cnt * RW * 8,
+                                   cudaMemcpyDefault, dc->s_out));
+            total_rows += cnt;
+        }
+        CK(cudaStreamSynchronize(dc->s_out));
+        *n_rows = total_rows;
+        if (overflow) {
+            for (int i = 0; i < kComputeStreams; ++i) CK(cudaStreamSynchronize(dc->s_c[i]));
+            CK(cudaStreamSynchronize(dc->s_in));
+            return fail(XPB200_ENOMEM, "rows buffer too small: " + std::to_string(total_rows) + " rows needed");
+        }
     }
     uint32_t nf[kMaxChunks];
     CK(cudaMemcpyAsync(nf, d_nf, sizeof(nf), cudaMemcpyDefault, dc->s_out));
@@ -473,6 +549,7 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
     if (n_fitted) *n_fitted = total;
     return 0;
 }
+}  // namespace
 
 void xpb200_release(void) {
     std::lock_guard<std::mutex> lk(g_cache_mu);

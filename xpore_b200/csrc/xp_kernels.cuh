@@ -481,6 +481,69 @@ __global__ void xp_pack_records_kernel(PackArgs a) {
     }
 }
 
+// Rows of diffmod.table only: records (same layout) of the positions [0, P) whose status carries every bit of
+// `need` (SELECTED | KEEP_ROW: fitted and past the row filter of io.py:363-367), compacted in position
+// order.  Two small launches: every warp owns a contiguous span of positions and counts its rows
+// (xp_count_rows_kernel); then it adds up the counts of the warps before it and writes its rows in order
+// (xp_pack_rows_kernel).  Deterministic, no atomics; the last warp leaves the total in n_rows.
+struct PackRowsArgs {
+    const uint32_t* status;
+    const int32_t* n_iter;
+    const double* pval;
+    const double* fit;
+    const double* stats;
+    int P, FW, SW;
+    int span;              // positions per warp, a multiple of 32
+    int n_warps;           // warps of the launch (gridDim.x * blockDim.x / 32)
+    uint32_t need;
+    long long index_offset, capacity;
+    unsigned int* counts;  // [n_warps]
+    unsigned int* n_rows;
+    double* out;
+};
+
+__global__ void xp_count_rows_kernel(PackRowsArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= a.n_warps) return;
+    const int lo = w * a.span, hi = min(a.P, lo + a.span);
+    unsigned c = 0;
+    for (int p = lo + lane; p < hi; p += 32) c += ((a.status[p] & a.need) == a.need) ? 1u : 0u;
+    c = __reduce_add_sync(kFull, c);
+    if (lane == 0) a.counts[w] = c;
+}
+
+__global__ void xp_pack_rows_kernel(PackRowsArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= a.n_warps) return;
+    const int W = 4 + a.FW + a.SW;
+    unsigned before = 0;
+    for (int j = lane; j < w; j += 32) before += a.counts[j];
+    long long row = __reduce_add_sync(kFull, before);
+    if (w == a.n_warps - 1 && lane == 0) *a.n_rows = (unsigned)row + a.counts[w];
+    const int lo = w * a.span, hi = min(a.P, lo + a.span);
+    for (int p0 = lo; p0 < hi; p0 += 32) {
+        const int p = p0 + lane;
+        const bool keep = p < hi && (a.status[p] & a.need) == a.need;
+        for (unsigned rest = __ballot_sync(kFull, keep); rest; rest &= rest - 1, ++row) {
+            if (row >= a.capacity) return;
+            const int q = p0 + __ffs(rest) - 1;
+            double* o = a.out + (size_t)row * W;
+            if (lane == 0) {
+                o[0] = (double)(a.index_offset + q);
+                o[1] = (double)a.status[q];
+                o[2] = (double)a.n_iter[q];
+                o[3] = a.pval[q];
+            }
+            const double* f = a.fit + (size_t)q * a.FW;
+            const double* t = a.stats + (size_t)q * a.SW;
+            for (int c = lane; c < a.FW; c += 32) o[4 + c] = f[c];
+            for (int c = lane; c < a.SW; c += 32) o[4 + a.FW + c] = t[c];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // FP64 peak: 8 independent DFMA chains per thread, no memory traffic.
 // ------------------------------------------------------------------------------------------

@@ -152,6 +152,30 @@ def fit_batch(batch: Batch, method: Method, device: int = 0) -> FitResult:
     return res
 
 
+def fit_rows(batch: Batch, method: Method, device: int = 0, capacity_rows: int | None = None):
+    """Rows of ``diffmod.table`` only (``xpb200_fit_host_rows``): ``(records, n_fitted)`` with ``records`` the
+    ``[n_rows, 4+FW+SW]`` matrix ``[position, status, n_iter, pval, fit, stats]`` of the positions that were
+    fitted and pass the reference's row filter, ascending by position (``dist.unpack_records`` splits it)."""
+    L = _lib.lib()
+    P, G, Cn = batch.n_positions, batch.layout.n_groups, batch.layout.n_conditions
+    y, yfmt, yscale = _y_buffer(batch)
+    read_off = np.ascontiguousarray(batch.read_off, dtype=np.int64)
+    grp_len = np.ascontiguousarray(batch.grp_len, dtype=np.int32)
+    km = np.ascontiguousarray(batch.kmer_mean, dtype=np.float64)
+    ks = np.ascontiguousarray(batch.kmer_std, dtype=np.float64)
+    gc = np.ascontiguousarray(batch.layout.grp_cond, dtype=np.int32)
+    W = 4 + fit_width(G) + stats_width(G, Cn)
+    cap = P if capacity_rows is None else int(capacity_rows)
+    rows = np.empty((max(cap, 1), W), dtype=np.float64)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    b = _lib.XpBatch(P, G, Cn, _max_reads(batch), batch.n_reads, ptr(y), ptr(read_off), ptr(grp_len), ptr(km),
+                     ptr(ks), ptr(gc), yfmt, 0, yscale)
+    m = method.c_struct()
+    nr, nf = C.c_int64(0), C.c_uint32(0)
+    _lib.check(L.xpb200_fit_host_rows(int(device), C.byref(b), C.byref(m), ptr(rows), cap, C.byref(nr), C.byref(nf)))
+    return rows[:int(nr.value)], int(nf.value)
+
+
 class DeviceBatch:
     """A batch resident in HBM (torch tensors own the memory)."""
 
