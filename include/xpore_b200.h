@@ -93,6 +93,9 @@ typedef struct xpb200_result {
     double* stats;     /* [P, xpb200_stats_width(G,C)] mu_unmod mu_mod s2_unmod s2_mod conf_unmod conf_mod
                           p_overlap cdf[4] mod_rate[G] coverage[G] pairwise[C(C,2)][diff,pval,z]
                           one_vs_all[C][diff,pval,z] (only when C > 2) */
+    double* coef;      /* optional (may be NULL), device paths only: [P, G+2] coefficients of the LAST E-step of
+                          every fitted position, d_n = A_g + y'(B + C y') with y' = y - kmer_mean, stored as
+                          A_0..A_{G-1}, B, C - what xpb200_posterior_device needs to restate the z node */
 } xpb200_result;
 
 int32_t xpb200_fit_width(int32_t n_groups);
@@ -131,6 +134,13 @@ int32_t xpb200_prefilter_device(const xpb200_batch* batch, const xpb200_method* 
                                 double* pval, void* cuda_stream);
 int32_t xpb200_stats_device(const xpb200_batch* batch, const xpb200_method* method, const xpb200_result* result,
                             const int32_t* worklist, const uint32_t* n_work_dev, void* cuda_stream);
+
+/* `--save_models` support (io.save_models_to_hdf5, io.py:99-139): the z node of every fitted position, i.e. the
+ * responsibilities of its last E-step (gmm.py:236-243), recomputed from result->coef (which the fit must have
+ * been given).  prob0[R] = q(z_n = 0) (q(z_n = 1) = 1 - prob0, gmm.py:242); ln_prob[R, 2] = ln q(z_n = k)
+ * (gmm.py:243, not clipped).  Reads of positions that were not fitted are left untouched.  Device pointers. */
+int32_t xpb200_posterior_device(const xpb200_batch* batch, const xpb200_result* result, double* prob0,
+                                double* ln_prob, void* cuda_stream);
 
 /* Compact records of the fitted positions of the last xpb200_fit_device call that used `workspace`
  * (worklist order): row = [index_offset + position, status, n_iter, pval, fit[FW], stats[SW]] as

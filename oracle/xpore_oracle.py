@@ -247,6 +247,10 @@ def fit_position(y, X, kmer_mean, kmer_std, max_iters=500, stopping_criteria=1e-
            "elbo_last": elbo_old}
     if trace:
         out["elbos"] = elbos
+        # the z and y nodes as io.save_models_to_hdf5 (io.py:125-137) would write them: responsibilities of the
+        # last E-step (gmm.py:241-243) and the sufficient statistics taken from them (gmm.py:179-189)
+        out["z_prob"], out["z_ln_prob"] = prob, ln_prob
+        out["y_mean"], out["y_variance"] = mean, var
     return out
 
 

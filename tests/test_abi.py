@@ -44,7 +44,7 @@ def test_struct_layouts_match_header():
     # field order/sizes of the ctypes mirrors (x86-64 / LP64)
     assert C.sizeof(_lib.XpBatch) == 4 * 4 + 8 + 6 * 8 + 2 * 4 + 8
     assert C.sizeof(_lib.XpMethod) == 2 * 4 + 3 * 8
-    assert C.sizeof(_lib.XpResult) == 5 * 8
+    assert C.sizeof(_lib.XpResult) == 6 * 8  # status n_iter pval fit stats coef
     assert C.sizeof(_lib.XpLaunchInfo) == 6 * 4
 
 

@@ -73,3 +73,32 @@ def test_oracle_matches_reference(golden_case):
             else:
                 b = fnum(b)
                 assert (np.isnan(a) and np.isnan(b)) or a == pytest.approx(b, rel=1e-12, abs=1e-300)
+
+
+@pytest.mark.parametrize("name", ["g1_runs", "g3_pooled"])
+def test_oracle_model_nodes(name):
+    """The node values `--save_models` dumps (io.py:99-139): responsibilities of the last E-step and the y-node
+    statistics, oracle against the live reference (tests/golden/make_golden_models.py)."""
+    import json
+    import os
+
+    from conftest import GOLDEN
+    models = json.load(open(os.path.join(GOLDEN, name, "models.json")))
+    assert len(models) >= 4
+    for m in models:
+        y = np.asarray(m["y_data"])
+        g = np.asarray(m["x_group_of_read"])
+        X = np.zeros((len(y), len(m["x_group_names"])), dtype=bool)
+        X[np.arange(len(y)), g] = True
+        from xpore_b200.kmer_model import KmerModel
+        km = KmerModel.load()
+        row = km.kmers.index(m["kmer"]) if isinstance(km.kmers, list) else list(km.kmers).index(m["kmer"])
+        f = orc.fit_position(y, X, float(km.mean[row]), float(km.stdv[row]), rng=np.random.RandomState(0), trace=True)
+        np.testing.assert_allclose(f["z_prob"], np.asarray(m["z_prob"]), rtol=1e-9, atol=1e-300)
+        np.testing.assert_allclose(f["z_ln_prob"], np.asarray(m["z_ln_prob"]), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(f["y_mean"], m["y_mean"], rtol=1e-12)
+        np.testing.assert_allclose(f["y_variance"], m["y_variance"], rtol=1e-10)
+        np.testing.assert_allclose(f["N"], np.asarray(m["y_N"]), rtol=1e-10, atol=1e-300)
+        np.testing.assert_allclose(f["conc"], np.asarray(m["w_concentration"]), rtol=1e-10)
+        for k in ("location", "lambda", "alpha", "beta"):
+            np.testing.assert_allclose(f[k], m["mu_tau"][k], rtol=1e-10)

@@ -33,7 +33,7 @@ class XpMethod(C.Structure):
 
 class XpResult(C.Structure):
     _fields_ = [("status", C.c_void_p), ("n_iter", C.c_void_p), ("pval", C.c_void_p), ("fit", C.c_void_p),
-                ("stats", C.c_void_p)]
+                ("stats", C.c_void_p), ("coef", C.c_void_p)]
 
 
 class XpLaunchInfo(C.Structure):
@@ -43,7 +43,7 @@ class XpLaunchInfo(C.Structure):
 
 EXPORTS = ["xpb200_fit_width", "xpb200_stats_width", "xpb200_workspace_bytes", "xpb200_fit_device",
            "xpb200_fit_host", "xpb200_fit_host_rows", "xpb200_release", "xpb200_prefilter_device", "xpb200_stats_device",
-           "xpb200_fit_launch_info", "xpb200_launch_count", "xpb200_measure_fp64_peak", "xpb200_eval_special",
+           "xpb200_posterior_device", "xpb200_fit_launch_info", "xpb200_launch_count", "xpb200_measure_fp64_peak", "xpb200_eval_special",
            "xpb200_set_stage_timing", "xpb200_get_stage_ms", "xpb200_pack_records",
            "xpb200_debug_fill_smem", "xpb200_last_error", "xpb200_version",
            "xpb200_ingest_open", "xpb200_ingest_genes", "xpb200_ingest_copy", "xpb200_ingest_close",
@@ -119,6 +119,9 @@ def lib():
         L.xpb200_stats_device.restype = C.c_int32
         L.xpb200_stats_device.argtypes = [C.POINTER(XpBatch), C.POINTER(XpMethod), C.POINTER(XpResult), C.c_void_p,
                                           C.c_void_p, C.c_void_p]
+        L.xpb200_posterior_device.restype = C.c_int32
+        L.xpb200_posterior_device.argtypes = [C.POINTER(XpBatch), C.POINTER(XpResult), C.c_void_p, C.c_void_p,
+                                              C.c_void_p]
         L.xpb200_fit_launch_info.restype = C.c_int32
         L.xpb200_fit_launch_info.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(XpLaunchInfo)]
         L.xpb200_launch_count.restype = C.c_uint64

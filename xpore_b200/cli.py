@@ -19,7 +19,8 @@ def parse_options(argv):
     p.add_argument("--n_processes", dest="n_processes", type=int, default=1,
                    help="number of host processes that parse data.json and select positions (the fit runs on the GPU).")
     p.add_argument("--save_models", dest="save_models", default=False, action="store_true",
-                   help="accepted for compatibility; per-position model dumps are not written (needs h5py).")
+                   help="with this argument, the program will save the model parameters for each id "
+                        "(<out>/models/<id>.npz, and <id>.hdf5 in the reference's layout when h5py is installed).")
     p.add_argument("--resume", dest="resume", default=False, action="store_true",
                    help="with this argument, the program will resume from the previous run.")
     p.add_argument("--ids", dest="ids", default=[], nargs="*", help="gene or transcript ids to model.")
@@ -43,8 +44,6 @@ def main(argv=None):
     options = parse_options(argv)
     if options.cmd == "diffmod":
         from .diffmod import diffmod
-        if options.save_models:
-            print("warning: --save_models is accepted but not implemented in xpore_b200", file=sys.stderr)
         diffmod(options)
     elif options.cmd == "postprocessing":
         from .postprocessing import postprocessing

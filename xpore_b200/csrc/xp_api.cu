@@ -277,7 +277,7 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
     fa.G = b->n_groups; fa.max_iters = m->max_iters; fa.stopping = m->stopping_criteria;
     fa.conc0 = m->dirichlet_conc;
     fa.lg_prior_w = xpm::xlgamma(2.0 * m->dirichlet_conc) - 2.0 * xpm::xlgamma(m->dirichlet_conc);
-    fa.fit = r->fit; fa.n_iter = r->n_iter; fa.status = r->status;
+    fa.fit = r->fit; fa.n_iter = r->n_iter; fa.status = r->status; fa.coef = r->coef;
     if (two_class) {
         Geometry gl;
         if (int rc = fit_geometry(b->n_groups, b->max_reads, 4, &gl)) return rc;
@@ -480,6 +480,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         xpb200_result dr;
         dr.status = d_status + p0; dr.n_iter = d_niter + p0; dr.pval = d_pval + p0;
         dr.fit = d_fit + (size_t)p0 * FW; dr.stats = d_stats + (size_t)p0 * SW;
+        dr.coef = nullptr;
         CK(cudaMemsetAsync(dr.n_iter, 0, (size_t)pc * 4, sc));
         CK(cudaMemsetAsync(dr.fit, 0xFF, (size_t)pc * FW * 8, sc));
         CK(cudaMemsetAsync(dr.stats, 0xFF, (size_t)pc * SW * 8, sc));
@@ -597,6 +598,23 @@ int32_t xpb200_measure_fp64_peak(int32_t device, int32_t repeats, double* tflops
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(out);
+    return 0;
+}
+
+int32_t xpb200_posterior_device(const xpb200_batch* b, const xpb200_result* r, double* prob0, double* ln_prob,
+                                void* stream) {
+    if (!b || !r || !r->status || !r->n_iter || !r->coef || !prob0 || !ln_prob)
+        return fail(XPB200_EINVAL, "null argument (the fit must have been given result->coef)");
+    if (b->n_positions <= 0) return 0;
+    xpk::PosteriorArgs a;
+    a.y = b->y; a.y_format = b->y_format; a.y_scale = b->y_scale; a.read_off = b->read_off; a.grp_len = b->grp_len;
+    a.kmer_mean = b->kmer_mean; a.status = r->status; a.n_iter = r->n_iter; a.coef = r->coef;
+    a.P = b->n_positions; a.G = b->n_groups; a.prob0 = prob0; a.ln_prob = ln_prob;
+    const int threads = 256, wpb = threads / 32;
+    const int blocks = std::max(1, std::min((b->n_positions + wpb - 1) / wpb, 148 * 8));
+    xpk::xp_posterior_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(a);
+    ++g_launches;
+    CK(cudaGetLastError());
     return 0;
 }
 

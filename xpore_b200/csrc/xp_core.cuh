@@ -92,6 +92,23 @@ XP_HD void estep_read(const Tab& tab, double d, double& inv, double& rmin, doubl
     h = fma(rmin, ax, l1p);  // |d| > 500 only when rmin < 1e-217: the clip does not show
 }
 
+// The z node as the reference stores it (gmm.py:241-243): prob0 = q(z=0) and ln q(z=k).  ln q of the likelier
+// component is -log1p(exp(-|d|)), of the other one -|d| - log1p(exp(-|d|)); |d| is NOT clipped there
+// (gmm.py:243 takes ln_rho - logsumexp), only inside the sigmoid (gmm.py:240-241).
+template <class Tab>
+XP_HD void posterior_read(const Tab& tab, double d, double& prob0, double& lnp0, double& lnp1) {
+    double inv, rmin, h;
+    bool pos;
+    estep_read(tab, d, inv, rmin, h, pos);
+    const double ad = fabs(d);
+    const double adc = ad < 500.0 ? ad : 500.0;
+    const double l1p = h - rmin * adc;  // h = rmin |d|_clipped + log1p(t)
+    prob0 = pos ? rmin : inv;
+    const double ln_big = -l1p, ln_small = -ad - l1p;
+    lnp0 = pos ? ln_small : ln_big;
+    lnp1 = pos ? ln_big : ln_small;
+}
+
 // ---- psi / lgamma of one posterior parameter inside the sweeps (xp_math.cuh: shift10, xlog_tab) -------
 // Returns psi(x), lgamma(x) + ln den and den, where den is the shift product (1 for x >= 10): the caller
 // multiplies the den of all its parameters and subtracts one logarithm of the product from the ELBO.

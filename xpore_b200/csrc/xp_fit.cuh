@@ -69,6 +69,7 @@ struct FitArgs {
     double* fit;
     int32_t* n_iter;
     uint32_t* status;
+    double* coef;  // optional [P, G+2]: A_g, B, C of the last E-step (for xp_posterior_kernel)
 };
 
 constexpr int kTabExpDoubles = 256;
@@ -501,6 +502,12 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
                 // ---- scalar phase: special functions spread over lanes, one uniform code path ----
                 // slots: [0,2G) c_gk -> psi, lgamma;  2G+k alpha_k -> psi, lgamma;
                 //        2G+2+k -> ln beta_k;  2G+4+k -> ln lambda_k       (slot parity = component)
+                if (a.coef != nullptr && it >= 1) {  // --save_models: keep the coefficients of the E-step just done
+                    double* cf = a.coef + (size_t)p * (G + 2);
+                    for (int g = lane; g < G; g += 32) cf[g] = Asm[g];
+                    if (lane < 2) cf[G + lane] = bc[lane];
+                    __syncwarp();
+                }
                 double e_loc = 0.0;
                 for (int s0 = 0; s0 < 2 * G + 6; s0 += 32) {
                     const int s = s0 + lane;

@@ -545,6 +545,50 @@ __global__ void xp_pack_rows_kernel(PackRowsArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// z node for --save_models (io.py:99-139): responsibilities of the last E-step, one warp per position.
+// ------------------------------------------------------------------------------------------
+struct PosteriorArgs {
+    const void* y;
+    int y_format;
+    double y_scale;
+    const int64_t* read_off;
+    const int32_t* grp_len;
+    const double* kmer_mean;
+    const uint32_t* status;
+    const int32_t* n_iter;
+    const double* coef;  // [P, G+2]
+    int P, G;
+    double* prob0;    // [R]
+    double* ln_prob;  // [R, 2]
+};
+
+__global__ void xp_posterior_kernel(PosteriorArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const double rscale = 1.0 / a.y_scale;
+    for (int p = blockIdx.x * wpb + (threadIdx.x >> 5); p < a.P; p += gridDim.x * wpb) {
+        if (!(a.status[p] & STATUS_SELECTED) || a.n_iter[p] < 1) continue;
+        const int64_t off = a.read_off[p];
+        const int n = (int)(a.read_off[p + 1] - off);
+        const double m0 = a.kmer_mean[p];
+        const double* cf = a.coef + (size_t)p * (a.G + 2);
+        const double B = cf[a.G], C = cf[a.G + 1];
+        const int32_t* glen = a.grp_len + (size_t)p * a.G;
+        for (int i = lane; i < n; i += 32) {
+            int g = 0, gend = glen[0];
+            while (i >= gend) gend += glen[++g];
+            const double yc = y_load_global(a.y, a.y_format, a.y_scale, rscale, off + i) - m0;
+            const double d = fma(yc, fma(C, yc, B), cf[g]);
+            double p0, l0, l1;
+            posterior_read(HostTab(), d, p0, l0, l1);
+            a.prob0[off + i] = p0;
+            a.ln_prob[2 * (off + i)] = l0;
+            a.ln_prob[2 * (off + i) + 1] = l1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // FP64 peak: 8 independent DFMA chains per thread, no memory traffic.
 // ------------------------------------------------------------------------------------------
 __global__ void xp_dfma_peak_kernel(double* out, int iters, double seed) {

@@ -74,9 +74,20 @@ def diffmod(args, fit_fn=None):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    save_models = bool(getattr(args, "save_models", False))
+    models_fn = None  # (batch, method) -> (FitResult, prob0, ln_prob): the fit plus the z node of every position
     if fit_fn is None:
         from .fit import fit_batch
         fit_fn = lambda b, m: fit_batch(b, m, device=local_rank)  # noqa: E731
+        if save_models:
+            def models_fn(b, m):
+                from .fit import DeviceBatch, DeviceResult, fit_device, posterior_device
+                db = DeviceBatch(b, device="cuda:%d" % local_rank)
+                out = fit_device(db, m, DeviceResult(db.P, db.G, db.C, db.device, with_coef=True))
+                prob0, ln_prob = posterior_device(db, out)
+                return out.to_host(), prob0.cpu().numpy(), ln_prob.cpu().numpy()
+    elif save_models:
+        models_fn = getattr(fit_fn, "with_models", None)
     dist = None
     if world > 1:
         import torch
@@ -149,7 +160,12 @@ def diffmod(args, fit_fn=None):
         else:
             batch = reader.read(chunk, f_index, n_threads=n_proc)
             batch.encode_reads()  # u16 / i32 when every read is a 2-decimal literal: 4x less PCIe traffic
-        res = fit_fn(batch, m) if batch.n_positions else None
+        if save_models and models_fn is not None and batch.n_positions:
+            from .models import save_models as write_models
+            res, prob0, ln_prob = models_fn(batch, m)
+            write_models(paths["models"], batch, res, prob0, ln_prob, m.dirichlet_conc)  # diffmod.py:61-63
+        else:
+            res = fit_fn(batch, m) if batch.n_positions else None
         rows = result_rows(batch, res, pm) if res is not None else []
         by_gene = OrderedDict((idx, []) for idx in chunk)
         for r in rows:

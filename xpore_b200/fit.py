@@ -218,7 +218,7 @@ class DeviceBatch:
 
 
 class DeviceResult:
-    def __init__(self, P: int, G: int, Cn: int, device):
+    def __init__(self, P: int, G: int, Cn: int, device, with_coef: bool = False):
         import torch
         self.torch = torch
         self.P, self.G, self.C = P, G, Cn
@@ -227,12 +227,15 @@ class DeviceResult:
         self.pval = torch.full((P,), math.nan, dtype=torch.float64, device=device)
         self.fit = torch.full((P, fit_width(G)), math.nan, dtype=torch.float64, device=device)
         self.stats = torch.full((P, stats_width(G, Cn)), math.nan, dtype=torch.float64, device=device)
+        # coefficients of the last E-step, only kept for --save_models (xpb200_posterior_device)
+        self.coef = torch.full((P, G + 2), math.nan, dtype=torch.float64, device=device) if with_coef else None
         self.n_fitted = torch.zeros(1, dtype=torch.int32, device=device)
         self.workspace = torch.empty(int(_lib.lib().xpb200_workspace_bytes(P)), dtype=torch.uint8, device=device)
 
     def c_struct(self) -> _lib.XpResult:
         return _lib.XpResult(self.status.data_ptr(), self.n_iter.data_ptr(), self.pval.data_ptr(),
-                             self.fit.data_ptr(), self.stats.data_ptr())
+                             self.fit.data_ptr(), self.stats.data_ptr(),
+                             self.coef.data_ptr() if self.coef is not None else None)
 
     def to_host(self) -> FitResult:
         return FitResult(self.G, self.C, self.status.cpu().numpy().view(np.uint32), self.n_iter.cpu().numpy(),
@@ -252,6 +255,23 @@ def fit_device(dbatch: DeviceBatch, method: Method, out: DeviceResult | None = N
         _lib.check(L.xpb200_fit_device(C.byref(b), C.byref(m), C.byref(r), out.workspace.data_ptr(),
                                        out.workspace.numel(), out.n_fitted.data_ptr(), C.c_void_p(stream)))
     return out
+
+
+def posterior_device(dbatch: DeviceBatch, out: DeviceResult):
+    """The z node of every fitted position (``xpb200_posterior_device``): ``(prob0[R], ln_prob[R, 2])`` device
+    tensors, NaN for reads of positions that were not fitted.  ``out`` must come from a fit with
+    ``DeviceResult(..., with_coef=True)``."""
+    torch = dbatch.torch
+    assert out.coef is not None, "fit with DeviceResult(with_coef=True) first"
+    R = int(dbatch.R)
+    prob0 = torch.full((max(R, 1),), math.nan, dtype=torch.float64, device=dbatch.device)
+    ln_prob = torch.full((max(R, 1), 2), math.nan, dtype=torch.float64, device=dbatch.device)
+    b, r = dbatch.c_struct(), out.c_struct()
+    with torch.cuda.device(dbatch.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().xpb200_posterior_device(C.byref(b), C.byref(r), prob0.data_ptr(), ln_prob.data_ptr(),
+                                                      C.c_void_p(stream)))
+    return prob0[:R], ln_prob[:R]
 
 
 def pack_records_device(out: DeviceResult, index_offset: int = 0, buf=None):
