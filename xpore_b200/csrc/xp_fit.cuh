@@ -26,7 +26,9 @@
 //                      group, S1_0, S2_0 and entropy of the current sweep (odd stride: conflict free);
 //                      doubles as the 256-bin select histogram before the first sweep
 //   tot[G+4]           row totals
-//   Asm[G]             per-group constant of d_n
+//   Asm[G]             per-group constant A_g of d_n, as used by the E-step of the current sweep
+//   dps[G]             psi(c_g1) - psi(c_g0) of the scalar phase in progress (becomes Asm only if another sweep follows,
+//                      so Asm / bc still describe the last E-step when the position is done: --save_models)
 //   sc[8]              psi(alpha_k), lgamma(alpha_k), ln beta_k, ln lambda_k published by their lanes
 //   bc[8]              leader -> team broadcast: B, C, continue flag, ticket, reduction slots
 //   pc[8]              per-position values the leader needs once per sweep (m0, a0, b0, the two ELBO constants,
@@ -83,7 +85,7 @@ __host__ __device__ inline size_t fit_scratch_doubles(int G, int TW) {
     return s > 128 ? s : 128;  // >= 1 KB: the radix-select histogram lives here before the first sweep
 }
 __host__ __device__ inline size_t fit_team_smem_bytes(int cap, int G, int TW) {
-    const size_t doubles = (size_t)(cap + 2) + fit_scratch_doubles(G, TW) + (G + 4) + G + 8 + 8 + 8;
+    const size_t doubles = (size_t)(cap + 2) + fit_scratch_doubles(G, TW) + (G + 4) + 2 * G + 8 + 8 + 8;
     const size_t bytes = doubles * 8 + (size_t)((G + 2) & ~1) * 4 + 8 + (size_t)(cap + 2);
     return (bytes + 15) & ~(size_t)15;
 }
@@ -292,7 +294,8 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
     double* scratch = slab + a.cap + 2;
     double* tot = scratch + fit_scratch_doubles(G, TW);
     double* Asm = tot + G + 4;
-    double* sc = Asm + G;
+    double* dps = Asm + G;
+    double* sc = dps + G;
     double* bc = sc + 8;
     double* pc = bc + 8;
     int* goff = reinterpret_cast<int*>(pc + 8);
@@ -502,12 +505,6 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
                 // ---- scalar phase: special functions spread over lanes, one uniform code path ----
                 // slots: [0,2G) c_gk -> psi, lgamma;  2G+k alpha_k -> psi, lgamma;
                 //        2G+2+k -> ln beta_k;  2G+4+k -> ln lambda_k       (slot parity = component)
-                if (a.coef != nullptr && it >= 1) {  // --save_models: keep the coefficients of the E-step just done
-                    double* cf = a.coef + (size_t)p * (G + 2);
-                    for (int g = lane; g < G; g += 32) cf[g] = Asm[g];
-                    if (lane < 2) cf[G + lane] = bc[lane];
-                    __syncwarp();
-                }
                 double e_loc = 0.0;
                 for (int s0 = 0; s0 < 2 * G + 6; s0 += 32) {
                     const int s = s0 + lane;
@@ -539,7 +536,7 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
                     const double ldp = xlog_tab(tab, dp);
                     const double pso = __shfl_xor_sync(kFull, ps, 1);
                     if (role == 0) {
-                        if (kpar) Asm[s >> 1] = ps - pso;  // psi(c_g1) - psi(c_g0)  (gmm.py:283-284)
+                        if (kpar) dps[s >> 1] = ps - pso;  // psi(c_g1) - psi(c_g0)  (gmm.py:283-284)
                         if (counted) e_loc += lg;          // + sum_k lgamma(c_gk) (+ ln den, taken off below)
                     } else if (role == 1) {
                         sc[kpar] = ps;
@@ -584,7 +581,7 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
                     const double B = kpar ? (u - uo) : (uo - u);
                     const double C = -0.5 * (kpar ? (tb - tbo) : (tbo - tb));
                     const double base = 0.5 * (kpar ? (wq - wo) : (wo - wq));
-                    for (int g = lane; g < G; g += 32) Asm[g] += base;
+                    for (int g = lane; g < G; g += 32) Asm[g] = dps[g] + base;
                     if (lane == 0) {
                         bc[0] = B;
                         bc[1] = C;
@@ -721,6 +718,11 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
                 out[FIT_LAM + kpar] = c.lam;
                 out[FIT_ALPHA + kpar] = c.alpha;
                 out[FIT_BETA + kpar] = c.beta;
+            }
+            if (a.coef != nullptr && it >= 1) {  // --save_models: coefficients of the last E-step
+                double* cf = a.coef + (size_t)p * (G + 2);
+                for (int g = lane; g < G; g += 32) cf[g] = Asm[g];
+                if (lane < 2) cf[G + lane] = bc[lane];
             }
             if (lane == 0) {
                 out[FIT_ELBO] = elbo;
