@@ -20,7 +20,8 @@
 // The 256-entry 2^(j/256) table and the 129-entry {1/c, ln c} table live in shared memory (4 KB per CTA).
 //
 // CTA shared memory:  [ exp2 table 256 f64 | {1/c, ln c} table 129 double2 (+pad) | team 0 | team 1 | ... ]
-// team region (doubles unless noted):
+// team region (doubles unless noted; the fixed-size arrays come first so that their addresses are the team base
+// plus a constant, then the G-sized ones, then the 16-byte aligned slab, the scratch rows and gid):
 //   slab[cap+2]        centred reads y' (TMA destination; +2 = 16-byte alignment slack)
 //   scratch[32 TW x RL] one row of RL = odd(G+3) doubles per thread of the team: its partial N_g0 per
 //                      group, S1_0, S2_0 and entropy of the current sweep (odd stride: conflict free);
@@ -84,9 +85,14 @@ __host__ __device__ inline size_t fit_scratch_doubles(int G, int TW) {
     const size_t s = (size_t)fit_row_stride(G) * (32 * TW);
     return s > 128 ? s : 128;  // >= 1 KB: the radix-select histogram lives here before the first sweep
 }
+// fixed-size arrays first (sc, bc, pc, mbar at constant offsets from the team base), then the G-sized ones,
+// then - 16-byte aligned - the slab
+__host__ __device__ inline size_t fit_team_header_bytes(int G) {
+    const size_t bytes = (size_t)(8 + 8 + 8 + 2) * 8 + (size_t)((G + 4) + 2 * G) * 8 + (size_t)((G + 2) & ~1) * 4;
+    return (bytes + 15) & ~(size_t)15;
+}
 __host__ __device__ inline size_t fit_team_smem_bytes(int cap, int G, int TW) {
-    const size_t doubles = (size_t)(cap + 2) + fit_scratch_doubles(G, TW) + (G + 4) + 2 * G + 8 + 8 + 8;
-    const size_t bytes = doubles * 8 + (size_t)((G + 2) & ~1) * 4 + 8 + (size_t)(cap + 2);
+    const size_t bytes = fit_team_header_bytes(G) + ((size_t)(cap + 2) + fit_scratch_doubles(G, TW)) * 8 + (size_t)(cap + 2);
     return (bytes + 15) & ~(size_t)15;
 }
 
@@ -272,6 +278,37 @@ __device__ __forceinline__ void estep_dev(const SmemTab& tab, const EConst& K, d
     h = fma(rmin, ax, l1p);  // |d| > 500 only when rmin < 1e-217: the clip does not show
 }
 
+// Column sums of the team's rows of partial sums for R <= 32 / PARTS columns: PARTS lanes share a column
+// (each sums a contiguous block of rows with two accumulators), then butterfly shuffles combine the
+// parts, so EVERY lane ends up with the total of column lane % (32 / PARTS) (0 for columns >= R).
+template <int TW, int PARTS>
+__device__ __forceinline__ double team_colsum(const double* scratch, int RL, int R, int lane) {
+    constexpr int RPP = 32 / PARTS, LEN = 32 * TW / PARTS;
+    const int row = lane % RPP, part = lane / RPP;
+    double t0 = 0.0, t1 = 0.0;
+    if (row < R) {
+        const double* q = scratch + (size_t)(part * LEN) * RL + row;
+#pragma unroll(LEN <= 16 ? LEN / 2 : 4)
+        for (int l = 0; l < LEN; l += 2) {
+            t0 += q[(size_t)l * RL];
+            t1 += q[(size_t)(l + 1) * RL];
+        }
+    }
+    double t = t0 + t1;
+    if (PARTS >= 2) t += __shfl_xor_sync(kFull, t, RPP);
+    if (PARTS >= 4) t += __shfl_xor_sync(kFull, t, 2 * RPP);
+    return t;
+}
+// sum over the columns c < G of the per-lane column totals of team_colsum (every lane gets it)
+template <int PARTS>
+__device__ __forceinline__ double colsum_first(double t, int G, int lane) {
+    constexpr int RPP = 32 / PARTS;
+    double v = (lane % RPP < G) ? t : 0.0;
+#pragma unroll
+    for (int m = RPP / 2; m > 0; m >>= 1) v += __shfl_xor_sync(kFull, v, m);
+    return v;
+}
+
 template <int TW, int MAXT>
 __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -290,17 +327,17 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
     tab.lg = smem_u32(tab_lg) - (0x3ff00000u >> 13) * 16u;
 
     unsigned char* wbase = smem_raw + kFitTableBytes + (size_t)team * fit_team_smem_bytes(a.cap, G, TW);
-    double* slab = reinterpret_cast<double*>(wbase);
-    double* scratch = slab + a.cap + 2;
-    double* tot = scratch + fit_scratch_doubles(G, TW);
-    double* Asm = tot + G + 4;
-    double* dps = Asm + G;
-    double* sc = dps + G;
+    double* sc = reinterpret_cast<double*>(wbase);
     double* bc = sc + 8;
     double* pc = bc + 8;
-    int* goff = reinterpret_cast<int*>(pc + 8);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(goff + ((G + 2) & ~1));
-    unsigned char* gid = reinterpret_cast<unsigned char*>(mbar + 1);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(pc + 8);
+    double* tot = pc + 10;
+    double* Asm = tot + G + 4;
+    double* dps = Asm + G;
+    int* goff = reinterpret_cast<int*>(dps + G);
+    double* slab = reinterpret_cast<double*>(wbase + fit_team_header_bytes(G));
+    double* scratch = slab + a.cap + 2;
+    unsigned char* gid = reinterpret_cast<unsigned char*>(scratch + fit_scratch_doubles(G, TW));
 
     if (tid == 0) {
         mbar_init(mbar, 1);
@@ -501,6 +538,7 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
 
         for (;;) {
             bool go = true;
+            double B = 0.0, C = 0.0;
             if (leader) {
                 // ---- scalar phase: special functions spread over lanes, one uniform code path ----
                 // slots: [0,2G) c_gk -> psi, lgamma;  2G+k alpha_k -> psi, lgamma;
@@ -578,22 +616,26 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
                     const double uo = __shfl_xor_sync(kFull, u, 1);
                     const double tbo = __shfl_xor_sync(kFull, tb, 1);
                     const double wo = __shfl_xor_sync(kFull, wq, 1);
-                    const double B = kpar ? (u - uo) : (uo - u);
-                    const double C = -0.5 * (kpar ? (tb - tbo) : (tbo - tb));
+                    B = kpar ? (u - uo) : (uo - u);  // the same value in every lane
+                    C = -0.5 * (kpar ? (tb - tbo) : (tbo - tb));
                     const double base = 0.5 * (kpar ? (wq - wo) : (wo - wq));
-                    for (int g = lane; g < G; g += 32) Asm[g] = dps[g] + base;
+                    if (lane < G) Asm[lane] = dps[lane] + base;
+                    if (G > 32 && lane + 32 < G) Asm[lane + 32] = dps[lane + 32] + base;  // G <= kMaxGroups = 64
                     if (lane == 0) {
                         bc[0] = B;
                         bc[1] = C;
                     }
                 }
-                if (lane == 0) bc[2] = go ? 1.0 : 0.0;
+                if (TW > 1 && lane == 0) bc[2] = go ? 1.0 : 0.0;
             }
             team_sync<TW>(team);
-            if (TW > 1) go = bc[2] != 0.0;
+            if (TW > 1) {
+                go = bc[2] != 0.0;
+                B = bc[0];
+                C = bc[1];
+            }
             if (!go) break;
             first = false;
-            const double B = bc[0], C = bc[1];
             // ---- E-step + component-0 moments: one pass over the resident reads ------------------
             // A thread takes the adjacent reads 2j, 2j+1 (j = 32 trip + lane: one 16-byte load) of every
             // full trip of 64 reads, then single reads of the tail, so the groups it meets never decrease;
@@ -669,33 +711,36 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
             srow[G + 2] = Hh;
             team_sync<TW>(team);
             if (leader) {
-                // row sums: `parts` lanes share a row, then combine through shuffles
-                const int parts = (R <= 8) ? 4 : (R <= 16) ? 2 : 1;
-                const int rpp = 32 / parts;  // rows handled per pass
-                constexpr int NC = 32 * TW;
-                for (int r0 = 0; r0 < R; r0 += rpp) {
-                    const int row = r0 + lane % rpp, part = lane / rpp;
-                    double t0 = 0.0, t1 = 0.0;
-                    if (row < R) {
-                        const int len = NC / parts;
-                        const double* q = scratch + (size_t)(part * len) * RL + row;
-                        for (int l = 0; l < len; l += 2, q += 2 * RL) {
-                            t0 += q[0];
-                            t1 += q[RL];
+                // column sums of the rows of partial sums (several lanes per column when there are few columns)
+                double n0;
+                if (R <= 8) {
+                    const double t = team_colsum<TW, 4>(scratch, RL, R, lane);
+                    if (lane < R) tot[lane] = t;
+                    n0 = colsum_first<4>(t, G, lane);
+                } else if (R <= 16) {
+                    const double t = team_colsum<TW, 2>(scratch, RL, R, lane);
+                    if (lane < R) tot[lane] = t;
+                    n0 = colsum_first<2>(t, G, lane);
+                } else {
+                    constexpr int NC = 32 * TW;
+                    for (int r0 = 0; r0 < R; r0 += 32) {
+                        const int row = r0 + lane;
+                        double t0 = 0.0, t1 = 0.0;
+                        if (row < R) {
+                            const double* q = scratch + row;
+                            for (int l = 0; l < NC; l += 2, q += 2 * RL) {
+                                t0 += q[0];
+                                t1 += q[RL];
+                            }
+                            tot[row] = t0 + t1;
                         }
                     }
-                    double t = t0 + t1;
-                    if (parts >= 2) t += __shfl_down_sync(kFull, t, rpp);
-                    if (parts >= 4) {
-                        // lanes [0,rpp) now hold parts 0+1, lanes [2rpp,3rpp) parts 2+3
-                        t += __shfl_down_sync(kFull, t, 2 * rpp);
-                    }
-                    if (row < R && part == 0) tot[row] = t;
+                    __syncwarp();
+                    n0 = 0.0;
+                    for (int g = lane; g < G; g += 32) n0 += tot[g];
+                    n0 = warp_sum(n0);
                 }
                 __syncwarp();
-                double n0 = 0.0;
-                for (int g = lane; g < G; g += 32) n0 += tot[g];
-                n0 = warp_sum(n0);
                 const double s10 = tot[G], s20 = tot[G + 1];
                 Hent = tot[G + 2];
                 Nk = kpar ? ((double)n - n0) : n0;
