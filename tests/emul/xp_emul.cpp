@@ -102,28 +102,24 @@ void emul_fit(int n, const double* y, int G, const int* glen, double km, double 
     double tb[2], lt[2];
     bool first = true;
     for (;;) {
-        double e = 0.0, prod = 1.0;  // prod: product of the shift products den of every parameter
+        double e = 0.0;
         for (int g = 0; g < G; ++g) {
-            double ps[2], lg[2], den[2];
+            double ps[2], lg[2];
             for (int k = 0; k < 2; ++k) {
                 const double N = first ? 0.0 : (k ? (double)glen[g] - N0g[g] : N0g[g]);
-                psi_lgamma_parts(HostTab(), conc0 + N, &ps[k], &lg[k], &den[k]);
-                if (glen[g] > 0) {
-                    e += lg[k];
-                    prod *= den[k];
-                }
+                psi_lgamma_parts(HostTab(), conc0 + N, &ps[k], &lg[k]);
+                if (glen[g] > 0) e += lg[k];
             }
             dpsi[g] = ps[1] - ps[0];
         }
         for (int k = 0; k < 2; ++k) {
-            double ps, lg, den;
-            psi_lgamma_parts(HostTab(), c[k].alpha, &ps, &lg, &den);
-            prod *= den;
-            e += elbo_component(c[k], Nk[k], S1[k], S2[k], a0, b0, prior_gamma, ps, lg, xlog_tab(HostTab(), c[k].beta),
-                                xlog_tab(HostTab(), c[k].lam), tb[k], lt[k]);
+            double ps, lg;
+            psi_lgamma_parts(HostTab(), c[k].alpha, &ps, &lg);
+            const double lnb = xlog_tab(HostTab(), c[k].beta), lnl = xlog_tab(HostTab(), c[k].lam);
+            if (first) e += elbo_component(c[k], Nk[k], S1[k], S2[k], a0, b0, prior_gamma, ps, lg, lnb, lnl, tb[k], lt[k]);
+            else e += elbo_component_closed(c[k], ps, lg, lnb, lnl, tb[k], lt[k]);
         }
-        e -= xlog_tab(HostTab(), prod);
-        elbo = e + Kconst + Hent;
+        elbo = e + (first ? Kconst : Kconst + elbo_closed_const(prior_gamma, n)) + Hent;
         if (it >= 1) {
             if (elbos) elbos[it - 1] = elbo;
             const int rule = stop_rule(elbo, elbo_old, stopping);

@@ -110,16 +110,17 @@ XP_HD void posterior_read(const Tab& tab, double d, double& prob0, double& lnp0,
 }
 
 // ---- psi / lgamma of one posterior parameter inside the sweeps (xp_math.cuh: shift10, xlog_tab) -------
-// Returns psi(x), lgamma(x) + ln den and den, where den is the shift product (1 for x >= 10): the caller
-// multiplies the den of all its parameters and subtracts one logarithm of the product from the ELBO.
+// Returns psi(x) and lgamma(x); den is the shift product (1 for x >= 10), whose logarithm comes from the same table.
 template <class Tab>
-XP_HD void psi_lgamma_parts(const Tab& tab, double x, double* psi, double* lgam_plus_lden, double* den_out) {
+XP_HD void psi_lgamma_parts(const Tab& tab, double x, double* psi, double* lgam) {
     double z, num, den;
     shift10(x, z, num, den);
     const double lz = xlog_tab(tab, z);
+    const double lden = xlog_tab(tab, den);
     const double q = xrcp3(z * den);
-    psi_lgamma_shifted(z, lz, q * den, num * (q * z), psi, lgam_plus_lden);
-    *den_out = den;
+    double lg;
+    psi_lgamma_shifted(z, lz, q * den, num * (q * z), psi, &lg);
+    *lgam = lg - lden;
 }
 
 // ---- M-step for one component (gmm.py:364-370 in centred moments) ------------------------
@@ -152,6 +153,21 @@ XP_HD double elbo_component(const Comp& c, double Nk, double S1, double S2, doub
     const double t9 = c.alpha * ln_b - lg_a + (c.alpha - 1.0) * ltau - c.alpha;
     return t1 + t6 + t7 - t8 - t9;
 }
+
+// The same share once the component's posterior is the M-step of the very statistics the ELBO is evaluated
+// on (every sweep but the first, whose locations are the percentile start): with alpha = a0 + N/2,
+// lambda = 1 + N, m' = S1/lambda, beta = b0 + (S2 - S1 m')/2 the E[ln tau] terms cancel
+// (N/2 + a0 - alpha = 0), the quadratic terms sum to E[tau] beta = alpha, and what is left is the ratio of the
+// Normal-Gamma normalisers:
+//   lgamma(alpha) - alpha ln beta - ln(lambda)/2  +  [a0 ln b0 - lgamma(a0)]  -  (N/2) ln 2 pi
+// The last two terms are per-position constants (sum_k N_k = n): the caller adds elbo_closed_const once.
+XP_HD double elbo_component_closed(const Comp& c, double psi_a, double lg_a, double ln_b, double ln_lam,
+                                   double& tbar, double& ltau) {
+    tbar = xdiv3(c.alpha, c.beta);
+    ltau = psi_a - ln_b;
+    return lg_a - fma(c.alpha, ln_b, 0.5 * ln_lam);
+}
+XP_HD double elbo_closed_const(double prior_gamma, int n) { return fma(-0.5 * kLn2Pi, (double)n, 2.0 * prior_gamma); }
 
 // Coefficients of d_n = A_g + y'(B + C y') from the two components (gmm.py:236-238 expanded):
 //   A_g = base + (E ln w_g1 - E ln w_g0)

@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
         // ---- leader state: lanes of parity k hold component k ---------------------------------------
         Comp c = mstep(0.0, 0.0, 0.0, a0, b0);
         if (kpar) c.mp = loc1;
-        double Nk = 0.0, S1k = 0.0, S2k = 0.0, Hent = 0.0;
+        double Hent = 0.0;
         double elbo = -INFINITY, elbo_old = -INFINITY;
         if (XP_FIT_PARK && leader && lane == 0) {
             pc[0] = m0;
@@ -562,34 +562,33 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
                     double z, num, den;
                     shift10(role == 2 ? 16.0 : x, z, num, den);
                     if (role == 2) z = x;
-                    // one logarithm serves the ln den of every counted slot of this pass: ln of their product
-                    // (den <= 10!, at most 32 factors)
-                    double dp = counted ? den : 1.0;
-#pragma unroll
-                    for (int m = 16; m > 0; m >>= 1) dp *= __shfl_xor_sync(kFull, dp, m);
                     const double lz = xlog_tab(tab, z);
+                    const double lden = xlog_tab(tab, den);  // den = 1 -> exactly 0
                     const double q = xrcp3(z * den);
                     double ps, lg;
                     psi_lgamma_shifted(z, lz, q * den, num * (q * z), &ps, &lg);
-                    const double ldp = xlog_tab(tab, dp);
+                    lg -= lden;
                     const double pso = __shfl_xor_sync(kFull, ps, 1);
                     if (role == 0) {
                         if (kpar) dps[s >> 1] = ps - pso;  // psi(c_g1) - psi(c_g0)  (gmm.py:283-284)
-                        if (counted) e_loc += lg;          // + sum_k lgamma(c_gk) (+ ln den, taken off below)
+                        if (counted) e_loc += lg;          // + sum_k lgamma(c_gk)
                     } else if (role == 1) {
                         sc[kpar] = ps;
-                        sc[2 + kpar] = lg;                 // lgamma(alpha_k) + ln den
+                        sc[2 + kpar] = lg;                 // lgamma(alpha_k)
                     } else if (role == 2) {
                         sc[4 + (s - 2 * G - 2)] = lz;
                     }
-                    if (lane == 0) e_loc -= ldp;
                 }
                 __syncwarp();
-                double tb, lt;
-                const double ek = elbo_component(c, Nk, S1k, S2k, XP_PK(1, a0), XP_PK(2, b0), XP_PK(4, prior_gamma), sc[kpar], sc[2 + kpar],
-                                                 sc[4 + kpar], sc[6 + kpar], tb, lt);
+                double tb, lt, ek;
+                if (first)
+                    ek = elbo_component(c, 0.0, 0.0, 0.0, XP_PK(1, a0), XP_PK(2, b0), XP_PK(4, prior_gamma), sc[kpar], sc[2 + kpar],
+                                        sc[4 + kpar], sc[6 + kpar], tb, lt);
+                else
+                    ek = elbo_component_closed(c, sc[kpar], sc[2 + kpar], sc[4 + kpar], sc[6 + kpar], tb, lt);
                 if (lane < 2) e_loc += ek;
                 elbo = warp_sum(e_loc) + XP_PK(3, Kconst) + Hent;
+                if (first && lane == 0) pc[3] = pc[3] + elbo_closed_const(pc[4], n);  // constants of the closed form from now on
                 if (it >= 1) {
                     const int rule = stop_rule(elbo, XP_PK(7, elbo_old), a.stopping);
                     if (rule == 2) {
@@ -743,9 +742,9 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
                 __syncwarp();
                 const double s10 = tot[G], s20 = tot[G + 1];
                 Hent = tot[G + 2];
-                Nk = kpar ? ((double)n - n0) : n0;
-                S1k = kpar ? (XP_PK(5, T1) - s10) : s10;
-                S2k = kpar ? (XP_PK(6, T2) - s20) : s20;
+                const double Nk = kpar ? ((double)n - n0) : n0;
+                const double S1k = kpar ? (XP_PK(5, T1) - s10) : s10;
+                const double S2k = kpar ? (XP_PK(6, T2) - s20) : s20;
                 // ---- M-step (gmm.py:292-294, 364-370) ---------------------------------------------
                 c = mstep(Nk, S1k, S2k, XP_PK(1, a0), XP_PK(2, b0));
             }
