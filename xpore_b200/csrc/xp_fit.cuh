@@ -23,8 +23,9 @@
 // team region (doubles unless noted; the fixed-size arrays come first so that their addresses are the team base
 // plus a constant, then the G-sized ones, then the 16-byte aligned slab, the scratch rows and gid):
 //   slab[cap+2]        centred reads y' (TMA destination; +2 = 16-byte alignment slack)
-//   scratch[32 TW x RL] one row of RL = odd(G+3) doubles per thread of the team: its partial N_g0 per
-//                      group, S1_0, S2_0 and entropy of the current sweep (odd stride: conflict free);
+//   scratch[(G+3) x (32 TW + 1)]  column c holds one double per thread of the team: its partial N_g0 of
+//                      group c < G, then S1_0, S2_0 and the entropy of the current sweep (odd column pitch: the
+//                      column sums read conflict free, and a thread's entry is scratch + tid + c * pitch);
 //                      doubles as the 256-bin select histogram before the first sweep
 //   tot[G+4]           row totals
 //   Asm[G]             per-group constant A_g of d_n, as used by the E-step of the current sweep
@@ -80,19 +81,22 @@ constexpr int kTabLogDoubles = 130 * 2;
 constexpr size_t kFitTableBytes = (size_t)(kTabExpDoubles + kTabLogDoubles) * 8;
 
 __host__ __device__ inline int fit_rows(int G) { return G + 3; }
-__host__ __device__ inline int fit_row_stride(int G) { return (G + 3) | 1; }
+// scratch: column c (N_g0 of group c < G, then S1_0, S2_0, entropy) holds one double per thread of the team;
+// columns are 32 TW + 1 doubles apart (odd: the column sums read conflict free)
 __host__ __device__ inline size_t fit_scratch_doubles(int G, int TW) {
-    const size_t s = (size_t)fit_row_stride(G) * (32 * TW);
+    const size_t s = (size_t)fit_rows(G) * (32 * TW + 1);
     return s > 128 ? s : 128;  // >= 1 KB: the radix-select histogram lives here before the first sweep
 }
-// fixed-size arrays first (sc, bc, pc, mbar at constant offsets from the team base), then the G-sized ones,
-// then - 16-byte aligned - the slab
-__host__ __device__ inline size_t fit_team_header_bytes(int G) {
-    const size_t bytes = (size_t)(8 + 8 + 8 + 2) * 8 + (size_t)((G + 4) + 2 * G) * 8 + (size_t)((G + 2) & ~1) * 4;
+// fixed-size arrays first (sc, bc, pc, mbar at constant offsets from the team base), then the scratch columns
+// (constant offset too: the E-step's stores into them need no G- or cap-dependent address arithmetic), then the
+// G-sized arrays, then - 16-byte aligned - the slab
+constexpr int kFitFixedDoubles = 8 + 8 + 8 + 2;
+__host__ __device__ inline size_t fit_team_header_bytes(int G, int TW) {
+    const size_t bytes = ((size_t)kFitFixedDoubles + fit_scratch_doubles(G, TW) + (G + 4) + 2 * G) * 8 + (size_t)((G + 2) & ~1) * 4;
     return (bytes + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t fit_team_smem_bytes(int cap, int G, int TW) {
-    const size_t bytes = fit_team_header_bytes(G) + ((size_t)(cap + 2) + fit_scratch_doubles(G, TW)) * 8 + (size_t)(cap + 2);
+    const size_t bytes = fit_team_header_bytes(G, TW) + (size_t)(cap + 2) * 8 + (size_t)(cap + 2);
     return (bytes + 15) & ~(size_t)15;
 }
 
@@ -282,16 +286,16 @@ __device__ __forceinline__ void estep_dev(const SmemTab& tab, const EConst& K, d
 // (each sums a contiguous block of rows with two accumulators), then butterfly shuffles combine the
 // parts, so EVERY lane ends up with the total of column lane % (32 / PARTS) (0 for columns >= R).
 template <int TW, int PARTS>
-__device__ __forceinline__ double team_colsum(const double* scratch, int RL, int R, int lane) {
-    constexpr int RPP = 32 / PARTS, LEN = 32 * TW / PARTS;
+__device__ __forceinline__ double team_colsum(const double* scratch, int R, int lane) {
+    constexpr int RPP = 32 / PARTS, LEN = 32 * TW / PARTS, CS = 32 * TW + 1;
     const int row = lane % RPP, part = lane / RPP;
     double t0 = 0.0, t1 = 0.0;
     if (row < R) {
-        const double* q = scratch + (size_t)(part * LEN) * RL + row;
+        const double* q = scratch + row * CS + part * LEN;
 #pragma unroll(LEN <= 16 ? LEN / 2 : 4)
         for (int l = 0; l < LEN; l += 2) {
-            t0 += q[(size_t)l * RL];
-            t1 += q[(size_t)(l + 1) * RL];
+            t0 += q[l];
+            t1 += q[l + 1];
         }
     }
     double t = t0 + t1;
@@ -310,13 +314,14 @@ __device__ __forceinline__ double colsum_first(double t, int G, int lane) {
 }
 
 template <int TW, int MAXT>
-__global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
+__global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int team = warp / TW, tw = warp % TW, tid = tw * 32 + lane;  // tid: thread index inside the team
     const bool leader = (tw == 0);
     const int G = a.G;
-    const int R = fit_rows(G), RL = fit_row_stride(G);
+    const int R = fit_rows(G);
+    constexpr int CS = 32 * TW + 1;  // doubles between scratch columns
 
     double* tab_e2 = reinterpret_cast<double*>(smem_raw);
     double2* tab_lg = reinterpret_cast<double2*>(tab_e2 + kTabExpDoubles);
@@ -331,13 +336,13 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
     double* bc = sc + 8;
     double* pc = bc + 8;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(pc + 8);
-    double* tot = pc + 10;
+    double* scratch = pc + 10;
+    double* tot = scratch + fit_scratch_doubles(G, TW);
     double* Asm = tot + G + 4;
     double* dps = Asm + G;
     int* goff = reinterpret_cast<int*>(dps + G);
-    double* slab = reinterpret_cast<double*>(wbase + fit_team_header_bytes(G));
-    double* scratch = slab + a.cap + 2;
-    unsigned char* gid = reinterpret_cast<unsigned char*>(scratch + fit_scratch_doubles(G, TW));
+    double* slab = reinterpret_cast<double*>(wbase + fit_team_header_bytes(G, TW));
+    unsigned char* gid = reinterpret_cast<unsigned char*>(slab + a.cap + 2);
 
     if (tid == 0) {
         mbar_init(mbar, 1);
@@ -499,8 +504,8 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
         team_sync<TW>(team);
         // this thread's row of partial sums.  The groups a thread meets are the same in every sweep, so the
         // entries it never writes are cleared once per position.
-        double* srow = scratch + (size_t)tid * RL;
-        for (int g = 0; g < G; ++g) srow[g] = 0.0;
+        double* scol = scratch + tid;  // this thread's entry of column 0
+        for (int g = 0; g < G; ++g) scol[g * CS] = 0.0;
         const int g_first = gid[0];
 
         // ---- leader state: lanes of parity k hold component k ---------------------------------------
@@ -638,12 +643,12 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
             // ---- E-step + component-0 moments: one pass over the resident reads ------------------
             // A thread takes the adjacent reads 2j, 2j+1 (j = 32 trip + lane: one 16-byte load) of every
             // full trip of 64 reads, then single reads of the tail, so the groups it meets never decrease;
-            // its N_g0 partial goes to srow[g] whenever the group changes.  The loop body is branch free.
+            // its N_g0 partial goes to scol[g] whenever the group changes.  The loop body is branch free.
             double accN = 0.0, S1 = 0.0, S2 = 0.0, Hh = 0.0;
             {
                 EConst K;
                 K.load();
-                unsigned pg = g_first;  // group of this thread's last read; accN goes to srow[pg] on leaving it
+                unsigned pg = g_first;  // group of this thread's last read; accN goes to column pg on leaving it
                 constexpr int NR = XP_FIT_NR;   // adjacent reads per thread and trip
                 const int nfull = n / (32 * NR);
 #define XP_READ(yy, gg)                              \
@@ -652,7 +657,7 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
         double r_, h_;                               \
         estep_dev(tab, K, d_, r_, h_);               \
         if ((gg) != pg) {                            \
-            srow[pg] = accN;                         \
+            scol[pg * CS] = accN;                         \
             accN = 0.0;                              \
         }                                            \
         pg = (gg);                                   \
@@ -662,16 +667,18 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
         S2 = fma(w_, (yy), S2);                      \
         Hh += h_;                                    \
     }
-                for (int trip = tw; trip < nfull; trip += TW) {
-                    const int i0 = trip * (32 * NR) + lane;
+                const double* yp = yv + tw * (32 * NR) + lane;
+                const unsigned char* gp = gid + tw * (32 * NR) + lane;
+                const double* const yend = yv + nfull * (32 * NR) + lane;  // tw < TW <= trips apart: reached exactly
+                for (; yp < yend; yp += TW * (32 * NR), gp += TW * (32 * NR)) {
                     double y4[NR], d4[NR], r4[NR], h4[NR];
                     unsigned gg[NR];
                     // one load per read (not one wide load per thread): ptxas interleaves the NR dependency
                     // chains only when they start from separate loads
 #pragma unroll
                     for (int i = 0; i < NR; ++i) {
-                        gg[i] = gid[i0 + 32 * i];
-                        y4[i] = yv[i0 + 32 * i];
+                        gg[i] = gp[32 * i];
+                        y4[i] = yp[32 * i];
                     }
 #pragma unroll
                     for (int i = 0; i < NR; ++i) d4[i] = fma(y4[i], fma(C, y4[i], B), Asm[gg[i]]);
@@ -680,7 +687,7 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
 #pragma unroll
                     for (int i = 0; i < NR; ++i) {
                         if (gg[i] != pg) {
-                            srow[pg] = accN;
+                            scol[pg * CS] = accN;
                             accN = 0.0;
                         }
                         pg = gg[i];
@@ -703,21 +710,24 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
                     __syncwarp();
                 }
 #undef XP_READ
-                srow[pg] = accN;
+                scol[pg * CS] = accN;
             }
-            srow[G] = S1;
-            srow[G + 1] = S2;
-            srow[G + 2] = Hh;
+            {
+                double* sg = scol + G * CS;
+                sg[0] = S1;
+                sg[CS] = S2;
+                sg[2 * CS] = Hh;
+            }
             team_sync<TW>(team);
             if (leader) {
                 // column sums of the rows of partial sums (several lanes per column when there are few columns)
                 double n0;
                 if (R <= 8) {
-                    const double t = team_colsum<TW, 4>(scratch, RL, R, lane);
+                    const double t = team_colsum<TW, 4>(scratch, R, lane);
                     if (lane < R) tot[lane] = t;
                     n0 = colsum_first<4>(t, G, lane);
                 } else if (R <= 16) {
-                    const double t = team_colsum<TW, 2>(scratch, RL, R, lane);
+                    const double t = team_colsum<TW, 2>(scratch, R, lane);
                     if (lane < R) tot[lane] = t;
                     n0 = colsum_first<2>(t, G, lane);
                 } else {
@@ -726,10 +736,10 @@ __global__ void __launch_bounds__(MAXT) xp_fit_kernel(FitArgs a) {
                         const int row = r0 + lane;
                         double t0 = 0.0, t1 = 0.0;
                         if (row < R) {
-                            const double* q = scratch + row;
-                            for (int l = 0; l < NC; l += 2, q += 2 * RL) {
-                                t0 += q[0];
-                                t1 += q[RL];
+                            const double* q = scratch + row * CS;
+                            for (int l = 0; l < NC; l += 2) {
+                                t0 += q[l];
+                                t1 += q[l + 1];
                             }
                             tot[row] = t0 + t1;
                         }
