@@ -85,7 +85,7 @@ __host__ __device__ inline int fit_rows(int G) { return G + 3; }
 // columns are 32 TW + 1 doubles apart (odd: the column sums read conflict free)
 __host__ __device__ inline size_t fit_scratch_doubles(int G, int TW) {
     const size_t s = (size_t)fit_rows(G) * (32 * TW + 1);
-    return s > 128 ? s : 128;  // >= 1 KB: the radix-select histogram lives here before the first sweep
+    return s > 256 ? s : 256;  // >= 2 KB: the two select histograms live here before the first sweep
 }
 // fixed-size arrays first (sc, bc, pc, mbar at constant offsets from the team base), then the scratch columns
 // (constant offset too: the E-step's stores into them need no G- or cap-dependent address arithmetic), then the
@@ -220,6 +220,69 @@ __device__ void team_select2(const double* yv, int n, int r, uint64_t kmin, uint
         }
         b = keyd(warp_min_u64(mn));
     }
+}
+
+// ---- order statistics of the u16 read format, taken on the integer codes before they are decoded -----------
+// (the decode is strictly increasing, so rank r of the codes is rank r of the reads).  16-bit keys need at most
+// two 8-bit digits, and the histogram of the high byte serves both percentiles of a position.
+//
+// Bin of a 256-bin histogram holding rank `rank`, that bin's count and the rank inside it (every lane gets them).
+__device__ __forceinline__ void hist_find(const int* hist, int rank, int lane, int& bin, int& within, int& cnt) {
+    int h[8], s = 0;
+    {
+        const int4 v0 = reinterpret_cast<const int4*>(hist)[lane * 2], v1 = reinterpret_cast<const int4*>(hist)[lane * 2 + 1];
+        h[0] = v0.x, h[1] = v0.y, h[2] = v0.z, h[3] = v0.w, h[4] = v1.x, h[5] = v1.y, h[6] = v1.z, h[7] = v1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += h[j];
+    int incl = s;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+        const int v = __shfl_up_sync(kFull, incl, m);
+        if (lane >= m) incl += v;
+    }
+    const int L = __ffs(__ballot_sync(kFull, incl > rank)) - 1;  // lane whose bins hold the wanted rank
+    int below = incl - s, d = 0, c = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (c == 0) {
+            if (below + h[j] > rank) {
+                d = j;
+                c = h[j];
+            } else below += h[j];
+        }
+    }
+    bin = __shfl_sync(kFull, lane * 8 + d, L);
+    within = rank - __shfl_sync(kFull, below, L);
+    cnt = __shfl_sync(kFull, c, L);
+}
+// codes sorted[r] and sorted[min(r + 1, n - 1)]; hist1 = histogram of the high bytes (already built), hist2 = work space
+template <int TW>
+__device__ void team_select2_u16(const unsigned short* q, int n, int r, const int* hist1, int* hist2, int lane, int tid,
+                                 int team, unsigned& qa, unsigned& qb) {
+    constexpr int NT = TW * 32;
+    int bh, wh, ch;
+    hist_find(hist1, r, lane, bh, wh, ch);
+    for (int j = tid; j < 256; j += NT) hist2[j] = 0;
+    team_sync<TW>(team);
+    for (int i = tid; i < n; i += NT) {
+        const unsigned v = q[i];
+        if ((int)(v >> 8) == bh) atomicAdd(&hist2[v & 255u], 1);
+    }
+    team_sync<TW>(team);
+    int bl, wl, cl;
+    hist_find(hist2, wh, lane, bl, wl, cl);
+    qa = ((unsigned)bh << 8) | (unsigned)bl;
+    qb = qa;
+    if (r + 1 < n && wl + 1 >= cl) {  // the next order statistic is the smallest code above qa
+        unsigned mn = 0xffffffffu;
+        for (int i = lane; i < n; i += 32) {
+            const unsigned v = q[i];
+            if (v > qa && v < mn) mn = v;
+        }
+        qb = __reduce_min_sync(kFull, mn);
+    }
+    team_sync<TW>(team);  // everybody is done with hist2 before it is cleared again
 }
 
 template <int TW>
@@ -444,6 +507,26 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
         double* yv = slab;
         const double rscale = 1.0 / a.y_scale;
         constexpr int TT = TW * 32;
+        double med = 0.0, loc1 = 0.0;
+        if (fmt == kYU16) {
+            // initial locations (gmm.py:39-44) from the integer codes, before the decode overwrites them
+            const unsigned short* q = reinterpret_cast<const unsigned short*>(slab) + sh;
+            int* hist1 = reinterpret_cast<int*>(scratch);  // scratch is idle until the first sweep
+            int* hist2 = hist1 + 256;
+            for (int j = tid; j < 256; j += TT) hist1[j] = 0;
+            team_sync<TW>(team);
+            for (int i = tid; i < n; i += TT) atomicAdd(&hist1[q[i] >> 8], 1);
+            team_sync<TW>(team);
+            int lo, hi;
+            double gamma;
+            unsigned qa, qb;
+            percentile_index(n, 0.5, lo, hi, gamma);
+            team_select2_u16<TW>(q, n, lo, hist1, hist2, lane, tid, team, qa, qb);
+            med = np_lerp(y_decode((double)qa, a.y_scale, rscale) - m0, y_decode((double)qb, a.y_scale, rscale) - m0, gamma);
+            percentile_index(n, (0.0 < med) ? 0.75 : 0.25, lo, hi, gamma);
+            team_select2_u16<TW>(q, n, lo, hist1, hist2, lane, tid, team, qa, qb);
+            loc1 = np_lerp(y_decode((double)qa, a.y_scale, rscale) - m0, y_decode((double)qb, a.y_scale, rscale) - m0, gamma);
+        }
         {
             const int last = ((n - 1) / TT) * TT;
             const int step = (fmt == kYF64) ? TT : -TT;
@@ -460,23 +543,32 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
                 if (i < n) yv[i] = v;
             }
         }
-        // totals and min/max keys in one fixed order, whatever the encoding was
+        // totals (and, for the generic select, min/max keys) in one fixed order, whatever the encoding was
         uint64_t kmin = ~0ull, kmax = 0ull;
         double T1 = 0.0, T2 = 0.0;
-        for (int i = tid; i < n; i += TT) {
-            const double v = yv[i];
-            const uint64_t k = dkey(v);
-            kmin = k < kmin ? k : kmin;
-            kmax = k > kmax ? k : kmax;
-            T1 += v;
-            T2 = fma(v, v, T2);
+        if (fmt == kYU16) {
+            for (int i = tid; i < n; i += TT) {
+                const double v = yv[i];
+                T1 += v;
+                T2 = fma(v, v, T2);
+            }
+        } else {
+            for (int i = tid; i < n; i += TT) {
+                const double v = yv[i];
+                const uint64_t k = dkey(v);
+                kmin = k < kmin ? k : kmin;
+                kmax = k > kmax ? k : kmax;
+                T1 += v;
+                T2 = fma(v, v, T2);
+            }
+            kmin = warp_min_u64(kmin);
+            kmax = warp_max_u64(kmax);
         }
-        kmin = warp_min_u64(kmin);
-        kmax = warp_max_u64(kmax);
         T1 = warp_sum(T1);
         T2 = warp_sum(T2);
         if (TW > 1) {  // combine the warps of the team (fixed order: deterministic)
             uint64_t* sk = reinterpret_cast<uint64_t*>(scratch);
+            team_sync<TW>(team);  // the u16 select is done with its histograms
             if (lane == 0) {
                 sk[tw] = kmin;
                 sk[TW + tw] = kmax;
@@ -498,9 +590,11 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
         }
         team_sync<TW>(team);
         // ---- initial locations (gmm.py:39-44) -------------------------------------------------------
-        int* hist = reinterpret_cast<int*>(scratch);  // scratch is idle until the first sweep
-        const double med = team_percentile<TW>(yv, n, 0.5, kmin, kmax, hist, lane, tid, team);
-        const double loc1 = team_percentile<TW>(yv, n, (0.0 < med) ? 0.75 : 0.25, kmin, kmax, hist, lane, tid, team);
+        if (fmt != kYU16) {
+            int* hist = reinterpret_cast<int*>(scratch);  // scratch is idle until the first sweep
+            med = team_percentile<TW>(yv, n, 0.5, kmin, kmax, hist, lane, tid, team);
+            loc1 = team_percentile<TW>(yv, n, (0.0 < med) ? 0.75 : 0.25, kmin, kmax, hist, lane, tid, team);
+        }
         team_sync<TW>(team);
         // this thread's row of partial sums.  The groups a thread meets are the same in every sweep, so the
         // entries it never writes are cleared once per position.
