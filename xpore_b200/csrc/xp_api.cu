@@ -143,7 +143,9 @@ int fit_geometry(int G, int cap_reads, int tw, Geometry* g) {
     return 0;
 }
 
-int launch_fit(const Geometry& g, const xpk::FitArgs& fa, int max_teams_needed, cudaStream_t st) {
+int launch_fit(const Geometry& g, const xpk::FitArgs& fa_in, int max_teams_needed, cudaStream_t st) {
+    xpk::FitArgs fa = fa_in;
+    xpk::fit_fill_layout(fa, g.tw);
     const int need = (max_teams_needed + g.teams - 1) / g.teams;
     const int grid = std::max(1, std::min(g.sms * g.ctas_per_sm, need));
     if (g.tw == 1) {

@@ -74,6 +74,9 @@ struct FitArgs {
     int32_t* n_iter;
     uint32_t* status;
     double* coef;  // optional [P, G+2]: A_g, B, C of the last E-step (for xp_posterior_kernel)
+    // byte offsets inside a team's shared-memory region and its size, filled by fit_fill_layout: the kernel adds
+    // them to the team base as constant-bank operands instead of re-deriving them from G and cap
+    int team_bytes, off_tot, off_asm, off_dps, off_goff, off_slab, off_gid;
 };
 
 constexpr int kTabExpDoubles = 256;
@@ -98,6 +101,17 @@ __host__ __device__ inline size_t fit_team_header_bytes(int G, int TW) {
 __host__ __device__ inline size_t fit_team_smem_bytes(int cap, int G, int TW) {
     const size_t bytes = fit_team_header_bytes(G, TW) + (size_t)(cap + 2) * 8 + (size_t)(cap + 2);
     return (bytes + 15) & ~(size_t)15;
+}
+
+inline void fit_fill_layout(FitArgs& a, int TW) {
+    const int G = a.G;
+    a.team_bytes = (int)fit_team_smem_bytes(a.cap, G, TW);
+    a.off_tot = (int)((kFitFixedDoubles + fit_scratch_doubles(G, TW)) * 8);
+    a.off_asm = a.off_tot + (G + 4) * 8;
+    a.off_dps = a.off_asm + G * 8;
+    a.off_goff = a.off_dps + G * 8;
+    a.off_slab = (int)fit_team_header_bytes(G, TW);
+    a.off_gid = a.off_slab + (a.cap + 2) * 8;
 }
 
 // shared-memory tables, addressed through the 32-bit shared window
@@ -362,8 +376,8 @@ __device__ __forceinline__ double team_colsum(const double* scratch, int R, int 
         }
     }
     double t = t0 + t1;
-    if (PARTS >= 2) t += __shfl_xor_sync(kFull, t, RPP);
-    if (PARTS >= 4) t += __shfl_xor_sync(kFull, t, 2 * RPP);
+    if (PARTS >= 2) t += shfl_xor_f64(t, RPP);
+    if (PARTS >= 4) t += shfl_xor_f64(t, 2 * RPP);
     return t;
 }
 // sum over the columns c < G of the per-lane column totals of team_colsum (every lane gets it)
@@ -372,7 +386,7 @@ __device__ __forceinline__ double colsum_first(double t, int G, int lane) {
     constexpr int RPP = 32 / PARTS;
     double v = (lane % RPP < G) ? t : 0.0;
 #pragma unroll
-    for (int m = RPP / 2; m > 0; m >>= 1) v += __shfl_xor_sync(kFull, v, m);
+    for (int m = RPP / 2; m > 0; m >>= 1) v += shfl_xor_f64(v, m);
     return v;
 }
 
@@ -394,18 +408,18 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
     tab.e2 = smem_u32(tab_e2);
     tab.lg = smem_u32(tab_lg) - (0x3ff00000u >> 13) * 16u;
 
-    unsigned char* wbase = smem_raw + kFitTableBytes + (size_t)team * fit_team_smem_bytes(a.cap, G, TW);
+    unsigned char* wbase = smem_raw + kFitTableBytes + team * a.team_bytes;
     double* sc = reinterpret_cast<double*>(wbase);
     double* bc = sc + 8;
     double* pc = bc + 8;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(pc + 8);
     double* scratch = pc + 10;
-    double* tot = scratch + fit_scratch_doubles(G, TW);
-    double* Asm = tot + G + 4;
-    double* dps = Asm + G;
-    int* goff = reinterpret_cast<int*>(dps + G);
-    double* slab = reinterpret_cast<double*>(wbase + fit_team_header_bytes(G, TW));
-    unsigned char* gid = reinterpret_cast<unsigned char*>(slab + a.cap + 2);
+    double* tot = reinterpret_cast<double*>(wbase + a.off_tot);
+    double* Asm = reinterpret_cast<double*>(wbase + a.off_asm);
+    double* dps = reinterpret_cast<double*>(wbase + a.off_dps);
+    int* goff = reinterpret_cast<int*>(wbase + a.off_goff);
+    double* slab = reinterpret_cast<double*>(wbase + a.off_slab);
+    unsigned char* gid = wbase + a.off_gid;
 
     if (tid == 0) {
         mbar_init(mbar, 1);
@@ -495,7 +509,7 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
                 }
             }
             Kconst = warp_sum(kpart);
-            lga0 = __shfl_sync(kFull, lga0, G & 31);
+            lga0 = shfl_f64(lga0, G & 31);
             prior_gamma = a0 * xlog(b0) - lga0;  // a0 ln b0 - lgamma(a0)   (gmm.py:334)
         }
 
@@ -667,7 +681,7 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
                     double ps, lg;
                     psi_lgamma_shifted(z, lz, q * den, num * (q * z), &ps, &lg);
                     lg -= lden;
-                    const double pso = __shfl_xor_sync(kFull, ps, 1);
+                    const double pso = shfl_xor_f64(ps, 1);
                     if (role == 0) {
                         if (kpar) dps[s >> 1] = ps - pso;  // psi(c_g1) - psi(c_g0)  (gmm.py:283-284)
                         if (counted) e_loc += lg;          // + sum_k lgamma(c_gk)
@@ -711,9 +725,9 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
                     // coefficients of d_n = A_g + y'(B + C y'): every term is (component 1) - (component 0)
                     const double u = tb * c.mp;
                     const double wq = lt - c.il - u * c.mp;
-                    const double uo = __shfl_xor_sync(kFull, u, 1);
-                    const double tbo = __shfl_xor_sync(kFull, tb, 1);
-                    const double wo = __shfl_xor_sync(kFull, wq, 1);
+                    const double uo = shfl_xor_f64(u, 1);
+                    const double tbo = shfl_xor_f64(tb, 1);
+                    const double wo = shfl_xor_f64(wq, 1);
                     B = kpar ? (u - uo) : (uo - u);  // the same value in every lane
                     C = -0.5 * (kpar ? (tb - tbo) : (tbo - tb));
                     const double base = 0.5 * (kpar ? (wq - wo) : (wo - wq));

@@ -27,9 +27,21 @@ constexpr unsigned kFull = 0xffffffffu;
 // ------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------
+// shuffles of a double through the 32-bit intrinsics (the toolkit's double overloads split and rejoin the value
+// with volatile asm, which costs two extra moves per shuffle in SASS)
+__device__ __forceinline__ double shfl_xor_f64(double v, int m) {
+    const int lo = __shfl_xor_sync(kFull, __double2loint(v), m);
+    const int hi = __shfl_xor_sync(kFull, __double2hiint(v), m);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+    const int lo = __shfl_sync(kFull, __double2loint(v), src);
+    const int hi = __shfl_sync(kFull, __double2hiint(v), src);
+    return __hiloint2double(hi, lo);
+}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(kFull, v, m);
+    for (int m = 16; m > 0; m >>= 1) v += shfl_xor_f64(v, m);
     return v;
 }
 __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
