@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -98,6 +99,8 @@ int prepare_kernel(Geometry* g) {
 }
 
 constexpr int kFitWarpsDefault = 28;
+constexpr size_t kSmemPerSm = 228u << 10;
+thread_local int g_pipe_ctas = 0;  // > 1 while fit_host_impl launches its chunks (see fit_geometry)
 
 int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -118,7 +121,22 @@ int fit_geometry(int G, int cap_reads, int tw, Geometry* g) {
         return fail(XPB200_EINVAL, "a position has more reads than one CTA's shared memory holds (max_reads=" +
                                        std::to_string(cap_reads) + ")");
     int teams = (int)((kMaxSmemPerCta - xpk::kFitTableBytes) / per_team);
-    if (tw == 1) {
+    const int K = g_pipe_ctas;
+    int t_pipe = 0;
+    if (tw == 1 && K > 1) {
+        // chunked host pipeline: K small CTAs per SM instead of one large one.  A CTA leaves when its slowest warp
+        // is done, so small CTAs hand an SM over to the next chunk's launch piecemeal instead of idling through
+        // the drain of 28 warps; what the launch leaves free of an SM (registers, shared memory) lets the next
+        // chunk's prefilter / worklist launches run beside it.
+        const size_t per_cta = kSmemPerSm / K - 1024;  // 1 KB per resident CTA is reserved by the system
+        if (per_cta > xpk::kFitTableBytes + per_team)
+            t_pipe = std::min((int)((per_cta - xpk::kFitTableBytes) / per_team), std::max(1, kFitWarpsDefault / K));
+    }
+    if (t_pipe >= 1) {
+        teams = t_pipe;
+        const int total = teams * K;
+        g->maxt = total <= 20 ? 640 : total <= 24 ? 768 : 896;
+    } else if (tw == 1) {
         teams = std::min(teams, std::max(1, env_int("XPB200_FIT_WARPS", kFitWarpsDefault)));
         teams = std::min(teams, 32);
         g->maxt = teams <= 20 ? 640 : teams <= 24 ? 768 : teams <= 28 ? 896 : 1024;
@@ -307,6 +325,7 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
 namespace {
 constexpr int kMaxChunks = 64;
 constexpr size_t kChunkBytes = 112u << 20;
+constexpr int kChunkGrowthPct = 150;
 
 constexpr int kComputeStreams = 3;
 constexpr int kPackWarps = 2048;  // warps of the row-compaction launches of one chunk
@@ -315,8 +334,10 @@ struct DevCache {
     int device = -1;
     cudaStream_t s_in = nullptr, s_c[kComputeStreams] = {nullptr, nullptr, nullptr}, s_out = nullptr;
     cudaEvent_t e_in[kMaxChunks], e_done[kMaxChunks];
+    cudaEvent_t t_0 = nullptr, t_in[kMaxChunks], t_start[kMaxChunks], t_done[kMaxChunks];  // XPB200_TRACE=1 only
     void* buf = nullptr;
     size_t cap = 0;
+    long calls = 0;
 };
 std::mutex g_cache_mu;
 std::vector<DevCache*> g_cache;
@@ -374,8 +395,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     const int FW = xpc::fit_width(G), SW = xpc::stats_width(G, C);
 
     // chunk boundaries (positions), cut where the read offsets cross the chunk targets.  The first chunks are
-    // small (1/8, 1/4, 1/2 of a full chunk) so the SMs start early, and so is the last one, whose result copy
-    // is the only one nothing overlaps with.
+    // small so the SMs start early; a remainder of less than a quarter chunk joins the last one.
     const int64_t* roff = b->read_off;
     const size_t chunk_bytes = (size_t)std::max(1, env_int("XPB200_CHUNK_MB", (int)(kChunkBytes >> 20))) << 20;
     const size_t total_bytes = (size_t)b->n_reads * eb;
@@ -383,18 +403,15 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     {
         std::vector<size_t> ends;  // byte targets of the chunk ends
         size_t pos = 0;
-        const size_t ramp[3] = {chunk_bytes / 8, chunk_bytes / 4, chunk_bytes / 2};
-        const size_t tail = chunk_bytes / 4;
-        for (int i = 0; i < 3 && total_bytes > 2 * chunk_bytes && pos + ramp[i] + tail < total_bytes; ++i) {
-            pos += ramp[i];
+        // sizes grow by kChunkGrowth from an eighth of a full chunk: the copy is only ~1.2x faster than the fit, so
+        // a chunk that is much larger than its predecessor would leave the SMs waiting for it to arrive
+        size_t sz = std::max<size_t>(chunk_bytes / 8, 1u << 20);
+        const double growth = std::max(1.0, env_int("XPB200_CHUNK_GROWTH_PCT", kChunkGrowthPct) / 100.0);
+        while (pos + sz + sz / 4 < total_bytes && (int)ends.size() < kMaxChunks - 2) {
+            pos += sz;
             ends.push_back(pos);
+            sz = std::min(chunk_bytes, (size_t)((double)sz * growth));
         }
-        const size_t last_start = (total_bytes > 2 * chunk_bytes) ? total_bytes - tail : total_bytes;
-        while (pos + chunk_bytes < last_start && (int)ends.size() < kMaxChunks - 2) {
-            pos += chunk_bytes;
-            ends.push_back(pos);
-        }
-        if (last_start < total_bytes && pos < last_start) ends.push_back(last_start);
         for (size_t e : ends) {
             const int64_t target = (int64_t)(e / eb);
             int p = (int)(std::lower_bound(roff, roff + P + 1, target) - roff);
@@ -404,7 +421,20 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         cut.push_back(P);
     }
     const int nchunks = (int)cut.size() - 1;
-    const int n_streams = std::min(kComputeStreams, std::max(1, env_int("XPB200_STREAMS", 2)));
+    const bool nocopy = env_int("XPB200_DEBUG_NOCOPY", 0) != 0;
+    ++dc->calls;
+    const bool trace = env_int("XPB200_TRACE", 0) != 0;  // timed events per chunk, printed to stderr
+    if (trace && !dc->t_0) {
+        CK(cudaEventCreate(&dc->t_0));
+        for (int i = 0; i < kMaxChunks; ++i) {
+            CK(cudaEventCreate(&dc->t_in[i]));
+            CK(cudaEventCreate(&dc->t_start[i]));
+            CK(cudaEventCreate(&dc->t_done[i]));
+        }
+    }
+    const auto host_t0 = std::chrono::steady_clock::now();
+    const int pipe_ctas = std::max(1, env_int("XPB200_PIPE_CTAS", 1));
+    const int n_streams = std::min(kComputeStreams, std::max(1, env_int("XPB200_STREAMS", 3)));
 
     // device layout
     size_t o = 0;
@@ -456,6 +486,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     uint32_t* d_cnt = (uint32_t*)(d + o_cnt);
     double* d_rows = (double*)(d + o_rows);
 
+    if (trace) CK(cudaEventRecord(dc->t_0, dc->s_in));
     CK(cudaMemcpyAsync(d + o_gc, b->grp_cond, (size_t)G * 4, cudaMemcpyDefault, dc->s_in));
     CK(cudaMemsetAsync(d_nf, 0, (size_t)kMaxChunks * 4, dc->s_in));
     CK(cudaMemsetAsync(d_nr, 0, (size_t)kMaxChunks * 4, dc->s_in));
@@ -464,6 +495,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         if (pc == 0) continue;
         const int64_t r0 = roff[p0], r1 = roff[p1];
         // copy-in
+        if (!(nocopy && dc->calls > 1))  // experiment: reuse the reads a previous identical call left on the device
         CK(cudaMemcpyAsync(d_y + (size_t)r0 * eb, (const char*)b->y + (size_t)r0 * eb, (size_t)(r1 - r0) * eb,
                            cudaMemcpyDefault, dc->s_in));
         CK(cudaMemcpyAsync(d_off + p0, roff + p0, (size_t)(pc + 1) * 8, cudaMemcpyDefault, dc->s_in));
@@ -471,9 +503,11 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         CK(cudaMemcpyAsync(d_km + p0, b->kmer_mean + p0, (size_t)pc * 8, cudaMemcpyDefault, dc->s_in));
         CK(cudaMemcpyAsync(d_ks + p0, b->kmer_std + p0, (size_t)pc * 8, cudaMemcpyDefault, dc->s_in));
         CK(cudaEventRecord(dc->e_in[c], dc->s_in));
+        if (trace) CK(cudaEventRecord(dc->t_in[c], dc->s_in));
         // compute
         cudaStream_t sc = dc->s_c[c % n_streams];
         CK(cudaStreamWaitEvent(sc, dc->e_in[c], 0));
+        if (trace) CK(cudaEventRecord(dc->t_start[c], sc));
         xpb200_batch db = *b;
         db.n_positions = pc;
         db.n_reads = r1 - r0;
@@ -486,8 +520,10 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         CK(cudaMemsetAsync(dr.n_iter, 0, (size_t)pc * 4, sc));
         CK(cudaMemsetAsync(dr.fit, 0xFF, (size_t)pc * FW * 8, sc));
         CK(cudaMemsetAsync(dr.stats, 0xFF, (size_t)pc * SW * 8, sc));
-        if (int rc = xpb200_fit_device(&db, m, &dr, d + o_ws[c], xpb200_workspace_bytes(pc), d_nf + c, sc))
-            return rc;
+        g_pipe_ctas = (nchunks > 1) ? pipe_ctas : 0;
+        const int rc_fit = xpb200_fit_device(&db, m, &dr, d + o_ws[c], xpb200_workspace_bytes(pc), d_nf + c, sc);
+        g_pipe_ctas = 0;
+        if (rc_fit) return rc_fit;
         if (rows) {  // compact the table's rows of this chunk
             xpk::PackRowsArgs pa;
             pa.status = dr.status; pa.n_iter = dr.n_iter; pa.pval = dr.pval; pa.fit = dr.fit; pa.stats = dr.stats;
@@ -504,6 +540,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
             CK(cudaGetLastError());
         }
         CK(cudaEventRecord(dc->e_done[c], sc));
+        if (trace) CK(cudaEventRecord(dc->t_done[c], sc));
         if (rows) continue;  // the rows are fetched below, once their counts are known
         // copy-out
         CK(cudaStreamWaitEvent(dc->s_out, dc->e_done[c], 0));
@@ -550,6 +587,19 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     uint32_t total = 0;
     for (int c = 0; c < nchunks; ++c) total += nf[c];
     if (n_fitted) *n_fitted = total;
+    if (trace) {
+        const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+        fprintf(stderr, "[xpb200 trace] %d chunks, host %.3f ms\n", nchunks, host_ms);
+        for (int c = 0; c < nchunks; ++c) {
+            if (cut[c + 1] == cut[c]) continue;
+            float a = 0, s2 = 0, e = 0;
+            cudaEventElapsedTime(&a, dc->t_0, dc->t_in[c]);
+            cudaEventElapsedTime(&s2, dc->t_0, dc->t_start[c]);
+            cudaEventElapsedTime(&e, dc->t_0, dc->t_done[c]);
+            fprintf(stderr, "[xpb200 trace] chunk %2d: %8d positions %7.1f MB  copied %7.3f  start %7.3f  done %7.3f ms\n", c,
+                    cut[c + 1] - cut[c], (double)(roff[cut[c + 1]] - roff[cut[c]]) * eb / 1048576.0, a, s2, e);
+        }
+    }
     return 0;
 }
 }  // namespace
