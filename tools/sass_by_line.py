@@ -7,7 +7,7 @@ import subprocess
 import sys
 import tempfile
 
-lib = os.path.join(os.path.dirname(__file__), "..", "xpore_b200", "libxpore_b200.so")
+lib = os.environ.get("XPLIB") or os.path.join(os.path.dirname(__file__), "..", "xpore_b200", "libxpore_b200.so")
 kern = sys.argv[1]
 lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (0, 0)
 fname = sys.argv[4] if len(sys.argv) > 4 else "xp_fit.cuh"

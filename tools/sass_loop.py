@@ -8,7 +8,7 @@ import sys
 import tempfile
 
 kern = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "xp_fit_kernelILi1ELi896"
-lib = os.path.join(os.path.dirname(__file__), "..", "xpore_b200", "libxpore_b200.so")
+lib = os.environ.get("XPLIB") or os.path.join(os.path.dirname(__file__), "..", "xpore_b200", "libxpore_b200.so")
 with tempfile.TemporaryDirectory() as td:
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=td, capture_output=True)
     txt = []
