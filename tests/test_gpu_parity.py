@@ -179,6 +179,67 @@ def test_encoded_reads_bit_identical(torch_cuda, shift, expect):
     assert 50 < ref.n_fitted < 700
 
 
+def _permute_slots(batch, perm):
+    """The same batch with its group slots in the order `perm` (reads of a position reordered accordingly)."""
+    from dataclasses import replace
+    from xpore_b200.batch import Batch, Layout
+    lay = batch.layout
+    assert not lay.pooling
+    new_lay = Layout(lay.condition_names, [lay.run_names[j] for j in perm], [lay.run_cond[j] for j in perm], False)
+    P, G = batch.grp_len.shape
+    y = np.empty_like(batch.y)
+    o = 0
+    for p in range(P):
+        starts = batch.read_off[p] + np.concatenate([[0], np.cumsum(batch.grp_len[p])[:-1]])
+        for j in perm:
+            n = batch.grp_len[p, j]
+            y[o:o + n] = batch.y[starts[j]:starts[j] + n]
+            o += n
+    return Batch(new_lay, y, batch.read_off.copy(), np.ascontiguousarray(batch.grp_len[:, perm]), batch.kmer_mean.copy(),
+                 batch.kmer_std.copy())
+
+
+def _drop_runs(batch, drops):
+    """Remove the reads of run j at position p for every (p, j) in drops (in place: y, read_off, grp_len)."""
+    P, G = batch.grp_len.shape
+    pieces, glen = [], batch.grp_len.copy()
+    dropped = set(drops)
+    for p in range(P):
+        o = batch.read_off[p]
+        for j in range(G):
+            n = batch.grp_len[p, j]
+            if (p, j) in dropped:
+                glen[p, j] = 0
+            else:
+                pieces.append(batch.y[o:o + n])
+            o += n
+    batch.y = np.ascontiguousarray(np.concatenate(pieces))
+    batch.grp_len = glen
+    batch.read_off = np.concatenate([[0], np.cumsum(glen.sum(axis=1))]).astype(np.int64)
+    return batch.validate()
+
+
+@pytest.mark.parametrize("perm", [[2, 3, 4, 0, 1], [0, 2, 1, 3, 4], [4, 0, 3, 1, 2]])
+def test_prefilter_slot_orders(torch_cuda, perm):
+    """The u16 prefilter keeps exact integer sums, so its p-values must not depend on the order of the group slots:
+    condition blocks swapped (prefix = the higher condition: masked streaming path) and conditions interleaved
+    (group-walk path) against the builder's order, bit for bit; the synthetic batch has absent runs and
+    one-condition positions."""
+    spec = Spec({"KO": 2, "WT": 3}, reads_lo=1, reads_hi=60, f_mod=0.4, seed=43,
+                method={"prefiltering": {"method": "t-test", "threshold": 0.2}})
+    base = make_batch(spec, KmerModel.load(), n_positions=600)
+    _drop_runs(base, [(p, j) for p in range(0, 600, 37) for j in ((0, 1) if p % 2 else (2, 3, 4))])  # one condition left
+    method = xf.Method.from_dict(spec.method)
+    assert base.encode_reads() == 2
+    ref = xf.fit_batch(base, method)
+    other = _permute_slots(base, perm)
+    assert other.encode_reads() == 2
+    res = xf.fit_batch(other, method)
+    np.testing.assert_array_equal(res.pval, ref.pval)
+    np.testing.assert_array_equal(res.status & 1, ref.status & 1)
+    assert np.isnan(ref.pval).sum() > 0 and (~np.isnan(ref.pval)).sum() > 400  # one-condition positions exist
+
+
 def test_empty_and_tiny_batches(torch_cuda):
     spec = Spec({"KO": 2, "WT": 2}, reads_lo=15, reads_hi=16, seed=3)
     b0 = make_batch(spec, KmerModel.load(), n_positions=0) if False else None

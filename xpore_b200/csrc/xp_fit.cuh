@@ -728,9 +728,12 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
                     const double uo = shfl_xor_f64(u, 1);
                     const double tbo = shfl_xor_f64(tb, 1);
                     const double wo = shfl_xor_f64(wq, 1);
-                    B = kpar ? (u - uo) : (uo - u);  // the same value in every lane
-                    C = -0.5 * (kpar ? (tb - tbo) : (tbo - tb));
-                    const double base = 0.5 * (kpar ? (wq - wo) : (wo - wq));
+                    // (component 1) - (component 0) in every lane: the even lanes flip the sign of own - other
+                    const int flip = kpar ? 0 : (int)0x80000000;
+                    const double du = u - uo, dt = tb - tbo, dw = wq - wo;
+                    B = __hiloint2double(__double2hiint(du) ^ flip, __double2loint(du));
+                    C = -0.5 * __hiloint2double(__double2hiint(dt) ^ flip, __double2loint(dt));
+                    const double base = 0.5 * __hiloint2double(__double2hiint(dw) ^ flip, __double2loint(dw));
                     if (lane < G) Asm[lane] = dps[lane] + base;
                     if (G > 32 && lane + 32 < G) Asm[lane + 32] = dps[lane + 32] + base;  // G <= kMaxGroups = 64
                     if (lane == 0) {

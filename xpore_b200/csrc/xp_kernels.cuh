@@ -162,12 +162,25 @@ constexpr int kPfIntMaxReads = 32767;
 // U16X: the batch is u16-encoded and no position has more than kPfIntMaxReads reads (the host checks
 // max_reads), so every position takes the exact-integer path and the FP accumulation is compiled out.
 template <int WARPS, bool U16X>
-__global__ void __launch_bounds__(WARPS * 32) xp_prefilter_kernel(PrefilterArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, 6) xp_prefilter_kernel(PrefilterArgs a) {
     __shared__ int s_cond[kMaxGroups];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = a.G;
     for (int g = threadIdx.x; g < G; g += blockDim.x) s_cond[g] = a.grp_cond[g];
     __syncthreads();
+    // Group slots blocked by condition (every condition's slots are adjacent - the batch builders emit the runs
+    // condition by condition): at a position with exactly two conditions present the reads of the condition whose
+    // block comes first are a prefix of the position, and the streaming loop needs no group walk.
+    bool cond_sorted = true;
+    {
+        unsigned seen = 1u << s_cond[0];
+        for (int g = 1; g < G; ++g) {
+            if (s_cond[g] != s_cond[g - 1]) {
+                cond_sorted = cond_sorted && !((seen >> s_cond[g]) & 1u);
+                seen |= 1u << s_cond[g];
+            }
+        }
+    }
     const int tile = blockIdx.x * WARPS + warp;
     const int p0 = tile * 32;
     if (p0 >= a.P) return;
@@ -216,18 +229,48 @@ __global__ void __launch_bounds__(WARPS * 32) xp_prefilter_kernel(PrefilterArgs 
                 // moments depend neither on the read encoding nor on where the position sits in the
                 // buffer).
                 bool side_a = (s_cond[0] == ca);  // side of the current group; looked up only at a boundary
-                auto addq = [&](unsigned q, int i) {  // read i of the position, raw integer
-                    while (i >= gend) {
-                        ++g;
-                        gend += glen[g];
+                // Integer sums are exact, so their order is free: a lane sums the reads of its current run inside one
+                // group (one add and one 64-bit multiply-add per read) and moves the run's sums to the group's side
+                // when it crosses into another group.  Counts come from the group lengths.
+                unsigned run1 = 0u, tot1 = 0u;  // cond_sorted: run = the prefix condition's sums, tot = the sums of all reads
+                unsigned long long run2 = 0ull, tot2 = 0ull;
+                // cond_sorted: the first `split` reads belong to the condition of the first present slot (side a or b)
+                int split = 0, n_a = 0;
+                bool prefix_a = true;
+                if (U16X) {
+                    int cfirst = -1;
+                    for (int gg = 0; gg < G; ++gg) {
+                        const int len = glen[gg];
+                        if (len > 0 && cfirst < 0) cfirst = s_cond[gg];
+                        if (s_cond[gg] == cfirst) split += len;
+                        if (s_cond[gg] == ca) n_a += len;
+                    }
+                    prefix_a = (cfirst == ca);
+                }
+                auto flush = [&]() {
+                    if (side_a) {
+                        mi.s1a += run1;
+                        mi.s2a += run2;
+                    } else {
+                        mi.s1b += run1;
+                        mi.s2b += run2;
+                    }
+                    run1 = 0u;
+                    run2 = 0ull;
+                };
+                auto advance = [&](int i) {  // make the current group the one holding read i
+                    if (i >= gend) {
+                        flush();
+                        do {
+                            ++g;
+                            gend += glen[g];
+                        } while (i >= gend);
                         side_a = (s_cond[g] == ca);
                     }
-                    const unsigned long long qq = (unsigned long long)q * q;
-                    mi.s1a += side_a ? q : 0u;
-                    mi.s1b += side_a ? 0u : q;
-                    mi.s2a += side_a ? qq : 0ull;
-                    mi.s2b += side_a ? 0ull : qq;
-                    mi.na += side_a ? 1 : 0;
+                };
+                auto addq = [&](unsigned q) {
+                    run1 += q;
+                    run2 += (unsigned long long)q * q;
                 };
                 exact = U16X;
                 if (U16X || a.y_format == kYU16) {
@@ -261,21 +304,56 @@ __global__ void __launch_bounds__(WARPS * 32) xp_prefilter_kernel(PrefilterArgs 
                         const unsigned x[4] = {__funnelshift_r(w0, w1, hs), __funnelshift_r(w1, w2, hs),
                                                __funnelshift_r(w2, w3, hs), __funnelshift_r(w3, w4, hs)};
                         const int ibase = bq << 3;
-                        if (U16X && ibase + 8 <= n) {  // a full block: no per-read bound checks
+                        if (U16X && cond_sorted) {
+                            // branch free: the block's valid reads (k < n - ibase) and those of the prefix condition
+                            // (k < split - ibase) are selected by masks on the packed words; integer sums of all
+                            // valid reads and of the prefix's reads, the other side follows by subtraction.
+                            const int b16 = max(min(n - ibase, 8), 0) * 16, a16 = max(min(split - ibase, 8), 0) * 16;
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) addq((x[k >> 1] >> ((k & 1) * 16)) & 0xffffu, ibase + k);
+                            for (int j = 0; j < 4; ++j) {
+                                const unsigned mv = __funnelshift_rc(0xffffffffu, 0u, max(32 * (j + 1) - b16, 0));
+                                const unsigned ma = __funnelshift_rc(0xffffffffu, 0u, max(32 * (j + 1) - a16, 0));
+                                const unsigned xv = x[j] & mv, xa = x[j] & ma;
+                                const unsigned vl = xv & 0xffffu, vh = xv >> 16, al = xa & 0xffffu, ah = xa >> 16;
+                                tot1 += vl + vh;
+                                tot2 += (unsigned long long)vl * vl;
+                                tot2 += (unsigned long long)vh * vh;
+                                run1 += al + ah;
+                                run2 += (unsigned long long)al * al;
+                                run2 += (unsigned long long)ah * ah;
+                            }
+                        } else if (U16X) {
+                            if (ibase < n) advance(ibase);
+                            if (ibase + 8 <= n && ibase + 8 <= gend) {  // a full block inside one group: no per-read checks
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) addq((x[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    if (ibase + k < n) {
+                                        advance(ibase + k);
+                                        addq((x[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
+                                    }
+                                }
+                            }
                         } else {
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
                                 const unsigned q = (x[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-                                if (ibase + k < n) {
-                                    if (U16X) addq(q, ibase + k);
-                                    else add(y_decode((double)q, a.y_scale, rscale), ibase + k);
-                                }
+                                if (ibase + k < n) add(y_decode((double)q, a.y_scale, rscale), ibase + k);
                             }
                         }
                         cur = nxt;
                         nxt = nn;
+                    }
+                    if (U16X) {
+                        if (cond_sorted) {  // run = the prefix condition's sums, tot = all reads
+                            mi.s1a = prefix_a ? run1 : tot1 - run1;
+                            mi.s2a = prefix_a ? run2 : tot2 - run2;
+                            mi.s1b = prefix_a ? tot1 - run1 : run1;
+                            mi.s2b = prefix_a ? tot2 - run2 : run2;
+                        } else flush();
+                        if (sl == 0) mi.na = n_a;  // the quad reduction below sums the lanes: lane 0 carries the count
                     }
                 } else {
                     for (int c = sl * 8; c < n; c += kPfLanes * 8) {  // 8 independent loads in flight
