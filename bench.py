@@ -226,6 +226,10 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    bound_cpus = 0
+    if world > 1:  # before any pinned allocation: host buffers next to this rank's GPU
+        from xpore_b200.dist import bind_to_gpu_cpus
+        bound_cpus = bind_to_gpu_cpus(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.build()
@@ -444,7 +448,7 @@ def main():
                        "smem_per_cta": info.smem_per_cta, "slab_reads": info.slab_reads,
                        "regs_per_thread": info.regs_per_thread},
             "cpu_baseline": cpu,
-            "host_cores": cores,
+            "host_cores": cores, "cpus_bound_to_gpu": bound_cpus,
         }
         print(json.dumps(line))
     if world > 1:

@@ -96,6 +96,8 @@ def diffmod(args, fit_fn=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
             if backend == "nccl":
                 torch.cuda.set_device(local_rank)
+                from .dist import bind_to_gpu_cpus
+                bind_to_gpu_cpus(local_rank)  # pinned buffers next to this rank's GPU
             dist.init_process_group(backend)
 
     out_table = os.path.join(paths["out_dir"], "diffmod.table")

@@ -27,6 +27,31 @@ def balanced_partition(cost: np.ndarray, world: int) -> list:
     return [np.arange(cuts[r], cuts[r + 1], dtype=np.int64) for r in range(world)]
 
 
+def bind_to_gpu_cpus(cuda_index: int) -> int:
+    """Pin this process to the CPUs NVML reports as local to the GPU (its NUMA node), so that pinned host
+    buffers allocated afterwards sit next to the GPU's PCIe root.  With one process per GPU and all ranks
+    copying at once, buffers on the far socket halve the host-to-device rate.  Best effort: returns the
+    number of CPUs bound to, 0 when NVML, the device or an allowed local CPU is missing (nothing changed)."""
+    import os
+    try:
+        import pynvml
+        import torch
+
+        pr = torch.cuda.get_device_properties(cuda_index)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1} & allowed
+        if not cpus or cpus == allowed:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:  # no NVML / no permission: leave the affinity alone
+        return 0
+
+
 def pack_records(status, n_iter, pval, fit, stats, index_offset: int = 0):
     """Compact float64 record matrix of the selected positions (torch tensors in, any device):
     columns = [global position index, status, n_iter, pval, fit..., stats...]."""
