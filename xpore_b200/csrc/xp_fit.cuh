@@ -393,7 +393,7 @@ __device__ __forceinline__ double colsum_first(double t, int G, int lane) {
 template <int TW, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // broadcast: warp-uniform for the compiler
     const int team = warp / TW, tw = warp % TW, tid = tw * 32 + lane;  // tid: thread index inside the team
     const bool leader = (tw == 0);
     const int G = a.G;
