@@ -57,3 +57,37 @@ def test_emulator_matches_reference(emul, golden_case):
     batch, method, _ = pack_case(golden_case["config_path"], exp["ids"])
     res = emul_fit_batch(emul, batch, xf.Method.from_dict(method))
     compare_with_golden(batch, res, method, exp, rtol_param=1e-8, rtol_p=1e-9)
+
+
+def test_closed_form_elbo_equals_the_nine_term_sum(emul):
+    """The kernels evaluate a component's ELBO share in closed form after the first sweep
+    (xp_core.cuh:elbo_component_closed).  Sweep by sweep the emulator's ELBO must equal the oracle's, which
+    adds the reference's nine terms (gmm.py:77-91) in the reference's order."""
+    import ctypes as C
+
+    from oracle import xpore_oracle as orc
+    from xpore_b200.kmer_model import KmerModel
+    from xpore_b200.synth import Spec, make_batch
+
+    spec = Spec({"KO": 2, "WT": 3}, reads_lo=5, reads_hi=80, f_mod=0.5, seed=11)
+    batch = make_batch(spec, KmerModel.load(), n_positions=60)
+    G = batch.layout.n_groups
+    checked = 0
+    for p in range(batch.n_positions):
+        y = np.ascontiguousarray(batch.y[batch.read_off[p]:batch.read_off[p + 1]])
+        gl = np.ascontiguousarray(batch.grp_len[p])
+        X = np.zeros((len(y), G), dtype=bool)
+        X[np.arange(len(y)), np.repeat(np.arange(G), gl)] = True
+        ref = orc.fit_position(y, X, batch.kmer_mean[p], batch.kmer_std[p], rng=np.random.RandomState(0), trace=True)
+        fit = np.empty(xf.fit_width(G))
+        elbos = np.full(500, np.nan)
+        nit, st = C.c_int(0), C.c_uint(0)
+        emul.emul_fit(len(y), y.ctypes.data, G, gl.ctypes.data, batch.kmer_mean[p], batch.kmer_std[p], 500, 1e-5, xf.Method().dirichlet_conc,
+                      fit.ctypes.data, C.byref(nit), C.byref(st), elbos.ctypes.data)
+        assert nit.value == ref["n_iterations"]
+        if st.value & xf.ELBO_DECREASED:
+            continue  # the reference breaks before recording the decreased value
+        want = np.array(ref["elbos"][1:] + [ref["elbo_last"]])  # ELBO after sweep 1, 2, ... (elbos[0] is the random start)
+        np.testing.assert_allclose(elbos[:nit.value], want, rtol=2e-12)
+        checked += nit.value
+    assert checked > 1000
