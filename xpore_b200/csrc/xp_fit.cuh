@@ -42,6 +42,9 @@
 #ifndef XP_FIT_NR
 #define XP_FIT_NR 2
 #endif
+#ifndef XP_FIT_NR_TEAM  // reads per lane and trip of the 4-warp teams (16 warps per SM: more chains per warp)
+#define XP_FIT_NR_TEAM 4
+#endif
 #ifndef XP_FIT_FLOOR
 #define XP_FIT_FLOOR 0
 #endif
@@ -760,7 +763,7 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
                 EConst K;
                 K.load();
                 unsigned pg = g_first;  // group of this thread's last read; accN goes to column pg on leaving it
-                constexpr int NR = XP_FIT_NR;   // adjacent reads per thread and trip
+                constexpr int NR = (TW > 1) ? XP_FIT_NR_TEAM : XP_FIT_NR;  // reads per thread and trip
                 const int nfull = n / (32 * NR);
 #define XP_READ(yy, gg)                              \
     {                                                \
