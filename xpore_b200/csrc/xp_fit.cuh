@@ -8,11 +8,12 @@
 // Per position:
 //   1. one TMA bulk copy (cp.async.bulk + mbarrier) lands the position's reads in the team's slab;
 //      they are decoded / centred on the k-mer mean in place and stay resident for all sweeps;
-//   2. initial locations by an exact MSD radix select (np.percentile, gmm.py:39-44);
+//   2. initial locations (np.percentile, gmm.py:39-44) by an exact radix select: on the integer codes of a u16
+//      batch before the decode (two 8-bit digits), on order-preserving 64-bit keys otherwise;
 //   3. sweeps.  The team leader (warp 0 of the team) runs the O(G) scalar phase — psi / lgamma of the
-//      2G+2 posterior parameters spread over lanes, ELBO from sufficient statistics, stopping rule
-//      (gmm.py:110-123), M-step — keeping component k in the lanes of parity k; all warps of the team
-//      run the E-step over their share of the resident reads (two reads per lane per trip).
+//      2G+2 posterior parameters spread over lanes, ELBO in closed form from sufficient statistics, stopping
+//      rule (gmm.py:110-123), M-step — keeping component k in the lanes of parity k; all warps of the team
+//      run the E-step over their share of the resident reads (two reads per lane per trip, four in 4-warp teams).
 //
 // E-step bookkeeping: only component 0 is accumulated per read (N_g0, S1_0, S2_0 and the entropy);
 // component 1 follows from the per-position totals because r_n1 = 1 - r_n0 (gmm.py:242):
@@ -20,22 +21,24 @@
 // The 256-entry 2^(j/256) table and the 129-entry {1/c, ln c} table live in shared memory (4 KB per CTA).
 //
 // CTA shared memory:  [ exp2 table 256 f64 | {1/c, ln c} table 129 double2 (+pad) | team 0 | team 1 | ... ]
-// team region (doubles unless noted; the fixed-size arrays come first so that their addresses are the team base
-// plus a constant, then the G-sized ones, then the 16-byte aligned slab, the scratch rows and gid):
-//   slab[cap+2]        centred reads y' (TMA destination; +2 = 16-byte alignment slack)
-//   scratch[(G+3) x (32 TW + 1)]  column c holds one double per thread of the team: its partial N_g0 of
-//                      group c < G, then S1_0, S2_0 and the entropy of the current sweep (odd column pitch: the
-//                      column sums read conflict free, and a thread's entry is scratch + tid + c * pitch);
-//                      doubles as the 256-bin select histogram before the first sweep
-//   tot[G+4]           row totals
-//   Asm[G]             per-group constant A_g of d_n, as used by the E-step of the current sweep
-//   dps[G]             psi(c_g1) - psi(c_g0) of the scalar phase in progress (becomes Asm only if another sweep follows,
-//                      so Asm / bc still describe the last E-step when the position is done: --save_models)
+// team region, in this order (doubles unless noted).  The fixed-size arrays and the scratch columns come first:
+// their addresses are the team base plus a constant; the offsets of the rest are kernel arguments (fit_fill_layout).
 //   sc[8]              psi(alpha_k), lgamma(alpha_k), ln beta_k, ln lambda_k published by their lanes
 //   bc[8]              leader -> team broadcast: B, C, continue flag, ticket, reduction slots
 //   pc[8]              per-position values the leader needs once per sweep (m0, a0, b0, the two ELBO constants,
 //                      sum y', sum y'^2, previous ELBO): parked here so they hold no registers during the E-step
-//   goff[G+1] (int), mbar (u64), gid[cap+2] (u8: group slot of every read)
+//   mbar (u64) + pad
+//   scratch[(G+3) x (32 TW + 1)]  column c holds one double per thread of the team: its partial N_g0 of
+//                      group c < G, then S1_0, S2_0 and the entropy of the current sweep (odd column pitch: the
+//                      column sums read conflict free, and a thread's entry is scratch + tid + c * pitch);
+//                      at least 2 KB: the two 256-bin select histograms live here before the first sweep
+//   tot[G+4]           column totals
+//   Asm[G]             per-group constant A_g of d_n, as used by the E-step of the current sweep
+//   dps[G]             psi(c_g1) - psi(c_g0) of the scalar phase in progress (becomes Asm only if another sweep follows,
+//                      so Asm / bc still describe the last E-step when the position is done: --save_models)
+//   goff[G+1] (int)    group offsets inside the position
+//   slab[cap+2]        16-byte aligned: centred reads y' (TMA destination; +2 = alignment slack)
+//   gid[cap+2] (u8)    group slot of every read
 #pragma once
 #include <cuda_runtime.h>
 
@@ -755,9 +758,9 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
             if (!go) break;
             first = false;
             // ---- E-step + component-0 moments: one pass over the resident reads ------------------
-            // A thread takes the adjacent reads 2j, 2j+1 (j = 32 trip + lane: one 16-byte load) of every
-            // full trip of 64 reads, then single reads of the tail, so the groups it meets never decrease;
-            // its N_g0 partial goes to scol[g] whenever the group changes.  The loop body is branch free.
+            // A thread takes the reads lane, lane + 32, ... of every full trip of 32 NR reads (one load each), then
+            // single reads of the tail, so the groups it meets never decrease; its N_g0 partial goes to the
+            // scratch column of the group it leaves.  The loop body is branch free.
             double accN = 0.0, S1 = 0.0, S2 = 0.0, Hh = 0.0;
             {
                 EConst K;
