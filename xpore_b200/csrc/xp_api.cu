@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstring>
 #include <chrono>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -53,6 +54,8 @@ struct Workspace {  // carved out of the caller's buffer
     unsigned int* ticket;
     uint32_t* n_large;
     unsigned int* ticket_large;
+    uint32_t* n_mid;
+    unsigned int* ticket_small;
     int32_t* worklist;
 };
 size_t ws_header_bytes() { return (size_t)(2 * xpk::kBuckets + 64) * 4; }
@@ -65,6 +68,8 @@ Workspace carve(void* ws) {
     w.ticket = u + 2 * xpk::kBuckets + 1;
     w.n_large = u + 2 * xpk::kBuckets + 2;
     w.ticket_large = u + 2 * xpk::kBuckets + 3;
+    w.n_mid = u + 2 * xpk::kBuckets + 4;
+    w.ticket_small = u + 2 * xpk::kBuckets + 5;
     w.worklist = reinterpret_cast<int32_t*>(u + 2 * xpk::kBuckets + 64);
     return w;
 }
@@ -158,6 +163,54 @@ int fit_geometry(int G, int cap_reads, int tw, Geometry* g) {
     } else rc = prepare_kernel<4, 512>(g);
     if (rc) return rc;
     if (g->ctas_per_sm < 1) return fail(XPB200_ECUDA, "fit kernel does not fit on an SM");
+    return 0;
+}
+
+// The class launches of one fit (4-warp teams, full-slab single-warp teams, small-slab single-warp teams) work on
+// disjoint positions.  On one stream each would wait for the stragglers of the one before; on side streams forked
+// from and joined back into the caller's stream their CTAs take over SMs as the earlier launch's CTAs leave.
+struct SideStreams {
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+};
+std::mutex g_side_mu;
+std::map<std::pair<int, cudaStream_t>, SideStreams*> g_side;
+int side_streams(cudaStream_t st, SideStreams** out) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    auto key = std::make_pair(dev, st);
+    auto it = g_side.find(key);
+    if (it == g_side.end()) {
+        auto* ss = new SideStreams();
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaStreamCreateWithFlags(&ss->s[i], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ss->join[i], cudaEventDisableTiming));
+        }
+        CK(cudaEventCreateWithFlags(&ss->fork, cudaEventDisableTiming));
+        it = g_side.emplace(key, ss).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+// Largest bucket boundary S of the worklist (xp_kernels.cuh:cost_bucket: 16 buckets per octave) such that a slab for
+// S - 1 reads lets a CTA hold the full number of single-warp teams; 0 when the launch for `max_reads` already
+// does (teams_now), or when no boundary of at least 64 reads qualifies.
+int small_class_split(int G, int max_reads, int teams_now) {
+    const int target = std::min(std::max(1, env_int("XPB200_FIT_WARPS", kFitWarpsDefault)), 32);
+    // Off by default: on c4 (20-5000 reads, log-uniform) the third launch cost more (8.2 ms) than its 28 instead of
+    // 19 warps per CTA gained (two classes on forked streams: 7.9 ms).  XPB200_SMALL_CLASS=1 turns it on.
+    if (teams_now >= target || !env_int("XPB200_SMALL_CLASS", 0)) return 0;
+    for (int e = 9; e >= 6; --e) {
+        for (int k = 15; k >= 0; --k) {
+            const int S = (1 << e) + k * (1 << (e - 4));
+            if (S > max_reads) continue;
+            const int cap = std::max(32, (S - 1 + 1 + 7) & ~7);
+            const size_t per_team = xpk::fit_team_smem_bytes(cap, G, 1);
+            if ((int)((kMaxSmemPerCta - xpk::kFitTableBytes) / per_team) >= target) return S;
+        }
+    }
     return 0;
 }
 
@@ -280,6 +333,15 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
     wa.n_work = ws.n_work; wa.worklist = ws.worklist; wa.n_large = ws.n_large;
     const bool two_class = b->max_reads >= kSplitReads;
     wa.split = two_class ? kSplitReads : 0;
+    // A third class when the single-warp slab sized for the longest position leaves fewer teams per CTA than the
+    // launch could hold: the positions below `split2` reads (a bucket boundary) get their own launch with a slab
+    // sized for them and the full number of teams - on coverage-skewed batches that is most positions.
+    const int tw1_reads = two_class ? kSplitReads - 1 : b->max_reads;
+    Geometry g;
+    if (int rc = fit_geometry(b->n_groups, tw1_reads, 1, &g)) return rc;
+    const int split2 = small_class_split(b->n_groups, tw1_reads, g.teams);
+    wa.n_mid = ws.n_mid;
+    wa.split2 = split2;
     const int wthreads = 256;
     const int wblocks = std::min((P + wthreads - 1) / wthreads, 1184);
     xpk::xp_worklist_count<<<wblocks, wthreads, 0, st>>>(wa);
@@ -298,16 +360,49 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
     fa.conc0 = m->dirichlet_conc;
     fa.lg_prior_w = xpm::xlgamma(2.0 * m->dirichlet_conc) - 2.0 * xpm::xlgamma(m->dirichlet_conc);
     fa.fit = r->fit; fa.n_iter = r->n_iter; fa.status = r->status; fa.coef = r->coef;
+    // class launches, longest positions first: the first on the caller's stream, the others on side streams
+    SideStreams* ss = nullptr;
+    const int n_class = 1 + (two_class ? 1 : 0) + (split2 ? 1 : 0);
+    if (n_class > 1) {
+        if (int rc = side_streams(st, &ss)) return rc;
+        CK(cudaEventRecord(ss->fork, st));
+    }
+    int k = 0;  // launches so far
+    auto class_stream = [&](int i) -> cudaStream_t { return i == 0 ? st : ss->s[i - 1]; };
+    auto begin_class = [&](int i) -> int {
+        if (i > 0) CK(cudaStreamWaitEvent(ss->s[i - 1], ss->fork, 0));
+        return 0;
+    };
+    auto end_class = [&](int i) -> int {
+        if (i > 0) {
+            CK(cudaEventRecord(ss->join[i - 1], ss->s[i - 1]));
+            CK(cudaStreamWaitEvent(st, ss->join[i - 1], 0));
+        }
+        return 0;
+    };
     if (two_class) {
         Geometry gl;
         if (int rc = fit_geometry(b->n_groups, b->max_reads, 4, &gl)) return rc;
         fa.cap = gl.cap; fa.w_begin = nullptr; fa.w_end = ws.n_large; fa.ticket = ws.ticket_large;
-        if (int rc = launch_fit(gl, fa, P, st)) return rc;
+        if (int rc = begin_class(k)) return rc;
+        if (int rc = launch_fit(gl, fa, P, class_stream(k))) return rc;
+        if (int rc = end_class(k)) return rc;
+        ++k;
     }
-    Geometry g;
-    if (int rc = fit_geometry(b->n_groups, two_class ? kSplitReads - 1 : b->max_reads, 1, &g)) return rc;
-    fa.cap = g.cap; fa.w_begin = two_class ? ws.n_large : nullptr; fa.w_end = ws.n_work; fa.ticket = ws.ticket;
-    if (int rc = launch_fit(g, fa, P, st)) return rc;
+    fa.cap = g.cap; fa.w_begin = two_class ? ws.n_large : nullptr; fa.w_end = split2 ? ws.n_mid : ws.n_work; fa.ticket = ws.ticket;
+    if (int rc = begin_class(k)) return rc;
+    if (int rc = launch_fit(g, fa, P, class_stream(k))) return rc;
+    if (int rc = end_class(k)) return rc;
+    ++k;
+    if (split2) {
+        Geometry gs;
+        if (int rc = fit_geometry(b->n_groups, split2 - 1, 1, &gs)) return rc;
+        fa.cap = gs.cap; fa.w_begin = ws.n_mid; fa.w_end = ws.n_work; fa.ticket = ws.ticket_small;
+        if (int rc = begin_class(k)) return rc;
+        if (int rc = launch_fit(gs, fa, P, class_stream(k))) return rc;
+        if (int rc = end_class(k)) return rc;
+        ++k;
+    }
 
     stage_mark(3, st);
     // K4 statistics
@@ -618,6 +713,17 @@ void xpb200_release(void) {
         delete c;
     }
     g_cache.clear();
+    std::lock_guard<std::mutex> lk2(g_side_mu);
+    for (auto& kv : g_side) {
+        cudaSetDevice(kv.first.first);
+        for (int i = 0; i < 2; ++i) {
+            if (kv.second->s[i]) cudaStreamDestroy(kv.second->s[i]);
+            if (kv.second->join[i]) cudaEventDestroy(kv.second->join[i]);
+        }
+        if (kv.second->fork) cudaEventDestroy(kv.second->fork);
+        delete kv.second;
+    }
+    g_side.clear();
 }
 
 int32_t xpb200_measure_fp64_peak(int32_t device, int32_t repeats, double* tflops) {

@@ -454,6 +454,8 @@ struct WorklistArgs {
     int32_t* worklist;   // [P]
     uint32_t* n_large;   // [1] entries of the worklist with at least `split` reads (they come first)
     int split;           // a bucket boundary (see cost_bucket), or 0: no large class
+    uint32_t* n_mid;     // [1] entries with at least `split2` reads (large ones included); = n_large when split2 = 0
+    int split2;          // a bucket boundary below `split`, or 0: no small class
 };
 
 __global__ void xp_worklist_count(WorklistArgs a) {
@@ -482,9 +484,12 @@ __global__ void xp_worklist_scan(WorklistArgs a) {  // <<<1, kBuckets>>>
     }
     a.cursor[t] = s[t] - a.hist[t];  // exclusive start
     if (t == kBuckets - 1) *a.n_work = s[t];
-    if (t == 0) *a.n_large = 0;
-    __syncthreads();
-    if (a.split > 0 && t == cost_bucket(a.split)) *a.n_large = s[t];  // buckets 0..t hold n >= split
+    // buckets 0..cost_bucket(x) hold the positions with n >= x when x is the first count of its bucket
+    const uint32_t nl = a.split > 0 ? s[cost_bucket(a.split)] : 0u;
+    if (t == 0) {
+        *a.n_large = nl;
+        *a.n_mid = a.split2 > 0 ? s[cost_bucket(a.split2)] : nl;
+    }
 }
 
 __global__ void xp_worklist_scatter(WorklistArgs a) {
