@@ -105,7 +105,9 @@ int32_t xpb200_stats_width(int32_t n_groups, int32_t n_conditions);
 size_t xpb200_workspace_bytes(int32_t n_positions);
 
 /* Whole path on DEVICE pointers: prefilter t-test -> worklist -> VB-EM fit -> statistics,
- * enqueued on `cuda_stream` (a cudaStream_t, may be NULL); does not synchronise.
+ * enqueued on `cuda_stream` (a cudaStream_t, may be NULL); does not synchronise.  When a batch has positions of
+ * 1024 reads or more, the two fit launches run on internal streams forked from and joined back into
+ * `cuda_stream`: everything the call enqueues is ordered before later work on `cuda_stream`, as with one stream.
  * `n_fitted_dev` (optional, device uint32) receives the number of selected positions. */
 int32_t xpb200_fit_device(const xpb200_batch* batch, const xpb200_method* method, const xpb200_result* result,
                           void* workspace, size_t workspace_bytes, uint32_t* n_fitted_dev, void* cuda_stream);
