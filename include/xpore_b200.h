@@ -44,6 +44,12 @@ extern "C" {
 #define XPB200_MOD_IS_1 32u       /* modified cluster = component 1 (io.py:277-282) */
 #define XPB200_HIGHER 64u         /* mod_assignment == "higher" (io.py:288) */
 #define XPB200_TTEST_VALID 128u   /* exactly two conditions present (statstest.py:20-21) */
+#define XPB200_NOT_FITTED 256u    /* selected but NOT fitted (n_iter = -1, record NaN): only when a device-pointer caller
+                                     understated batch.max_reads; the host entry points compute max_reads themselves */
+#define XPB200_NEAR_THRESHOLD 512u /* t-test p-value within 1e-9 (relative) of the prefilter threshold: the gate
+                                     `p < threshold` (diffmod.py:54) could fall either way under a different rounding of
+                                     the incomplete beta function; the decision taken is the one of THIS p-value, the bit
+                                     lets a caller re-check such positions in higher precision (none seen in 10^7 tests) */
 
 /* A CSR-packed ragged batch of positions (what io.load_data yields for many genes).
  * Reads of a position are contiguous, and within the position contiguous per group slot, in
@@ -105,9 +111,13 @@ int32_t xpb200_stats_width(int32_t n_groups, int32_t n_conditions);
 size_t xpb200_workspace_bytes(int32_t n_positions);
 
 /* Whole path on DEVICE pointers: prefilter t-test -> worklist -> VB-EM fit -> statistics,
- * enqueued on `cuda_stream` (a cudaStream_t, may be NULL); does not synchronise.  When a batch has positions of
- * 1024 reads or more, the two fit launches run on internal streams forked from and joined back into
- * `cuda_stream`: everything the call enqueues is ordered before later work on `cuda_stream`, as with one stream.
+ * enqueued on `cuda_stream` (a cudaStream_t, may be NULL); does not synchronise.  Positions are fitted by depth class:
+ * one warp per position below 1024 reads, a 4-warp team up to what one CTA's shared memory holds (~23 000 reads), a
+ * streaming CTA that re-reads the position from global memory in every sweep beyond that - there is no cap on the
+ * reads of a position (the reference has none, gmm.py:93-127).  With more than one class the launches run on internal
+ * streams forked from and joined back into `cuda_stream`: everything the call enqueues is ordered before later work
+ * on `cuda_stream`, as with one stream.  batch->max_reads must not be understated (a position deeper than stated is
+ * reported with XPB200_NOT_FITTED instead of being fitted).
  * `n_fitted_dev` (optional, device uint32) receives the number of selected positions. */
 int32_t xpb200_fit_device(const xpb200_batch* batch, const xpb200_method* method, const xpb200_result* result,
                           void* workspace, size_t workspace_bytes, uint32_t* n_fitted_dev, void* cuda_stream);
@@ -127,6 +137,17 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* batch, const xpb200_
  * copies the batch up in chunks like xpb200_fit_host, synchronises. */
 int32_t xpb200_fit_host_rows(int32_t device, const xpb200_batch* batch, const xpb200_method* method, double* rows,
                              int64_t capacity_rows, int64_t* n_rows, uint32_t* n_fitted);
+
+/* The same rows left on the DEVICE, without any host synchronisation - the per-rank step of a multi-GPU run, whose
+ * rows go on to the writer rank over NCCL (the reference appends rows from many processes under a file lock,
+ * scripts/diffmod.py:68-69).  Host buffers in (pinned: the copies are asynchronous; they must stay valid until the
+ * work completes); rows_dev[capacity_rows][4+FW+SW] and counts_dev[2] = {rows needed, positions fitted} are device
+ * memory.  Record column 0 is index_offset + position.  Rows beyond capacity_rows are dropped (counts_dev[0] still
+ * reports the number needed).  Everything is ordered after the work already enqueued on `cuda_stream`, and later work on
+ * `cuda_stream` is ordered after it; the call returns as soon as the work is enqueued. */
+int32_t xpb200_fit_host_rows_async(int32_t device, const xpb200_batch* batch, const xpb200_method* method,
+                                   double* rows_dev, int64_t capacity_rows, int64_t index_offset, uint32_t* counts_dev,
+                                   void* cuda_stream);
 
 /* Release the cached device buffers of xpb200_fit_host (all devices). */
 void xpb200_release(void);
@@ -152,11 +173,22 @@ int32_t xpb200_pack_records(const xpb200_result* result, int32_t n_positions, in
                             int32_t n_conditions, const void* workspace, int64_t index_offset, double* out,
                             int64_t capacity_rows, void* cuda_stream);
 
+/* Records (same layout) of the table's rows only - fitted AND past the row filter (io.py:363-367) - of the last
+ * xpb200_fit_device call whose results are in `result`, compacted in position order into out[capacity_rows, 4+FW+SW]
+ * (device); *n_rows_dev (device) = rows needed.  `workspace` is the fit's workspace (scratch).  Deterministic, no atomics. */
+int32_t xpb200_pack_rows(const xpb200_result* result, int32_t n_positions, int32_t n_groups, int32_t n_conditions,
+                         void* workspace, int64_t index_offset, double* out, int64_t capacity_rows,
+                         uint32_t* n_rows_dev, void* cuda_stream);
+
 /* Launch geometry the fit kernel would use for this batch (for reporting): */
 typedef struct xpb200_launch_info {
     int32_t sm_count, ctas_per_sm, warps_per_cta, smem_per_cta, slab_reads, regs_per_thread;
 } xpb200_launch_info;
 int32_t xpb200_fit_launch_info(int32_t device, int32_t n_groups, int32_t max_reads, xpb200_launch_info* out);
+
+/* Positions with at least this many reads are fitted by the streaming class (reads re-read from global memory in
+ * every sweep) instead of being held in shared memory; depends on the number of group slots only. */
+int32_t xpb200_deep_split(int32_t n_groups);
 
 /* Kernel launches issued by this library in the calling thread since load (bench.py's gpu_launches). */
 uint64_t xpb200_launch_count(void);

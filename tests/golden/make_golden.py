@@ -152,6 +152,11 @@ CASES = {
     "g6_ragged_pooled": dict(spec=Spec({"KO": 2, "WT": 3}, n_genes=2, pos_per_gene=20, reads_lo=8, reads_hi=40,
                                        f_mod=0.5, seed=13, method={"pooling": True},
                                        criteria={"readcount_min": 40, "readcount_max": 90})),
+    # BASELINE c5 shape: 6 conditions x 3 replicates (15 pairwise + 6 one-vs-all z-tests, 63 test columns); the
+    # t-test prefilter is configured and yields NaN (more than two conditions) => every position is fitted
+    "g7_six_conditions": dict(spec=Spec({c: 3 for c in ["A549", "HEK293T", "HEPG2", "K562", "KO", "MCF7"]},
+                                        n_genes=1, pos_per_gene=36, reads_lo=20, reads_hi=60, f_mod=0.6, seed=14,
+                                        method={"prefiltering": {"method": "t-test", "threshold": 0.1}})),
 }
 
 
@@ -186,7 +191,10 @@ def mutate_g5(root, spec):
 
 
 def main():
+    only = set(sys.argv[1:])
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         spec = case["spec"]
         root = os.path.join(HERE, name)
         if os.path.isdir(root):

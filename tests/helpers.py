@@ -114,27 +114,16 @@ def compare_with_golden(batch, res, method, expected, rtol_param=1e-5, rtol_p=1e
     exp_rows = {tuple(r[:3]): r for r in expected["rows"]}
     assert set(rows) == set(exp_rows)
     hdr = expected["header"]
-    knife = 0
+    knife, bound = 0, 0
+    index_of = {k: i for i, k in enumerate(keys)}
     for k, r in rows.items():
-        e = exp_rows[k]
-        assert len(r) == len(e)
-        alt = _knife_edge_alternatives(hdr, e, lay)
-        for name, a, b in zip(hdr[3:], r[3:], e[3:]):
-            if b is None or isinstance(a, str):
-                assert a == b, (k, name, a, b)
-                continue
-            b = _num(b)
-            if np.isnan(b):
-                assert np.isnan(a), (k, name)
-                continue
-            tol = rtol_p if (name.startswith("pval") or name == pm) else rtol_param
-            if np.isclose(a, b, rtol=tol, atol=1e-300):
-                continue
-            # z-test columns: the reference's n = round(mean coverage) sits on x.5 and its rounding
-            # direction is sub-ulp noise (see xp_core.cuh cond_summary) - accept the other direction
-            cands = alt.get(name, [])
-            assert any(np.isclose(a, c, rtol=tol, atol=1e-300) for c in cands), (k, name, a, b, cands)
-            knife += 1
+        # z-test columns: where the reference's n = round(mean coverage) sits on x.5 its rounding direction is sub-ulp
+        # noise (see xp_core.cuh cond_summary) - the other direction is accepted there, counted, and bounded by the
+        # number of cells for which that can legitimately happen
+        knife += compare_row_cells(k, hdr, r, exp_rows[k], lay, pm, rtol_param, rtol_p)
+        bound += half_integer_tests(batch, index_of[k])
+    assert knife <= bound, (knife, bound)
+    print("knife-edge z-test cells accepted: %d (cells on a half-integer mean read count: %d, rows: %d)" % (knife, bound, len(rows)))
     return iters_diff, knife
 
 
@@ -276,21 +265,97 @@ def read_table(path):
     return header, rows
 
 
-def compare_tables(got_rows, exp_rows, header, layout, prefilter_method, rtol_param=1e-5, rtol_p=1e-4):
+def compare_row_cells(key, header, got, exp, layout, prefilter_method, rtol_param=1e-5, rtol_p=1e-4):
+    """One table row against the reference's / the oracle's: north-star tolerances cell by cell.  Returns the
+    number of z-test cells that only agree with the OTHER rounding of a mean coverage lying on x.5 (SURVEY.md Q8:
+    there the reference's own direction is decided by sub-ulp summation noise)."""
     import numpy as np
+    assert len(got) == len(exp) == len(header), (key, len(got), len(exp), len(header))
+    alt = None
+    knife = 0
+    for name, a, b in zip(header[3:], got[3:], exp[3:]):
+        if b is None or name == "mod_assignment":
+            assert a == b, (key, name, a, b)
+            continue
+        b = _num(b)
+        assert a is not None, (key, name, b)
+        if np.isnan(b):
+            assert np.isnan(a), (key, name, a)
+            continue
+        tol = rtol_p if (name.startswith("pval") or name == prefilter_method) else rtol_param
+        if np.isclose(a, b, rtol=tol, atol=1e-300):
+            continue
+        if alt is None:
+            alt = _knife_edge_alternatives(header, exp, layout)
+        assert any(np.isclose(a, c, rtol=tol, atol=1e-300) for c in alt.get(name, [])), (key, name, a, b, alt.get(name))
+        knife += 1
+    return knife
+
+
+def half_integer_tests(batch, p):
+    """Number of z-test cells of position p for which a knife-edge acceptance is legitimate: tests with a side whose
+    mean EXACT read count over its present groups is a half-integer (3 cells - diff, pval, z - per such test; the
+    diff_mod_rate cell never depends on n, so at most 2 can differ)."""
+    import numpy as np
+    lay = batch.layout
+    gc = np.asarray(lay.grp_cond)
+    gl = batch.grp_len[p]
+    Cn = lay.n_conditions
+
+    def half(groups):
+        g = [x for x in groups if gl[x] > 0]
+        return bool(g) and (2 * int(gl[g].sum())) % (2 * len(g)) == len(g)
+
+    sides = [[g for g in range(lay.n_groups) if gc[g] == c] for c in range(Cn)]
+    rest = [[g for g in range(lay.n_groups) if gc[g] != c] for c in range(Cn)]
+    n = 0
+    for a in range(Cn):
+        for b in range(a + 1, Cn):
+            n += 2 * int(half(sides[a]) or half(sides[b]))
+    if Cn > 2:
+        for a in range(Cn):
+            n += 2 * int(half(sides[a]) or half(rest[a]))
+    return n
+
+
+def compare_tables(got_rows, exp_rows, header, layout, prefilter_method, rtol_param=1e-5, rtol_p=1e-4):
     assert set(got_rows) == set(exp_rows)
+    knife = 0
     for k, r in got_rows.items():
-        e = exp_rows[k]
-        alt = _knife_edge_alternatives(header, e, layout)
-        for name, a, b in zip(header[3:], r[3:], e[3:]):
-            if b is None or isinstance(b, str) and name == "mod_assignment":
-                assert a == b, (k, name, a, b)
-                continue
-            b = _num(b)
-            if np.isnan(b):
-                assert np.isnan(a), (k, name)
-                continue
-            tol = rtol_p if (name.startswith("pval") or name == prefilter_method) else rtol_param
-            if np.isclose(a, b, rtol=tol, atol=1e-300):
-                continue
-            assert any(np.isclose(a, c, rtol=tol, atol=1e-300) for c in alt.get(name, [])), (k, name, a, b)
+        knife += compare_row_cells(k, header, r, exp_rows[k], layout, prefilter_method, rtol_param, rtol_p)
+    return knife
+
+
+def compare_stats_with_oracle(batch, res, p, fit, present, data_info, prefilter_method, table_row, header):
+    """EVERY statistic of fitted position p (kept by the row filter or not) against the oracle's result_row() evaluated on
+    `fit` (posterior parameters: the oracle's own fit, or the reference's golden parameters): the table cells
+    (z-test triples, mod rates, coverages, mu / sigma2 / conf, assignment), the overlap of the two Gaussians, the
+    four cdfs and the keep decision (io.py:255-367).  Returns the knife-edge count of compare_row_cells."""
+    import numpy as np
+
+    from oracle import xpore_oracle as orc
+    from xpore_b200 import fit as xf
+    lay = batch.layout
+    names = [lay.group_names[g] for g in present]
+    pv = None
+    if prefilter_method:
+        pv = float(res.pval[p])
+    key = (table_row[0], table_row[1], table_row[2])
+    row, keep, extra = orc.result_row(key, fit, names, batch.kmer_mean[p], batch.kmer_std[p], data_info, lay.pooling, pv)
+    knife = compare_row_cells(key, header, table_row, row, lay, prefilter_method)
+    st = res.stats[p]
+    if np.isnan(extra["p_overlap"]):
+        assert np.isnan(st[xf.ST_POV]), key
+        assert not keep
+    else:
+        # 1 - (|F_Y(x1) - F_X(x1)| + |F_Y(x2) - F_X(x2)|): differences of cdfs, absolute accuracy is what exists
+        np.testing.assert_allclose(st[xf.ST_POV], extra["p_overlap"], rtol=1e-5, atol=1e-9, err_msg=str(key))
+        np.testing.assert_allclose(st[xf.ST_CDF:xf.ST_CDF + 4], extra["cdfs"], rtol=1e-5, atol=1e-9, err_msg=str(key))
+    # keep decision: identical unless the reference's own inputs sit on a threshold of the filter (never seen)
+    got_keep = bool(res.status[p] & xf.KEEP_ROW)
+    if got_keep != keep:
+        c = np.asarray(extra["cdfs"])
+        near = abs(extra["p_overlap"] - 0.5) < 1e-6 or (np.abs(c - 0.1) < 1e-6).any() or (np.abs(c - 0.9) < 1e-6).any()
+        assert near, (key, got_keep, keep, extra["p_overlap"], extra["cdfs"])
+    assert bool(res.status[p] & xf.MOD_IS_1) == (extra["mod"] == 1), key
+    return knife

@@ -11,7 +11,7 @@ from xpore_b200 import fit as xf
 from xpore_b200.kmer_model import KmerModel
 from xpore_b200.synth import Spec, make_batch
 
-from helpers import compare_with_golden, pack_case
+from helpers import compare_stats_with_oracle, compare_with_golden, half_integer_tests, pack_case
 
 pytestmark = pytest.mark.gpu
 
@@ -135,6 +135,14 @@ def test_device_path_vs_oracle(torch_cuda, shape):
     idx = np.nonzero(sel)[0]
     idx = rng.choice(idx, size=min(n_check, len(idx)), replace=False)
     same_iters = 0
+    from xpore_b200.table import get_result_table_header, result_rows
+    batch.ids = ["id"] * batch.n_positions
+    batch.positions = [str(i) for i in range(batch.n_positions)]
+    batch.kmers = ["NNNNN"] * batch.n_positions
+    pm = method.prefilter_method
+    header = get_result_table_header(batch.layout, pm)
+    row_of = dict(zip(np.nonzero(sel)[0].tolist(), result_rows(batch, res, pm, only_kept=False)))
+    knife = bound = 0
     for p in idx:
         f, present = _oracle_fit(batch, p, method)
         same_iters += int(f["n_iterations"] == res.n_iter[p])
@@ -143,8 +151,13 @@ def test_device_path_vs_oracle(torch_cuda, shape):
         np.testing.assert_allclose(res.beta[p], f["beta"], rtol=1e-5)
         np.testing.assert_allclose(res.N[p][present], f["N"], rtol=1e-5, atol=1e-9)
         assert bool(res.status[p] & xf.CONVERGED) == f["converged"]
-    print("%s: %d/%d sampled positions with the oracle's sweep count" % (shape, same_iters, len(idx)))
+        # every statistic of the position, kept by the row filter or not (io.py:255-367)
+        knife += compare_stats_with_oracle(batch, res, int(p), f, present, spec.data_info(), pm, row_of[int(p)], header)
+        bound += half_integer_tests(batch, int(p))
+    print("%s: %d/%d sampled positions with the oracle's sweep count; knife-edge z-test cells %d of %d eligible"
+          % (shape, same_iters, len(idx), knife, bound))
     assert same_iters == len(idx)
+    assert knife <= bound
 
 
 @pytest.mark.parametrize("shift,expect", [(0.0, 2), (-200.0, 1), (1e-9, 0)])
@@ -473,3 +486,98 @@ def test_fit_host_rows_equals_dense_records(torch_cuda):
         xf.fit_rows(batch, method, capacity_rows=len(keep) - 1)
     rows2, _ = xf.fit_rows(batch, method, capacity_rows=len(keep))
     np.testing.assert_array_equal(rows2, rows)
+
+
+@pytest.mark.parametrize("grouping", ["pooled", "runs"])
+def test_deep_positions_vs_oracle(torch_cuda, grouping):
+    """Positions deeper than one CTA's shared memory (the reference has no cap on n, gmm.py:93-127; pooled mode keeps
+    the reads of conditions that failed the count test, io.py:46-58,70-73) go to the streaming class and must not
+    abort the batch: 30k- and 60k-read positions, and read counts on both sides of the boundary between the 4-warp
+    teams and the streaming CTAs, beside ordinary positions - every position against the oracle, f64 and u16."""
+    from xpore_b200.batch import Batch, Layout
+    rng = np.random.default_rng(17)
+    if grouping == "pooled":
+        lay = Layout(["KO", "WT"], ["KO-r1", "KO-r2", "WT-r1", "WT-r2"], [0, 0, 1, 1], True)
+        method = xf.Method(pooling=True)
+    else:
+        lay = Layout(["KO", "WT"], ["KO-r1", "KO-r2", "WT-r1", "WT-r2"], [0, 0, 1, 1], False)
+        method = xf.Method(prefilter_method="t-test", prefilter_threshold=2.0)  # gate open: the generic t-test path runs
+    G = lay.n_groups
+    # boundary of the 4-warp class for this G (xp_api.cu deep_class_split): the slab of a 4-warp team holds
+    # cap reads, 9 bytes each, beside its header
+    from xpore_b200 import _lib
+    L = _lib.lib()
+    L.xpb200_deep_split.restype = C.c_int32
+    L.xpb200_deep_split.argtypes = [C.c_int32]
+    S = int(L.xpb200_deep_split(G))
+    assert 16384 <= S <= 32768
+    km, ks = 95.0, 3.0
+    sizes = [400, 1500, S - 1, S, S + 1, 30000, 60000, 90, 5000]
+    groups = []
+    for n in sizes:
+        per = [n // G + (1 if j < n % G else 0) for j in range(G)]
+        g = []
+        for j, m in enumerate(per):
+            frac = 0.05 if lay.grp_cond[j] == 0 else 0.5
+            k = int(m * frac)
+            g.append(np.round(np.r_[rng.normal(km, ks, m - k), rng.normal(km + 7.0, 1.3 * ks, k)], 2))
+        groups.append(g)
+    y = np.concatenate([np.concatenate(g) for g in groups])
+    glen = np.asarray([[len(x) for x in g] for g in groups], dtype=np.int32)
+    off = np.zeros(len(sizes) + 1, dtype=np.int64)
+    np.cumsum(glen.sum(axis=1), out=off[1:])
+    batch = Batch(lay, y, off, glen, np.full(len(sizes), km), np.full(len(sizes), ks))
+    oracle = [_oracle_fit(batch, p, method) for p in range(len(sizes))]
+    ref = None
+    for encode in (False, True):
+        if encode:
+            assert batch.encode_reads() == 2
+        res = xf.fit_batch(batch, method)
+        assert res.n_fitted == len(sizes) and not (res.status & xf.NOT_FITTED).any()
+        for p, (f, present) in enumerate(oracle):
+            assert res.n_iter[p] == f["n_iterations"], (p, sizes[p], res.n_iter[p], f["n_iterations"])
+            assert bool(res.status[p] & xf.CONVERGED) == f["converged"], p
+            np.testing.assert_allclose(res.mu[p], f["location"], rtol=1e-5, err_msg=str(p))
+            np.testing.assert_allclose(res.alpha[p], f["alpha"], rtol=1e-5, err_msg=str(p))
+            np.testing.assert_allclose(res.beta[p], f["beta"], rtol=1e-5, err_msg=str(p))
+            np.testing.assert_allclose(res.N[p][present], f["N"], rtol=1e-5, atol=1e-9, err_msg=str(p))
+        if method.prefilter_method:
+            for p in range(len(sizes)):
+                a = batch.y[off[p]:off[p + 1]]
+                cond = np.repeat(lay.grp_cond, glen[p])
+                pv = scipy.stats.ttest_ind(a[cond == 0], a[cond == 1]).pvalue
+                np.testing.assert_allclose(res.pval[p], pv, rtol=1e-8, atol=1e-300)
+        if ref is None:
+            ref = res
+        else:  # the encoding changes nothing but the bytes moved
+            np.testing.assert_array_equal(res.n_iter, ref.n_iter)
+            np.testing.assert_array_equal(res.fit, ref.fit)
+            np.testing.assert_array_equal(res.stats, ref.stats)
+    # the same batch resident on the device, and as rows
+    out = xf.fit_device(xf.DeviceBatch(batch), method)
+    torch_cuda.cuda.synchronize()
+    dev = out.to_host()
+    np.testing.assert_array_equal(dev.n_iter, ref.n_iter)
+    np.testing.assert_array_equal(dev.fit, ref.fit)
+
+
+def test_understated_max_reads_is_flagged(torch_cuda):
+    """A device-pointer caller that understates batch.max_reads gets the affected positions back with
+    XPB200_NOT_FITTED (n_iter = -1) instead of a wrong fit or an aborted batch; the others are fitted."""
+    torch = torch_cuda
+    spec = Spec({"KO": 2, "WT": 2}, reads_lo=20, reads_hi=60, f_mod=0.4, seed=52)
+    batch = make_batch(spec, KmerModel.load(), n_positions=500)
+    method = xf.Method()
+    db = xf.DeviceBatch(batch)
+    n = np.diff(batch.read_off)
+    good = xf.fit_device(db, method).to_host()
+    db.max_reads = int(np.sort(n)[250])  # understated: the slab is sized for the median position
+    bad = xf.fit_device(db, method).to_host()
+    torch.cuda.synchronize()
+    cap = (db.max_reads + 1 + 7) & ~7
+    too_deep = n > max(cap, 32)
+    assert too_deep.sum() > 100
+    assert ((bad.status[too_deep] & xf.NOT_FITTED) != 0).all() and (bad.n_iter[too_deep] == -1).all()
+    ok = ~too_deep
+    assert not (bad.status[ok] & xf.NOT_FITTED).any()
+    np.testing.assert_array_equal(bad.fit[ok], good.fit[ok])

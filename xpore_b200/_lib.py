@@ -42,8 +42,8 @@ class XpLaunchInfo(C.Structure):
 
 
 EXPORTS = ["xpb200_fit_width", "xpb200_stats_width", "xpb200_workspace_bytes", "xpb200_fit_device",
-           "xpb200_fit_host", "xpb200_fit_host_rows", "xpb200_release", "xpb200_prefilter_device", "xpb200_stats_device",
-           "xpb200_posterior_device", "xpb200_fit_launch_info", "xpb200_launch_count", "xpb200_measure_fp64_peak", "xpb200_eval_special",
+           "xpb200_fit_host", "xpb200_fit_host_rows", "xpb200_fit_host_rows_async", "xpb200_pack_rows", "xpb200_release", "xpb200_prefilter_device", "xpb200_stats_device",
+           "xpb200_posterior_device", "xpb200_fit_launch_info", "xpb200_deep_split", "xpb200_launch_count", "xpb200_measure_fp64_peak", "xpb200_eval_special",
            "xpb200_set_stage_timing", "xpb200_get_stage_ms", "xpb200_pack_records",
            "xpb200_debug_fill_smem", "xpb200_last_error", "xpb200_version",
            "xpb200_ingest_open", "xpb200_ingest_genes", "xpb200_ingest_copy", "xpb200_ingest_close",
@@ -98,6 +98,12 @@ def lib():
         L.xpb200_fit_host_rows.restype = C.c_int32
         L.xpb200_fit_host_rows.argtypes = [C.c_int32, C.POINTER(XpBatch), C.POINTER(XpMethod), C.c_void_p, C.c_int64,
                                            C.POINTER(C.c_int64), C.POINTER(C.c_uint32)]
+        L.xpb200_fit_host_rows_async.restype = C.c_int32
+        L.xpb200_fit_host_rows_async.argtypes = [C.c_int32, C.POINTER(XpBatch), C.POINTER(XpMethod), C.c_void_p, C.c_int64,
+                                                 C.c_int64, C.c_void_p, C.c_void_p]
+        L.xpb200_pack_rows.restype = C.c_int32
+        L.xpb200_pack_rows.argtypes = [C.POINTER(XpResult), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         if hasattr(L, "xpb200_debug_fill_smem"):  # absent only in experiment builds (XPB200_LIB)
             L.xpb200_debug_fill_smem.restype = C.c_int32
             L.xpb200_debug_fill_smem.argtypes = [C.c_uint64, C.c_void_p]
@@ -124,6 +130,8 @@ def lib():
                                               C.c_void_p]
         L.xpb200_fit_launch_info.restype = C.c_int32
         L.xpb200_fit_launch_info.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(XpLaunchInfo)]
+        L.xpb200_deep_split.restype = C.c_int32
+        L.xpb200_deep_split.argtypes = [C.c_int32]
         L.xpb200_launch_count.restype = C.c_uint64
         L.xpb200_measure_fp64_peak.restype = C.c_int32
         L.xpb200_measure_fp64_peak.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_double)]

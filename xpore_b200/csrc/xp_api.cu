@@ -54,11 +54,14 @@ struct Workspace {  // carved out of the caller's buffer
     unsigned int* ticket;
     uint32_t* n_large;
     unsigned int* ticket_large;
-    uint32_t* n_mid;
-    unsigned int* ticket_small;
+    uint32_t* n_deep;
+    unsigned int* ticket_deep;
+    uint32_t* pack_counts;  // [kPackWarps] scratch of xpb200_pack_rows
     int32_t* worklist;
 };
-size_t ws_header_bytes() { return (size_t)(2 * xpk::kBuckets + 64) * 4; }
+constexpr int kPackWarps = 2048;  // warps of the row-compaction launches of one batch / chunk
+size_t ws_header_bytes() { return (size_t)(2 * xpk::kBuckets + 64) * 4; }  // the part zeroed before every fit
+size_t ws_fixed_bytes() { return ws_header_bytes() + (size_t)kPackWarps * 4; }
 Workspace carve(void* ws) {
     Workspace w;
     uint32_t* u = reinterpret_cast<uint32_t*>(ws);
@@ -68,9 +71,10 @@ Workspace carve(void* ws) {
     w.ticket = u + 2 * xpk::kBuckets + 1;
     w.n_large = u + 2 * xpk::kBuckets + 2;
     w.ticket_large = u + 2 * xpk::kBuckets + 3;
-    w.n_mid = u + 2 * xpk::kBuckets + 4;
-    w.ticket_small = u + 2 * xpk::kBuckets + 5;
-    w.worklist = reinterpret_cast<int32_t*>(u + 2 * xpk::kBuckets + 64);
+    w.n_deep = u + 2 * xpk::kBuckets + 4;
+    w.ticket_deep = u + 2 * xpk::kBuckets + 5;
+    w.pack_counts = u + 2 * xpk::kBuckets + 64;
+    w.worklist = reinterpret_cast<int32_t*>(u + 2 * xpk::kBuckets + 64 + kPackWarps);
     return w;
 }
 
@@ -90,11 +94,14 @@ int check_batch(const xpb200_batch* b, const xpb200_method* m) {
 struct Geometry {
     int tw, teams, threads, maxt, cap, ctas_per_sm, sms, regs;
     size_t smem;
+    bool stream;
 };
 
-template <int TW, int MAXT>
+constexpr int kStreamWarps = 16;  // warps of a streaming team (one CTA, one position)
+
+template <int TW, int MAXT, bool STREAM = false>
 int prepare_kernel(Geometry* g) {
-    auto* k = xpk::xp_fit_kernel<TW, MAXT>;
+    auto* k = xpk::xp_fit_kernel<TW, MAXT, STREAM>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g->ctas_per_sm, k, g->threads, g->smem));
     cudaFuncAttributes fa;
@@ -104,45 +111,40 @@ int prepare_kernel(Geometry* g) {
 }
 
 constexpr int kFitWarpsDefault = 28;
-constexpr size_t kSmemPerSm = 228u << 10;
-thread_local int g_pipe_ctas = 0;  // > 1 while fit_host_impl launches its chunks (see fit_geometry)
 
-int env_int(const char* name, int dflt) {
+// Tuning knobs read from the environment exist only in experiment builds (-DXPB200_EXPERIMENTS); the shipped
+// library always runs its defaults.
+int exp_int(const char* name, int dflt) {
+#ifdef XPB200_EXPERIMENTS
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
+#else
+    (void)name;
+    return dflt;
+#endif
 }
 
-// Teams per CTA: as many as 227 KB of shared memory (after the 24.5 KB of tables) allows, up to 28
-// single-warp teams (XPB200_FIT_WARPS overrides, <= 32).  The kernel is instantiated per thread limit
+// Teams per CTA: as many as 227 KB of shared memory (after the 4 KB of tables) allows, up to 28
+// single-warp teams.  The kernel is instantiated per thread limit
 // (640 / 768 / 896 / 1024 threads => 96 / 80 / 72 / 64 registers per thread) so that ptxas knows its budget.
+// tw = kStreamWarps: the streaming flavour (reads stay in global memory; no cap on the reads of a position).
 int fit_geometry(int G, int cap_reads, int tw, Geometry* g) {
     int dev = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&g->sms, cudaDevAttrMultiProcessorCount, dev));
     g->tw = tw;
+    g->stream = (tw == kStreamWarps);
     g->cap = std::max(32, (cap_reads + 1 + 7) & ~7);
-    const size_t per_team = xpk::fit_team_smem_bytes(g->cap, G, tw);
+    const size_t per_team = xpk::fit_team_smem_bytes(g->cap, G, tw, g->stream);
     if (xpk::kFitTableBytes + per_team > kMaxSmemPerCta)
-        return fail(XPB200_EINVAL, "a position has more reads than one CTA's shared memory holds (max_reads=" +
-                                       std::to_string(cap_reads) + ")");
+        return fail(XPB200_EINVAL, "internal: a resident-class slab for " + std::to_string(cap_reads) +
+                                       " reads exceeds one CTA's shared memory (the streaming class takes those)");
     int teams = (int)((kMaxSmemPerCta - xpk::kFitTableBytes) / per_team);
-    const int K = g_pipe_ctas;
-    int t_pipe = 0;
-    if (tw == 1 && K > 1) {
-        // chunked host pipeline: K small CTAs per SM instead of one large one.  A CTA leaves when its slowest warp
-        // is done, so small CTAs hand an SM over to the next chunk's launch piecemeal instead of idling through
-        // the drain of 28 warps; what the launch leaves free of an SM (registers, shared memory) lets the next
-        // chunk's prefilter / worklist launches run beside it.
-        const size_t per_cta = kSmemPerSm / K - 1024;  // 1 KB per resident CTA is reserved by the system
-        if (per_cta > xpk::kFitTableBytes + per_team)
-            t_pipe = std::min((int)((per_cta - xpk::kFitTableBytes) / per_team), std::max(1, kFitWarpsDefault / K));
-    }
-    if (t_pipe >= 1) {
-        teams = t_pipe;
-        const int total = teams * K;
-        g->maxt = total <= 20 ? 640 : total <= 24 ? 768 : 896;
+    if (g->stream) {
+        teams = 1;
+        g->maxt = kStreamWarps * 32;
     } else if (tw == 1) {
-        teams = std::min(teams, std::max(1, env_int("XPB200_FIT_WARPS", kFitWarpsDefault)));
+        teams = std::min(teams, std::max(1, exp_int("XPB200_FIT_WARPS", kFitWarpsDefault)));
         teams = std::min(teams, 32);
         g->maxt = teams <= 20 ? 640 : teams <= 24 ? 768 : teams <= 28 ? 896 : 1024;
     } else {
@@ -153,7 +155,8 @@ int fit_geometry(int G, int cap_reads, int tw, Geometry* g) {
     g->threads = teams * tw * 32;
     g->smem = xpk::kFitTableBytes + per_team * teams;
     int rc;
-    if (tw == 1) {
+    if (g->stream) rc = prepare_kernel<kStreamWarps, kStreamWarps * 32, true>(g);
+    else if (tw == 1) {
         switch (g->maxt) {
             case 640: rc = prepare_kernel<1, 640>(g); break;
             case 768: rc = prepare_kernel<1, 768>(g); break;
@@ -194,32 +197,27 @@ int side_streams(cudaStream_t st, SideStreams** out) {
     return 0;
 }
 
-// Largest bucket boundary S of the worklist (xp_kernels.cuh:cost_bucket: 16 buckets per octave) such that a slab for
-// S - 1 reads lets a CTA hold the full number of single-warp teams; 0 when the launch for `max_reads` already
-// does (teams_now), or when no boundary of at least 64 reads qualifies.
-int small_class_split(int G, int max_reads, int teams_now) {
-    const int target = std::min(std::max(1, env_int("XPB200_FIT_WARPS", kFitWarpsDefault)), 32);
-    // Off by default: on c4 (20-5000 reads, log-uniform) the third launch cost more (8.2 ms) than its 28 instead of
-    // 19 warps per CTA gained (two classes on forked streams: 7.9 ms).  XPB200_SMALL_CLASS=1 turns it on.
-    if (teams_now >= target || !env_int("XPB200_SMALL_CLASS", 0)) return 0;
-    for (int e = 9; e >= 6; --e) {
-        for (int k = 15; k >= 0; --k) {
+// Positions with at least this many reads go to the streaming class: the smallest bucket boundary S of the worklist
+// (xp_kernels.cuh:cost_bucket, 16 buckets per octave) such that a 4-warp team's slab cannot hold S reads any more,
+// i.e. the largest S whose predecessor S - 1 still fits one CTA.
+int deep_class_split(int G) {
+    int best = 0;
+    for (int e = 10; e <= 17; ++e)
+        for (int k = 0; k < 16; ++k) {
             const int S = (1 << e) + k * (1 << (e - 4));
-            if (S > max_reads) continue;
             const int cap = std::max(32, (S - 1 + 1 + 7) & ~7);
-            const size_t per_team = xpk::fit_team_smem_bytes(cap, G, 1);
-            if ((int)((kMaxSmemPerCta - xpk::kFitTableBytes) / per_team) >= target) return S;
+            if (xpk::kFitTableBytes + xpk::fit_team_smem_bytes(cap, G, 4) <= kMaxSmemPerCta) best = S;
         }
-    }
-    return 0;
+    return best;  // > kSplitReads for every G <= kMaxGroups
 }
 
 int launch_fit(const Geometry& g, const xpk::FitArgs& fa_in, int max_teams_needed, cudaStream_t st) {
     xpk::FitArgs fa = fa_in;
-    xpk::fit_fill_layout(fa, g.tw);
+    xpk::fit_fill_layout(fa, g.tw, g.stream);
     const int need = (max_teams_needed + g.teams - 1) / g.teams;
     const int grid = std::max(1, std::min(g.sms * g.ctas_per_sm, need));
-    if (g.tw == 1) {
+    if (g.stream) xpk::xp_fit_kernel<kStreamWarps, kStreamWarps * 32, true><<<grid, g.threads, g.smem, st>>>(fa);
+    else if (g.tw == 1) {
         switch (g.maxt) {
             case 640: xpk::xp_fit_kernel<1, 640><<<grid, g.threads, g.smem, st>>>(fa); break;
             case 768: xpk::xp_fit_kernel<1, 768><<<grid, g.threads, g.smem, st>>>(fa); break;
@@ -277,7 +275,12 @@ const char* xpb200_version(void) { return "xpore_b200 0.1 (sm_100a)"; }
 uint64_t xpb200_launch_count(void) { return g_launches; }
 int32_t xpb200_fit_width(int32_t G) { return xpc::fit_width(G); }
 int32_t xpb200_stats_width(int32_t G, int32_t C) { return xpc::stats_width(G, C); }
-size_t xpb200_workspace_bytes(int32_t P) { return ws_header_bytes() + (size_t)std::max(P, 1) * 4; }
+size_t xpb200_workspace_bytes(int32_t P) { return ws_fixed_bytes() + (size_t)std::max(P, 1) * 4; }
+
+int32_t xpb200_deep_split(int32_t G) {
+    if (G < 1 || G > xpk::kMaxGroups) return fail(XPB200_EINVAL, "n_groups must be 1..64");
+    return deep_class_split(G);
+}
 
 int32_t xpb200_fit_launch_info(int32_t device, int32_t G, int32_t max_reads, xpb200_launch_info* out) {
     if (!out) return fail(XPB200_EINVAL, "null out");
@@ -331,17 +334,17 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
     xpk::WorklistArgs wa;
     wa.status = sel; wa.read_off = b->read_off; wa.P = P; wa.hist = ws.hist; wa.cursor = ws.cursor;
     wa.n_work = ws.n_work; wa.worklist = ws.worklist; wa.n_large = ws.n_large;
+    // Three classes by depth, each with its own launch: n >= deep_split reads -> streaming CTAs (reads stay in global
+    // memory: no cap), n >= kSplitReads -> 4-warp teams, the rest -> one warp per position.
+    const int deep_split = deep_class_split(b->n_groups);
+    const bool has_deep = b->max_reads >= deep_split;
     const bool two_class = b->max_reads >= kSplitReads;
     wa.split = two_class ? kSplitReads : 0;
-    // A third class when the single-warp slab sized for the longest position leaves fewer teams per CTA than the
-    // launch could hold: the positions below `split2` reads (a bucket boundary) get their own launch with a slab
-    // sized for them and the full number of teams - on coverage-skewed batches that is most positions.
+    wa.n_deep = ws.n_deep;
+    wa.split_deep = has_deep ? deep_split : 0;
     const int tw1_reads = two_class ? kSplitReads - 1 : b->max_reads;
     Geometry g;
     if (int rc = fit_geometry(b->n_groups, tw1_reads, 1, &g)) return rc;
-    const int split2 = small_class_split(b->n_groups, tw1_reads, g.teams);
-    wa.n_mid = ws.n_mid;
-    wa.split2 = split2;
     const int wthreads = 256;
     const int wblocks = std::min((P + wthreads - 1) / wthreads, 1184);
     xpk::xp_worklist_count<<<wblocks, wthreads, 0, st>>>(wa);
@@ -351,7 +354,7 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
     CK(cudaGetLastError());
 
     stage_mark(2, st);
-    // K3 fit: persistent CTAs; 4-warp teams for the deep positions first, then one warp per position
+    // K3 fit: persistent CTAs; the deepest positions first
     xpk::FitArgs fa;
     fa.y = b->y; fa.y_format = b->y_format; fa.y_scale = b->y_scale;
     fa.read_off = b->read_off; fa.grp_len = b->grp_len; fa.kmer_mean = b->kmer_mean;
@@ -362,7 +365,7 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
     fa.fit = r->fit; fa.n_iter = r->n_iter; fa.status = r->status; fa.coef = r->coef;
     // class launches, longest positions first: the first on the caller's stream, the others on side streams
     SideStreams* ss = nullptr;
-    const int n_class = 1 + (two_class ? 1 : 0) + (split2 ? 1 : 0);
+    const int n_class = 1 + (two_class ? 1 : 0) + (has_deep ? 1 : 0);
     if (n_class > 1) {
         if (int rc = side_streams(st, &ss)) return rc;
         CK(cudaEventRecord(ss->fork, st));
@@ -380,29 +383,29 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
         }
         return 0;
     };
+    if (has_deep) {
+        Geometry gd;
+        if (int rc = fit_geometry(b->n_groups, 0, kStreamWarps, &gd)) return rc;
+        fa.cap = 0; fa.w_begin = nullptr; fa.w_end = ws.n_deep; fa.ticket = ws.ticket_deep;
+        if (int rc = begin_class(k)) return rc;
+        if (int rc = launch_fit(gd, fa, P, class_stream(k))) return rc;
+        if (int rc = end_class(k)) return rc;
+        ++k;
+    }
     if (two_class) {
         Geometry gl;
-        if (int rc = fit_geometry(b->n_groups, b->max_reads, 4, &gl)) return rc;
-        fa.cap = gl.cap; fa.w_begin = nullptr; fa.w_end = ws.n_large; fa.ticket = ws.ticket_large;
+        if (int rc = fit_geometry(b->n_groups, std::min(b->max_reads, deep_split - 1), 4, &gl)) return rc;
+        fa.cap = gl.cap; fa.w_begin = has_deep ? ws.n_deep : nullptr; fa.w_end = ws.n_large; fa.ticket = ws.ticket_large;
         if (int rc = begin_class(k)) return rc;
         if (int rc = launch_fit(gl, fa, P, class_stream(k))) return rc;
         if (int rc = end_class(k)) return rc;
         ++k;
     }
-    fa.cap = g.cap; fa.w_begin = two_class ? ws.n_large : nullptr; fa.w_end = split2 ? ws.n_mid : ws.n_work; fa.ticket = ws.ticket;
+    fa.cap = g.cap; fa.w_begin = two_class ? ws.n_large : nullptr; fa.w_end = ws.n_work; fa.ticket = ws.ticket;
     if (int rc = begin_class(k)) return rc;
     if (int rc = launch_fit(g, fa, P, class_stream(k))) return rc;
     if (int rc = end_class(k)) return rc;
     ++k;
-    if (split2) {
-        Geometry gs;
-        if (int rc = fit_geometry(b->n_groups, split2 - 1, 1, &gs)) return rc;
-        fa.cap = gs.cap; fa.w_begin = ws.n_mid; fa.w_end = ws.n_work; fa.ticket = ws.ticket_small;
-        if (int rc = begin_class(k)) return rc;
-        if (int rc = launch_fit(gs, fa, P, class_stream(k))) return rc;
-        if (int rc = end_class(k)) return rc;
-        ++k;
-    }
 
     stage_mark(3, st);
     // K4 statistics
@@ -413,22 +416,23 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
     return 0;
 }
 
-// ---- host-buffer entry point --------------------------------------------------------------
+// ---- host-buffer entry points -------------------------------------------------------------
 // The batch is cut into chunks of positions (~kChunkBytes of reads each).  Chunk c's reads go up
-// on the copy-in stream while chunk c-1 is being fitted on the compute stream and chunk c-2's
+// on the copy-in stream while chunk c-1 is being fitted on a compute stream and chunk c-2's
 // records come back on the copy-out stream, so PCIe (full duplex) and the SMs work concurrently.
 namespace {
-constexpr int kMaxChunks = 64;
+constexpr int kMaxChunks = xpk::kMaxRowChunks;
 constexpr size_t kChunkBytes = 112u << 20;
 constexpr int kChunkGrowthPct = 150;
 
 constexpr int kComputeStreams = 3;
-constexpr int kPackWarps = 2048;  // warps of the row-compaction launches of one chunk
 
 struct DevCache {
     int device = -1;
     cudaStream_t s_in = nullptr, s_c[kComputeStreams] = {nullptr, nullptr, nullptr}, s_out = nullptr;
     cudaEvent_t e_in[kMaxChunks], e_done[kMaxChunks];
+    cudaEvent_t e_call = nullptr;  // end of the previous call's device work (the arena is reused by the next one)
+    cudaEvent_t e_user = nullptr;  // the caller's stream at entry of an asynchronous call
     cudaEvent_t t_0 = nullptr, t_in[kMaxChunks], t_start[kMaxChunks], t_done[kMaxChunks];  // XPB200_TRACE=1 only
     void* buf = nullptr;
     size_t cap = 0;
@@ -438,13 +442,39 @@ std::mutex g_cache_mu;
 std::vector<DevCache*> g_cache;
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
-}  // namespace
 
-namespace {
-// r != null: dense result arrays come back (xpb200_fit_host).  rows != null: only the records of the table's
-// rows come back, compacted (xpb200_fit_host_rows).
-int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m, const xpb200_result* r,
-                  double* rows, int64_t rows_capacity, int64_t* n_rows, uint32_t* n_fitted);
+// Output mode of fit_host_impl
+struct HostOut {
+    const xpb200_result* dense = nullptr;  // dense result arrays of every position (host or device memory)
+    double* rows = nullptr;                // host: records of the table's rows, compacted
+    int64_t rows_capacity = 0;
+    int64_t* n_rows = nullptr;
+    uint32_t* n_fitted = nullptr;
+    double* rows_dev = nullptr;            // device: the same records, no host synchronisation
+    uint32_t* counts_dev = nullptr;        // device [2]: rows needed, positions fitted
+    int64_t index_offset = 0;
+    cudaStream_t user_stream = nullptr;
+};
+
+int launch_pack_rows(const xpb200_result& dr, int pc, int FW, int SW, long long index_offset, long long capacity,
+                     unsigned* counts, unsigned* n_rows_dev, double* out, cudaStream_t st) {
+    xpk::PackRowsArgs pa;
+    pa.status = dr.status; pa.n_iter = dr.n_iter; pa.pval = dr.pval; pa.fit = dr.fit; pa.stats = dr.stats;
+    pa.P = pc; pa.FW = FW; pa.SW = SW; pa.need = xpc::STATUS_SELECTED | xpc::STATUS_KEEP_ROW;
+    pa.index_offset = index_offset; pa.capacity = capacity; pa.n_rows = n_rows_dev; pa.out = out;
+    const int threads = 256, wpb = threads / 32;
+    pa.n_warps = std::max(1, std::min(kPackWarps, (pc + 255) / 256));
+    pa.span = ((pc + pa.n_warps - 1) / pa.n_warps + 31) & ~31;
+    pa.counts = counts;
+    const int blocks = (pa.n_warps + wpb - 1) / wpb;
+    xpk::xp_count_rows_kernel<<<blocks, threads, 0, st>>>(pa);
+    xpk::xp_pack_rows_kernel<<<blocks, threads, 0, st>>>(pa);
+    g_launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m, const HostOut& ho);
 }  // namespace
 
 int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_method* m, const xpb200_result* r,
@@ -452,19 +482,43 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_meth
     if (int rc = check_batch(b, m)) return rc;
     if (!r || !r->status || !r->n_iter || !r->pval || !r->fit || !r->stats)
         return fail(XPB200_EINVAL, "null result array");
-    return fit_host_impl(device, b, m, r, nullptr, 0, nullptr, n_fitted);
+    HostOut ho;
+    ho.dense = r;
+    ho.n_fitted = n_fitted;
+    return fit_host_impl(device, b, m, ho);
 }
 
 int32_t xpb200_fit_host_rows(int32_t device, const xpb200_batch* b, const xpb200_method* m, double* rows,
                              int64_t capacity_rows, int64_t* n_rows, uint32_t* n_fitted) {
     if (int rc = check_batch(b, m)) return rc;
     if (!rows || capacity_rows < 0 || !n_rows) return fail(XPB200_EINVAL, "null rows / n_rows");
-    return fit_host_impl(device, b, m, nullptr, rows, capacity_rows, n_rows, n_fitted);
+    HostOut ho;
+    ho.rows = rows;
+    ho.rows_capacity = capacity_rows;
+    ho.n_rows = n_rows;
+    ho.n_fitted = n_fitted;
+    return fit_host_impl(device, b, m, ho);
+}
+
+int32_t xpb200_fit_host_rows_async(int32_t device, const xpb200_batch* b, const xpb200_method* m, double* rows_dev,
+                                   int64_t capacity_rows, int64_t index_offset, uint32_t* counts_dev, void* stream) {
+    if (int rc = check_batch(b, m)) return rc;
+    if (!rows_dev || capacity_rows < 0 || !counts_dev) return fail(XPB200_EINVAL, "null rows_dev / counts_dev");
+    HostOut ho;
+    ho.rows_dev = rows_dev;
+    ho.rows_capacity = capacity_rows;
+    ho.counts_dev = counts_dev;
+    ho.index_offset = index_offset;
+    ho.user_stream = (cudaStream_t)stream;
+    return fit_host_impl(device, b, m, ho);
 }
 
 namespace {
-int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m, const xpb200_result* r,
-                  double* rows, int64_t rows_capacity, int64_t* n_rows, uint32_t* n_fitted) {
+int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m, const HostOut& ho) {
+    const xpb200_result* r = ho.dense;
+    double* rows = ho.rows;
+    const bool want_rows = ho.rows != nullptr || ho.rows_dev != nullptr;
+    const bool async = ho.rows_dev != nullptr;
     CK(cudaSetDevice(device));
     std::lock_guard<std::mutex> lk(g_cache_mu);
     DevCache* dc = nullptr;
@@ -480,19 +534,24 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
             CK(cudaEventCreateWithFlags(&dc->e_in[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&dc->e_done[i], cudaEventDisableTiming));
         }
+        CK(cudaEventCreateWithFlags(&dc->e_call, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&dc->e_user, cudaEventDisableTiming));
         g_cache.push_back(dc);
     }
     const int P = b->n_positions, G = b->n_groups, C = b->n_conditions;
-    if (n_fitted) *n_fitted = 0;
-    if (n_rows) *n_rows = 0;
-    if (P == 0) return 0;
+    if (ho.n_fitted) *ho.n_fitted = 0;
+    if (ho.n_rows) *ho.n_rows = 0;
+    if (P == 0) {
+        if (async) CK(cudaMemsetAsync(ho.counts_dev, 0, 8, ho.user_stream));
+        return 0;
+    }
     const size_t eb = b->y_format == XPB200_Y_F64 ? 8 : (b->y_format == XPB200_Y_I32 ? 4 : 2);
     const int FW = xpc::fit_width(G), SW = xpc::stats_width(G, C);
 
     // chunk boundaries (positions), cut where the read offsets cross the chunk targets.  The first chunks are
     // small so the SMs start early; a remainder of less than a quarter chunk joins the last one.
     const int64_t* roff = b->read_off;
-    const size_t chunk_bytes = (size_t)std::max(1, env_int("XPB200_CHUNK_MB", (int)(kChunkBytes >> 20))) << 20;
+    const size_t chunk_bytes = (size_t)std::max(1, exp_int("XPB200_CHUNK_MB", (int)(kChunkBytes >> 20))) << 20;
     const size_t total_bytes = (size_t)b->n_reads * eb;
     std::vector<int> cut(1, 0);
     {
@@ -501,7 +560,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         // sizes grow by kChunkGrowth from an eighth of a full chunk: the copy is only ~1.2x faster than the fit, so
         // a chunk that is much larger than its predecessor would leave the SMs waiting for it to arrive
         size_t sz = std::max<size_t>(chunk_bytes / 8, 1u << 20);
-        const double growth = std::max(1.0, env_int("XPB200_CHUNK_GROWTH_PCT", kChunkGrowthPct) / 100.0);
+        const double growth = std::max(1.0, exp_int("XPB200_CHUNK_GROWTH_PCT", kChunkGrowthPct) / 100.0);
         while (pos + sz + sz / 4 < total_bytes && (int)ends.size() < kMaxChunks - 2) {
             pos += sz;
             ends.push_back(pos);
@@ -516,9 +575,9 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         cut.push_back(P);
     }
     const int nchunks = (int)cut.size() - 1;
-    const bool nocopy = env_int("XPB200_DEBUG_NOCOPY", 0) != 0;
     ++dc->calls;
-    const bool trace = env_int("XPB200_TRACE", 0) != 0;  // timed events per chunk, printed to stderr
+    const char* trace_env = getenv("XPB200_TRACE");  // diagnostic only: timed events per chunk, printed to stderr
+    const bool trace = trace_env && *trace_env && atoi(trace_env) != 0 && !async;
     if (trace && !dc->t_0) {
         CK(cudaEventCreate(&dc->t_0));
         for (int i = 0; i < kMaxChunks; ++i) {
@@ -528,8 +587,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         }
     }
     const auto host_t0 = std::chrono::steady_clock::now();
-    const int pipe_ctas = std::max(1, env_int("XPB200_PIPE_CTAS", 1));
-    const int n_streams = std::min(kComputeStreams, std::max(1, env_int("XPB200_STREAMS", 3)));
+    const int n_streams = std::min(kComputeStreams, std::max(1, exp_int("XPB200_STREAMS", 3)));
 
     // device layout
     size_t o = 0;
@@ -546,15 +604,16 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     const size_t o_stats = o; o += align_up((size_t)P * SW * 8);
     const size_t o_nf = o; o += align_up((size_t)kMaxChunks * 4);
     const size_t o_nr = o; o += align_up((size_t)kMaxChunks * 4);
-    const size_t o_cnt = o; o += rows ? align_up((size_t)kMaxChunks * kPackWarps * 4) : 0;
+    const size_t o_cnt = o; o += want_rows ? align_up((size_t)kMaxChunks * kPackWarps * 4) : 0;
     const int RW = 4 + FW + SW;  // record width
-    const size_t o_rows = o; o += rows ? align_up((size_t)P * RW * 8) : 0;  // chunk c's rows start at row cut[c]
+    const size_t o_rows = o; o += want_rows ? align_up((size_t)P * RW * 8) : 0;  // chunk c's rows start at row cut[c]
     std::vector<size_t> o_ws(nchunks);
     for (int c = 0; c < nchunks; ++c) {
         o_ws[c] = o;
         o += align_up(xpb200_workspace_bytes(cut[c + 1] - cut[c]));
     }
     if (o > dc->cap) {
+        CK(cudaDeviceSynchronize());  // an asynchronous call may still be using the arena
         if (dc->buf) CK(cudaFree(dc->buf));
         dc->buf = nullptr;
         dc->cap = 0;
@@ -581,6 +640,16 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     uint32_t* d_cnt = (uint32_t*)(d + o_cnt);
     double* d_rows = (double*)(d + o_rows);
 
+    // the arena is shared with the previous call, which an asynchronous caller may not have waited for; and an
+    // asynchronous call starts after the work already enqueued on the caller's stream
+    if (dc->calls > 1) {
+        CK(cudaStreamWaitEvent(dc->s_in, dc->e_call, 0));
+        for (int i = 0; i < kComputeStreams; ++i) CK(cudaStreamWaitEvent(dc->s_c[i], dc->e_call, 0));
+    }
+    if (async) {
+        CK(cudaEventRecord(dc->e_user, ho.user_stream));
+        CK(cudaStreamWaitEvent(dc->s_in, dc->e_user, 0));
+    }
     if (trace) CK(cudaEventRecord(dc->t_0, dc->s_in));
     CK(cudaMemcpyAsync(d + o_gc, b->grp_cond, (size_t)G * 4, cudaMemcpyDefault, dc->s_in));
     CK(cudaMemsetAsync(d_nf, 0, (size_t)kMaxChunks * 4, dc->s_in));
@@ -590,7 +659,6 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         if (pc == 0) continue;
         const int64_t r0 = roff[p0], r1 = roff[p1];
         // copy-in
-        if (!(nocopy && dc->calls > 1))  // experiment: reuse the reads a previous identical call left on the device
         CK(cudaMemcpyAsync(d_y + (size_t)r0 * eb, (const char*)b->y + (size_t)r0 * eb, (size_t)(r1 - r0) * eb,
                            cudaMemcpyDefault, dc->s_in));
         CK(cudaMemcpyAsync(d_off + p0, roff + p0, (size_t)(pc + 1) * 8, cudaMemcpyDefault, dc->s_in));
@@ -606,6 +674,12 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         xpb200_batch db = *b;
         db.n_positions = pc;
         db.n_reads = r1 - r0;
+        // the chunk's own deepest position decides its launch classes (the host has the offsets: the caller's
+        // max_reads is not relied upon)
+        int64_t deepest = 0;
+        for (int p = p0; p < p1; ++p) deepest = std::max(deepest, roff[p + 1] - roff[p]);
+        if (deepest > 0x7fffffff) return fail(XPB200_EINVAL, "a position has more than 2^31 - 1 reads");
+        db.max_reads = (int32_t)deepest;
         db.y = d_y; db.read_off = d_off + p0; db.grp_len = d_glen + (size_t)p0 * G;
         db.kmer_mean = d_km + p0; db.kmer_std = d_ks + p0; db.grp_cond = (const int32_t*)(d + o_gc);
         xpb200_result dr;
@@ -615,28 +689,14 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         CK(cudaMemsetAsync(dr.n_iter, 0, (size_t)pc * 4, sc));
         CK(cudaMemsetAsync(dr.fit, 0xFF, (size_t)pc * FW * 8, sc));
         CK(cudaMemsetAsync(dr.stats, 0xFF, (size_t)pc * SW * 8, sc));
-        g_pipe_ctas = (nchunks > 1) ? pipe_ctas : 0;
-        const int rc_fit = xpb200_fit_device(&db, m, &dr, d + o_ws[c], xpb200_workspace_bytes(pc), d_nf + c, sc);
-        g_pipe_ctas = 0;
-        if (rc_fit) return rc_fit;
-        if (rows) {  // compact the table's rows of this chunk
-            xpk::PackRowsArgs pa;
-            pa.status = dr.status; pa.n_iter = dr.n_iter; pa.pval = dr.pval; pa.fit = dr.fit; pa.stats = dr.stats;
-            pa.P = pc; pa.FW = FW; pa.SW = SW; pa.need = xpc::STATUS_SELECTED | xpc::STATUS_KEEP_ROW;
-            pa.index_offset = p0; pa.capacity = pc; pa.n_rows = d_nr + c; pa.out = d_rows + (size_t)p0 * RW;
-            const int threads = 256, wpb = threads / 32;
-            pa.n_warps = std::max(1, std::min(kPackWarps, (pc + 255) / 256));
-            pa.span = ((pc + pa.n_warps - 1) / pa.n_warps + 31) & ~31;
-            pa.counts = d_cnt + (size_t)c * kPackWarps;
-            const int blocks = (pa.n_warps + wpb - 1) / wpb;
-            xpk::xp_count_rows_kernel<<<blocks, threads, 0, sc>>>(pa);
-            xpk::xp_pack_rows_kernel<<<blocks, threads, 0, sc>>>(pa);
-            g_launches += 2;
-            CK(cudaGetLastError());
-        }
+        if (int rc_fit = xpb200_fit_device(&db, m, &dr, d + o_ws[c], xpb200_workspace_bytes(pc), d_nf + c, sc)) return rc_fit;
+        if (want_rows)  // compact the table's rows of this chunk
+            if (int rc = launch_pack_rows(dr, pc, FW, SW, ho.index_offset + p0, pc, d_cnt + (size_t)c * kPackWarps, d_nr + c,
+                                          d_rows + (size_t)p0 * RW, sc))
+                return rc;
         CK(cudaEventRecord(dc->e_done[c], sc));
         if (trace) CK(cudaEventRecord(dc->t_done[c], sc));
-        if (rows) continue;  // the rows are fetched below, once their counts are known
+        if (want_rows) continue;  // the rows are fetched below, once their counts are known
         // copy-out
         CK(cudaStreamWaitEvent(dc->s_out, dc->e_done[c], 0));
         CK(cudaMemcpyAsync(r->status + p0, dr.status, (size_t)pc * 4, cudaMemcpyDefault, dc->s_out));
@@ -644,6 +704,21 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         CK(cudaMemcpyAsync(r->pval + p0, dr.pval, (size_t)pc * 8, cudaMemcpyDefault, dc->s_out));
         CK(cudaMemcpyAsync(r->fit + (size_t)p0 * FW, dr.fit, (size_t)pc * FW * 8, cudaMemcpyDefault, dc->s_out));
         CK(cudaMemcpyAsync(r->stats + (size_t)p0 * SW, dr.stats, (size_t)pc * SW * 8, cudaMemcpyDefault, dc->s_out));
+    }
+    if (async) {
+        // rows of all chunks, concatenated on the device into the caller's buffer; nothing waits on the host
+        for (int c = 0; c < nchunks; ++c)
+            if (cut[c + 1] > cut[c]) CK(cudaStreamWaitEvent(dc->s_out, dc->e_done[c], 0));
+        xpk::ConcatRowsArgs ca;
+        ca.rows = d_rows; ca.n_rows = d_nr; ca.n_fitted = d_nf; ca.n_chunks = nchunks; ca.RW = RW;
+        ca.capacity = ho.rows_capacity; ca.out = ho.rows_dev; ca.out_counts = ho.counts_dev;
+        for (int c = 0; c < nchunks; ++c) ca.chunk_start[c] = cut[c];
+        xpk::xp_concat_rows_kernel<<<148 * 4, 256, 0, dc->s_out>>>(ca);
+        ++g_launches;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(dc->e_call, dc->s_out));
+        CK(cudaStreamWaitEvent(ho.user_stream, dc->e_call, 0));
+        return 0;
     }
     if (rows) {
         // every chunk is enqueued; fetch each chunk's rows as soon as it is done (count first, then the rows)
@@ -656,7 +731,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
             CK(cudaStreamWaitEvent(dc->s_out, dc->e_done[c], 0));
             CK(cudaMemcpyAsync(&cnt, d_nr + c, 4, cudaMemcpyDefault, dc->s_out));
             CK(cudaStreamSynchronize(dc->s_out));
-            if (total_rows + cnt > rows_capacity) {
+            if (total_rows + cnt > ho.rows_capacity) {
                 overflow = true;
                 total_rows += cnt;
                 continue;
@@ -667,7 +742,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
             total_rows += cnt;
         }
         CK(cudaStreamSynchronize(dc->s_out));
-        *n_rows = total_rows;
+        *ho.n_rows = total_rows;
         if (overflow) {
             for (int i = 0; i < kComputeStreams; ++i) CK(cudaStreamSynchronize(dc->s_c[i]));
             CK(cudaStreamSynchronize(dc->s_in));
@@ -679,9 +754,10 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     CK(cudaStreamSynchronize(dc->s_out));
     for (int i = 0; i < kComputeStreams; ++i) CK(cudaStreamSynchronize(dc->s_c[i]));
     CK(cudaStreamSynchronize(dc->s_in));
+    CK(cudaEventRecord(dc->e_call, dc->s_out));
     uint32_t total = 0;
     for (int c = 0; c < nchunks; ++c) total += nf[c];
-    if (n_fitted) *n_fitted = total;
+    if (ho.n_fitted) *ho.n_fitted = total;
     if (trace) {
         const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
         fprintf(stderr, "[xpb200 trace] %d chunks, host %.3f ms\n", nchunks, host_ms);
@@ -703,6 +779,7 @@ void xpb200_release(void) {
     std::lock_guard<std::mutex> lk(g_cache_mu);
     for (auto* c : g_cache) {
         cudaSetDevice(c->device);
+        cudaDeviceSynchronize();  // an asynchronous call may still be using the arena
         if (c->buf) cudaFree(c->buf);
         for (cudaStream_t st : {c->s_in, c->s_c[0], c->s_c[1], c->s_c[2], c->s_out})
             if (st) cudaStreamDestroy(st);
@@ -710,6 +787,8 @@ void xpb200_release(void) {
             cudaEventDestroy(c->e_in[i]);
             cudaEventDestroy(c->e_done[i]);
         }
+        if (c->e_call) cudaEventDestroy(c->e_call);
+        if (c->e_user) cudaEventDestroy(c->e_user);
         delete c;
     }
     g_cache.clear();
@@ -791,6 +870,18 @@ int32_t xpb200_pack_records(const xpb200_result* r, int32_t P, int32_t G, int32_
     ++g_launches;
     CK(cudaGetLastError());
     return 0;
+}
+
+int32_t xpb200_pack_rows(const xpb200_result* r, int32_t P, int32_t G, int32_t C, void* workspace,
+                         int64_t index_offset, double* out, int64_t capacity_rows, uint32_t* n_rows_dev, void* stream) {
+    if (!r || !workspace || !out || !n_rows_dev) return fail(XPB200_EINVAL, "null argument");
+    if (P <= 0) {
+        CK(cudaMemsetAsync(n_rows_dev, 0, 4, (cudaStream_t)stream));
+        return 0;
+    }
+    Workspace ws = carve(workspace);
+    return launch_pack_rows(*r, P, xpc::fit_width(G), xpc::stats_width(G, C), index_offset, capacity_rows,
+                            ws.pack_counts, n_rows_dev, out, (cudaStream_t)stream);
 }
 
 // Test utility: overwrite the shared memory of every SM with a 64-bit pattern (a later kernel that

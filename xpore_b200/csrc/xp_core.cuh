@@ -32,6 +32,8 @@ constexpr uint32_t STATUS_KEEP_ROW = 16u;      // row filter io.py:363-367
 constexpr uint32_t STATUS_MOD_IS_1 = 32u;      // modified cluster is component 1 (io.py:277-282)
 constexpr uint32_t STATUS_HIGHER = 64u;        // mod_assignment == 'higher' (io.py:288)
 constexpr uint32_t STATUS_TTEST_VALID = 128u;  // exactly two conditions present (statstest.py:20-21)
+constexpr uint32_t STATUS_NOT_FITTED = 256u;   // selected but not fitted: the caller understated batch.max_reads (n_iter = -1)
+constexpr uint32_t STATUS_NEAR_THRESHOLD = 512u;  // prefilter p-value within 1e-9 (relative) of the threshold: see xp_prefilter_kernel
 
 struct Comp {
     double mp, lam, alpha, beta;  // centred location m', lambda, alpha, beta of q(mu_k, tau_k)

@@ -92,31 +92,34 @@ constexpr size_t kFitTableBytes = (size_t)(kTabExpDoubles + kTabLogDoubles) * 8;
 __host__ __device__ inline int fit_rows(int G) { return G + 3; }
 // scratch: column c (N_g0 of group c < G, then S1_0, S2_0, entropy) holds one double per thread of the team;
 // columns are 32 TW + 1 doubles apart (odd: the column sums read conflict free)
-__host__ __device__ inline size_t fit_scratch_doubles(int G, int TW) {
-    const size_t s = (size_t)fit_rows(G) * (32 * TW + 1);
+// (streaming flavour: one double per WARP of the team, columns TW + 1 doubles apart)
+__host__ __device__ inline size_t fit_scratch_doubles(int G, int TW, bool stream = false) {
+    const size_t s = (size_t)fit_rows(G) * (stream ? TW + 1 : 32 * TW + 1);
     return s > 256 ? s : 256;  // >= 2 KB: the two select histograms live here before the first sweep
 }
 // fixed-size arrays first (sc, bc, pc, mbar at constant offsets from the team base), then the scratch columns
 // (constant offset too: the E-step's stores into them need no G- or cap-dependent address arithmetic), then the
 // G-sized arrays, then - 16-byte aligned - the slab
 constexpr int kFitFixedDoubles = 8 + 8 + 8 + 2;
-__host__ __device__ inline size_t fit_team_header_bytes(int G, int TW) {
-    const size_t bytes = ((size_t)kFitFixedDoubles + fit_scratch_doubles(G, TW) + (G + 4) + 2 * G) * 8 + (size_t)((G + 2) & ~1) * 4;
+__host__ __device__ inline size_t fit_team_header_bytes(int G, int TW, bool stream = false) {
+    const size_t bytes = ((size_t)kFitFixedDoubles + fit_scratch_doubles(G, TW, stream) + (G + 4) + 2 * G) * 8 + (size_t)((G + 2) & ~1) * 4;
     return (bytes + 15) & ~(size_t)15;
 }
-__host__ __device__ inline size_t fit_team_smem_bytes(int cap, int G, int TW) {
+// a streaming team keeps no reads in shared memory: its region is the header alone
+__host__ __device__ inline size_t fit_team_smem_bytes(int cap, int G, int TW, bool stream = false) {
+    if (stream) return fit_team_header_bytes(G, TW, true);
     const size_t bytes = fit_team_header_bytes(G, TW) + (size_t)(cap + 2) * 8 + (size_t)(cap + 2);
     return (bytes + 15) & ~(size_t)15;
 }
 
-inline void fit_fill_layout(FitArgs& a, int TW) {
+inline void fit_fill_layout(FitArgs& a, int TW, bool stream = false) {
     const int G = a.G;
-    a.team_bytes = (int)fit_team_smem_bytes(a.cap, G, TW);
-    a.off_tot = (int)((kFitFixedDoubles + fit_scratch_doubles(G, TW)) * 8);
+    a.team_bytes = (int)fit_team_smem_bytes(a.cap, G, TW, stream);
+    a.off_tot = (int)((kFitFixedDoubles + fit_scratch_doubles(G, TW, stream)) * 8);
     a.off_asm = a.off_tot + (G + 4) * 8;
     a.off_dps = a.off_asm + G * 8;
     a.off_goff = a.off_dps + G * 8;
-    a.off_slab = (int)fit_team_header_bytes(G, TW);
+    a.off_slab = (int)fit_team_header_bytes(G, TW, stream);
     a.off_gid = a.off_slab + (a.cap + 2) * 8;
 }
 
@@ -170,9 +173,10 @@ __device__ __forceinline__ void team_sync(int team) {
 // radix select over the order-preserving 64-bit keys: 8-bit digits, 256-bin histogram (shared-memory
 // integer atomics by the whole team), starting below the common prefix of the smallest and largest
 // key and stopping as soon as one candidate is left.  Exact for any input.  Every warp of the team
-// runs the (cheap) scan redundantly, so no broadcast is needed.
-template <int TW>
-__device__ void team_select2(const double* yv, int n, int r, uint64_t kmin, uint64_t kmax, int* hist, int lane,
+// runs the (cheap) scan redundantly, so no broadcast is needed.  `yv(i)` yields read i: a shared-memory load for a
+// resident position, a decoding global load for a streamed one.
+template <int TW, class YF>
+__device__ void team_select2(YF yv, int n, int r, uint64_t kmin, uint64_t kmax, int* hist, int lane,
                              int tid, int team, double& a, double& b) {
     const uint64_t diff = kmin ^ kmax;
     int hi = diff ? 64 - __clzll((long long)diff) : 0;  // bits [hi,64) are common to every key
@@ -184,7 +188,7 @@ __device__ void team_select2(const double* yv, int n, int r, uint64_t kmin, uint
         for (int j = tid; j < 256; j += TW * 32) hist[j] = 0;
         team_sync<TW>(team);
         for (int i = tid; i < n; i += TW * 32) {
-            const uint64_t k = dkey(yv[i]);
+            const uint64_t k = dkey(yv(i));
             if (hi >= 64 || (k >> hi) == pre) atomicAdd(&hist[(unsigned)(k >> lo) & mask], 1);
         }
         team_sync<TW>(team);
@@ -225,7 +229,7 @@ __device__ void team_select2(const double* yv, int n, int r, uint64_t kmin, uint
     else {  // one candidate left: fetch it
         uint64_t found = 0;
         for (int i = lane; i < n; i += 32) {
-            const uint64_t k = dkey(yv[i]);
+            const uint64_t k = dkey(yv(i));
             if ((k >> hi) == pre) found = k;
         }
         ka = warp_max_u64(found);
@@ -235,7 +239,7 @@ __device__ void team_select2(const double* yv, int n, int r, uint64_t kmin, uint
     if (r + 1 < n && !(hi == 0 && rank + 1 < cnt)) {
         uint64_t mn = ~0ull;
         for (int i = lane; i < n; i += 32) {
-            const uint64_t k = dkey(yv[i]);
+            const uint64_t k = dkey(yv(i));
             if (k > ka && k < mn) mn = k;
         }
         b = keyd(warp_min_u64(mn));
@@ -305,8 +309,8 @@ __device__ void team_select2_u16(const unsigned short* q, int n, int r, const in
     team_sync<TW>(team);  // everybody is done with hist2 before it is cleared again
 }
 
-template <int TW>
-__device__ double team_percentile(const double* yv, int n, double q, uint64_t kmin, uint64_t kmax, int* hist,
+template <int TW, class YF>
+__device__ double team_percentile(YF yv, int n, double q, uint64_t kmin, uint64_t kmax, int* hist,
                                   int lane, int tid, int team) {
     int lo, hi;
     double gamma;
@@ -396,7 +400,12 @@ __device__ __forceinline__ double colsum_first(double t, int G, int lane) {
     return v;
 }
 
-template <int TW, int MAXT>
+// STREAM: the position's reads stay in global memory / L2 and are decoded in every sweep - the class for positions
+// deeper than one CTA's shared memory (the reference has no cap on n, gmm.py:93-127; pooled mode keeps the reads of
+// conditions that failed the count test, io.py:46-58,70-73).  One team (= the CTA) per position; per read the same
+// arithmetic as the resident flavour; per-thread partial sums go through a warp butterfly and one shared-memory entry
+// per warp and column, which the leader adds in warp order (deterministic).
+template <int TW, int MAXT, bool STREAM = false>
 __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // broadcast: warp-uniform for the compiler
@@ -404,7 +413,7 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
     const bool leader = (tw == 0);
     const int G = a.G;
     const int R = fit_rows(G);
-    constexpr int CS = 32 * TW + 1;  // doubles between scratch columns
+    constexpr int CS = STREAM ? TW + 1 : 32 * TW + 1;  // doubles between scratch columns
 
     double* tab_e2 = reinterpret_cast<double*>(smem_raw);
     double2* tab_lg = reinterpret_cast<double2*>(tab_e2 + kTabExpDoubles);
@@ -454,9 +463,9 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
         const int p = a.worklist ? a.worklist[w] : (int)w;
         const int64_t off = a.read_off[p];
         const int n = (int)(a.read_off[p + 1] - off);
-        if (n > a.cap || n <= 0) {  // cannot happen when the host sized the slab from max_reads
+        if ((!STREAM && n > a.cap) || n <= 0) {  // only when the caller understated batch.max_reads
             if (tid == 0) {
-                a.status[p] |= STATUS_SELECTED;
+                a.status[p] = (a.status[p] & (STATUS_TTEST_VALID | STATUS_NEAR_THRESHOLD)) | STATUS_SELECTED | STATUS_NOT_FITTED;
                 a.n_iter[p] = -1;
             }
             continue;
@@ -467,11 +476,13 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
         const int per16 = 16 / eb;                         // elements per 16 bytes
         const int sh = (int)(off & (per16 - 1));           // elements in front of this position
         const uint32_t bytes = (uint32_t)(((n + sh) * eb + 15) & ~15);
-        fence_proxy_async();  // order this team's generic-proxy slab accesses before the async-proxy write
-        team_sync<TW>(team);
-        if (tid == 0) {
-            mbar_expect_tx(mbar, bytes);
-            tma_bulk_g2s(slab, reinterpret_cast<const char*>(a.y) + (off - sh) * eb, bytes, mbar);
+        if (!STREAM) {
+            fence_proxy_async();  // order this team's generic-proxy slab accesses before the async-proxy write
+            team_sync<TW>(team);
+            if (tid == 0) {
+                mbar_expect_tx(mbar, bytes);
+                tma_bulk_g2s(slab, reinterpret_cast<const char*>(a.y) + (off - sh) * eb, bytes, mbar);
+            }
         }
         const double m0 = a.kmer_mean[p];
         const double sd = a.kmer_std[p];
@@ -489,7 +500,7 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
             }
         }
         team_sync<TW>(team);
-        {
+        if (!STREAM) {
             int g = 0, gend = goff[1];
             for (int i = tid; i < n; i += TW * 32) {
                 while (i >= gend) {
@@ -519,8 +530,10 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
             prior_gamma = a0 * xlog(b0) - lga0;  // a0 ln b0 - lgamma(a0)   (gmm.py:334)
         }
 
-        mbar_wait(mbar, parity);
-        parity ^= 1u;
+        if (!STREAM) {
+            mbar_wait(mbar, parity);
+            parity ^= 1u;
+        }
         // decode in place and centre on the k-mer mean.  Scaled integers expand (last step first, so no
         // unread raw bytes are overwritten); doubles move down by the `sh` leading elements of the aligned
         // superset (first step first), so the reads start 16-byte aligned in either case.
@@ -528,7 +541,9 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
         const double rscale = 1.0 / a.y_scale;
         constexpr int TT = TW * 32;
         double med = 0.0, loc1 = 0.0;
-        if (fmt == kYU16) {
+        // read i of a streamed position, decoded and centred exactly as the resident flavour does it in place
+        auto yg = [&](int i) -> double { return y_load_global(a.y, fmt, a.y_scale, rscale, off + i) - m0; };
+        if (!STREAM && fmt == kYU16) {
             // initial locations (gmm.py:39-44) from the integer codes, before the decode overwrites them
             const unsigned short* q = reinterpret_cast<const unsigned short*>(slab) + sh;
             int* hist1 = reinterpret_cast<int*>(scratch);  // scratch is idle until the first sweep
@@ -547,7 +562,7 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
             team_select2_u16<TW>(q, n, lo, hist1, hist2, lane, tid, team, qa, qb);
             loc1 = np_lerp(y_decode((double)qa, a.y_scale, rscale) - m0, y_decode((double)qb, a.y_scale, rscale) - m0, gamma);
         }
-        {
+        if (!STREAM) {
             const int last = ((n - 1) / TT) * TT;
             const int step = (fmt == kYF64) ? TT : -TT;
             for (int i0 = (fmt == kYF64) ? 0 : last; i0 >= 0 && i0 <= last; i0 += step) {
@@ -566,7 +581,18 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
         // totals (and, for the generic select, min/max keys) in one fixed order, whatever the encoding was
         uint64_t kmin = ~0ull, kmax = 0ull;
         double T1 = 0.0, T2 = 0.0;
-        if (fmt == kYU16) {
+        if (STREAM) {
+            for (int i = tid; i < n; i += TT) {
+                const double v = yg(i);
+                const uint64_t k = dkey(v);
+                kmin = k < kmin ? k : kmin;
+                kmax = k > kmax ? k : kmax;
+                T1 += v;
+                T2 = fma(v, v, T2);
+            }
+            kmin = warp_min_u64(kmin);
+            kmax = warp_max_u64(kmax);
+        } else if (fmt == kYU16) {
             for (int i = tid; i < n; i += TT) {
                 const double v = yv[i];
                 T1 += v;
@@ -610,17 +636,24 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
         }
         team_sync<TW>(team);
         // ---- initial locations (gmm.py:39-44) -------------------------------------------------------
-        if (fmt != kYU16) {
+        if (STREAM) {
+            int* hist = reinterpret_cast<int*>(scratch);
+            med = team_percentile<TW>(yg, n, 0.5, kmin, kmax, hist, lane, tid, team);
+            loc1 = team_percentile<TW>(yg, n, (0.0 < med) ? 0.75 : 0.25, kmin, kmax, hist, lane, tid, team);
+        } else if (fmt != kYU16) {
             int* hist = reinterpret_cast<int*>(scratch);  // scratch is idle until the first sweep
-            med = team_percentile<TW>(yv, n, 0.5, kmin, kmax, hist, lane, tid, team);
-            loc1 = team_percentile<TW>(yv, n, (0.0 < med) ? 0.75 : 0.25, kmin, kmax, hist, lane, tid, team);
+            const auto ys = [yv](int i) -> double { return yv[i]; };
+            med = team_percentile<TW>(ys, n, 0.5, kmin, kmax, hist, lane, tid, team);
+            loc1 = team_percentile<TW>(ys, n, (0.0 < med) ? 0.75 : 0.25, kmin, kmax, hist, lane, tid, team);
         }
         team_sync<TW>(team);
         // this thread's row of partial sums.  The groups a thread meets are the same in every sweep, so the
-        // entries it never writes are cleared once per position.
-        double* scol = scratch + tid;  // this thread's entry of column 0
-        for (int g = 0; g < G; ++g) scol[g * CS] = 0.0;
-        const int g_first = gid[0];
+        // entries it never writes are cleared once per position.  (Streaming: entry of this thread's WARP; every
+        // warp writes every column in every sweep.)
+        double* scol = scratch + (STREAM ? tw : tid);  // this thread's entry of column 0
+        if (!STREAM)
+            for (int g = 0; g < G; ++g) scol[g * CS] = 0.0;
+        const int g_first = STREAM ? 0 : gid[0];
 
         // ---- leader state: lanes of parity k hold component k ---------------------------------------
         Comp c = mstep(0.0, 0.0, 0.0, a0, b0);
@@ -762,7 +795,51 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
             // single reads of the tail, so the groups it meets never decrease; its N_g0 partial goes to the
             // scratch column of the group it leaves.  The loop body is branch free.
             double accN = 0.0, S1 = 0.0, S2 = 0.0, Hh = 0.0;
-            {
+            if (STREAM) {
+                // group by group (the reads of a group are contiguous): thread t takes the reads t, t + TT, ... of the
+                // group, two in flight; the group's N_g0 goes through a warp butterfly to the warp's entry of column g
+                EConst K;
+                K.load();
+                for (int g = 0; g < G; ++g) {
+                    const int ge = goff[g + 1];
+                    const double Ag = Asm[g];
+                    double aN = 0.0;
+                    int i = goff[g] + tid;
+                    for (; i + TT < ge; i += 2 * TT) {
+                        const double y0 = yg(i), y1 = yg(i + TT);
+                        const double d0 = fma(y0, fma(C, y0, B), Ag), d1 = fma(y1, fma(C, y1, B), Ag);
+                        double r0, h0, r1, h1;
+                        estep_dev(tab, K, d0, r0, h0);
+                        estep_dev(tab, K, d1, r1, h1);
+                        aN += r0;
+                        aN += r1;
+                        const double w0 = r0 * y0, w1 = r1 * y1;
+                        S1 += w0;
+                        S1 += w1;
+                        S2 = fma(w0, y0, S2);
+                        S2 = fma(w1, y1, S2);
+                        Hh += h0;
+                        Hh += h1;
+                    }
+                    if (i < ge) {
+                        const double y0 = yg(i);
+                        const double d0 = fma(y0, fma(C, y0, B), Ag);
+                        double r0, h0;
+                        estep_dev(tab, K, d0, r0, h0);
+                        aN += r0;
+                        const double w0 = r0 * y0;
+                        S1 += w0;
+                        S2 = fma(w0, y0, S2);
+                        Hh += h0;
+                    }
+                    __syncwarp();
+                    aN = warp_sum(aN);
+                    if (lane == 0) scol[g * CS] = aN;
+                }
+                S1 = warp_sum(S1);
+                S2 = warp_sum(S2);
+                Hh = warp_sum(Hh);
+            } else {
                 EConst K;
                 K.load();
                 unsigned pg = g_first;  // group of this thread's last read; accN goes to column pg on leaving it
@@ -829,7 +906,7 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
 #undef XP_READ
                 scol[pg * CS] = accN;
             }
-            {
+            if (!STREAM || lane == 0) {
                 double* sg = scol + G * CS;
                 sg[0] = S1;
                 sg[CS] = S2;
@@ -839,16 +916,16 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
             if (leader) {
                 // column sums of the rows of partial sums (several lanes per column when there are few columns)
                 double n0;
-                if (R <= 8) {
+                if (!STREAM && R <= 8) {
                     const double t = team_colsum<TW, 4>(scratch, R, lane);
                     if (lane < R) tot[lane] = t;
                     n0 = colsum_first<4>(t, G, lane);
-                } else if (R <= 16) {
+                } else if (!STREAM && R <= 16) {
                     const double t = team_colsum<TW, 2>(scratch, R, lane);
                     if (lane < R) tot[lane] = t;
                     n0 = colsum_first<2>(t, G, lane);
                 } else {
-                    constexpr int NC = 32 * TW;
+                    constexpr int NC = STREAM ? TW : 32 * TW;  // entries per column
                     for (int r0 = 0; r0 < R; r0 += 32) {
                         const int row = r0 + lane;
                         double t0 = 0.0, t1 = 0.0;
@@ -898,7 +975,7 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
             if (lane == 0) {
                 out[FIT_ELBO] = elbo;
                 a.n_iter[p] = it;
-                a.status[p] = (a.status[p] & STATUS_TTEST_VALID) | st;
+                a.status[p] = (a.status[p] & (STATUS_TTEST_VALID | STATUS_NEAR_THRESHOLD)) | st;
             }
             for (int s = lane; s < 2 * G; s += 32) {
                 const int g = s >> 1;

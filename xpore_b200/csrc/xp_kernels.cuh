@@ -424,6 +424,9 @@ __global__ void __launch_bounds__(WARPS * 32, 6) xp_prefilter_kernel(PrefilterAr
             st |= STATUS_TTEST_VALID;
         }
         if (pv != pv || pv < a.threshold) st |= STATUS_SELECTED;  // diffmod.py:54
+        // a p-value this close to the threshold could fall on the other side of it under another (equally accurate)
+        // evaluation of the incomplete beta function: flagged for the host (bit-exact selection)
+        if (fabs(pv - a.threshold) <= 1e-9 * a.threshold) st |= STATUS_NEAR_THRESHOLD;
         a.pval[p] = pv;
         a.status[p] = st;
     }
@@ -454,8 +457,8 @@ struct WorklistArgs {
     int32_t* worklist;   // [P]
     uint32_t* n_large;   // [1] entries of the worklist with at least `split` reads (they come first)
     int split;           // a bucket boundary (see cost_bucket), or 0: no large class
-    uint32_t* n_mid;     // [1] entries with at least `split2` reads (large ones included); = n_large when split2 = 0
-    int split2;          // a bucket boundary below `split`, or 0: no small class
+    uint32_t* n_deep;    // [1] entries with at least `split_deep` reads (the first ones of the worklist)
+    int split_deep;      // a bucket boundary above `split`, or 0: no streaming class
 };
 
 __global__ void xp_worklist_count(WorklistArgs a) {
@@ -488,7 +491,7 @@ __global__ void xp_worklist_scan(WorklistArgs a) {  // <<<1, kBuckets>>>
     const uint32_t nl = a.split > 0 ? s[cost_bucket(a.split)] : 0u;
     if (t == 0) {
         *a.n_large = nl;
-        *a.n_mid = a.split2 > 0 ? s[cost_bucket(a.split2)] : nl;
+        *a.n_deep = a.split_deep > 0 ? s[cost_bucket(a.split_deep)] : 0u;
     }
 }
 
@@ -636,6 +639,47 @@ __global__ void xp_pack_rows_kernel(PackRowsArgs a) {
             for (int c = lane; c < a.FW; c += 32) o[4 + c] = f[c];
             for (int c = lane; c < a.SW; c += 32) o[4 + a.FW + c] = t[c];
         }
+    }
+}
+
+// Rows of several chunks (xpb200_fit_host_rows_async: chunk c's rows sit at row chunk_start[c] of `rows`, n_rows[c] of
+// them) concatenated in chunk order into `out`; one warp per row.  out_counts = {rows needed, positions fitted}.
+constexpr int kMaxRowChunks = 64;
+struct ConcatRowsArgs {
+    const double* rows;
+    const unsigned int* n_rows;    // [n_chunks]
+    const unsigned int* n_fitted;  // [n_chunks]
+    int n_chunks, RW;
+    long long capacity;
+    int chunk_start[kMaxRowChunks];
+    double* out;
+    unsigned int* out_counts;  // [2]
+};
+
+__global__ void xp_concat_rows_kernel(ConcatRowsArgs a) {
+    __shared__ unsigned int s_first[kMaxRowChunks + 1];  // first output row of every chunk
+    if (threadIdx.x == 0) {
+        unsigned int acc = 0, fitted = 0;
+        for (int c = 0; c < a.n_chunks; ++c) {
+            s_first[c] = acc;
+            acc += a.n_rows[c];
+            fitted += a.n_fitted[c];
+        }
+        s_first[a.n_chunks] = acc;
+        if (blockIdx.x == 0) {
+            a.out_counts[0] = acc;
+            a.out_counts[1] = fitted;
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const long long total = min((long long)s_first[a.n_chunks], a.capacity);
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < total; row += (long long)gridDim.x * wpb) {
+        int c = 0;
+        while (row >= (long long)s_first[c + 1]) ++c;
+        const double* src = a.rows + ((size_t)a.chunk_start[c] + (size_t)(row - s_first[c])) * a.RW;
+        double* dst = a.out + (size_t)row * a.RW;
+        for (int k = lane; k < a.RW; k += 32) dst[k] = src[k];
     }
 }
 

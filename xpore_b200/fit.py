@@ -25,6 +25,7 @@ from . import _lib
 from .batch import Batch
 
 SELECTED, CONVERGED, ELBO_DECREASED, HIT_MAX, KEEP_ROW, MOD_IS_1, HIGHER, TTEST_VALID = 1, 2, 4, 8, 16, 32, 64, 128
+NOT_FITTED, NEAR_THRESHOLD = 256, 512
 FIT_MU, FIT_LAM, FIT_ALPHA, FIT_BETA, FIT_ELBO, FIT_N = 0, 2, 4, 6, 8, 9
 ST_MU, ST_S2, ST_CONF, ST_POV, ST_CDF, ST_RATE = 0, 2, 4, 6, 7, 11
 
