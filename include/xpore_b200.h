@@ -149,6 +149,11 @@ int32_t xpb200_fit_host_rows_async(int32_t device, const xpb200_batch* batch, co
                                    double* rows_dev, int64_t capacity_rows, int64_t index_offset, uint32_t* counts_dev,
                                    void* cuda_stream);
 
+/* Page-locked host memory for the buffers of the host entry points (copies from / to it are asynchronous and run at
+ * full PCIe rate); NULL when no CUDA device is usable.  Free with xpb200_host_free. */
+void* xpb200_host_alloc(size_t bytes);
+void xpb200_host_free(void* p);
+
 /* Release the cached device buffers of xpb200_fit_host (all devices). */
 void xpb200_release(void);
 
@@ -235,6 +240,13 @@ int32_t xpb200_ingest_genes(void* handle, int32_t n_genes, const int64_t* starts
                             int32_t n_threads, int64_t* n_positions, int64_t* n_reads, int64_t* string_bytes);
 int32_t xpb200_ingest_copy(void* handle, double* y, int64_t* read_off, int32_t* grp_len, int32_t* kmer_row,
                            int32_t* gene_of_position, char* strings);
+/* Encoding the reads of the last xpb200_ingest_genes call can travel in: XPB200_Y_U16 when every literal was a
+ * non-negative decimal with at most two fraction digits below 655.36 (what dataprep writes, dataprep.py:638) - the
+ * codes q = 100 y are taken from the text itself, and q / 100.0 is bit for bit the double xpb200_ingest_copy yields -
+ * else XPB200_Y_F64.  *max_reads (optional) = reads of the deepest position.  xpb200_ingest_copy_u16 writes the codes
+ * (yq[n_reads]; pad the buffer to a multiple of 8 elements for xpb200_batch). */
+int32_t xpb200_ingest_encoding(void* handle, int32_t* max_reads);
+int32_t xpb200_ingest_copy_u16(void* handle, uint16_t* yq);
 void xpb200_ingest_close(void* handle);
 const char* xpb200_ingest_last_error(void);
 

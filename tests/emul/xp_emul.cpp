@@ -88,8 +88,14 @@ void emul_fit(int n, const double* y, int G, const int* glen, double km, double 
         percentile_index(n, q, lo, hi, gamma);
         return np_lerp(sorted[lo], sorted[hi], gamma);
     };
-    const double med = pct(0.5);
-    const double loc1 = pct(0.0 < med ? 0.75 : 0.25);
+    bool up;
+    {
+        int lo, hi;
+        double gamma;
+        percentile_index(n, 0.5, lo, hi, gamma);
+        up = prior_below_median(sorted[lo] + km, sorted[hi] + km, gamma, km);  // as the kernel's generic path
+    }
+    const double loc1 = pct(up ? 0.75 : 0.25);
 
     Comp c[2];
     c[0] = mstep(0, 0, 0, a0, b0);

@@ -80,6 +80,22 @@ def test_oracle_on_big_golden_sample():
             np.testing.assert_allclose(f["N"], gf["N"], rtol=1e-12, atol=1e-300)
 
 
+@pytest.mark.parametrize("name", ["c1", "c5"])
+def test_kernel_arithmetic_on_big_golden(name):
+    """The host build of the kernels' arithmetic (tests/emul) against the reference on every position of two shapes:
+    the same selection, sweep counts and parameters.  (c5 holds a position whose median read equals the k-mer mean:
+    the reference's choice of the second start location, gmm.py:39-44, then hangs on the rounding of numpy's lerp.)"""
+    from helpers import emul_fit_batch, load_emulator
+    spec, batch, gold = load_shape(name)
+    method = xf.Method.from_dict(spec.method)
+    res = emul_fit_batch(load_emulator(), batch, method)
+    f = gold["fitted"]
+    np.testing.assert_array_equal(res.selected, f)
+    np.testing.assert_array_equal(res.n_iter[f], gold["n_iter"][f])
+    par = np.concatenate([res.mu, res.lam, res.alpha, res.beta], axis=1)
+    np.testing.assert_allclose(par[f], gold["params"][f], rtol=1e-9)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", SHAPES)
 def test_cuda_path_on_big_golden(name):
@@ -99,7 +115,8 @@ def test_cuda_path_on_big_golden(name):
         ok = ~np.isnan(gold["pval"])
         assert (np.isnan(res.pval) == ~ok).all()
         np.testing.assert_allclose(res.pval[ok], gold["pval"][ok], rtol=1e-4)
-        print("%s: max rel. deviation of the t-test p-value %.2e" % (name, np.max(np.abs(res.pval[ok] / gold["pval"][ok] - 1))))
+        if ok.any():
+            print("%s: max rel. deviation of the t-test p-value %.2e" % (name, np.max(np.abs(res.pval[ok] / gold["pval"][ok] - 1))))
     fitted = np.nonzero(gold["fitted"])[0]
     # sweep counts, convergence flags, posterior parameters: every fitted position
     same = int((res.n_iter[fitted] == gold["n_iter"][fitted]).sum())

@@ -1,8 +1,9 @@
+# usage: bash tools/gpu_round.sh <tag> [configs...]: GPU tests, then short bench lines (no CPU baseline) of the configs
 set -x
 D=gpurun_out/$1
+shift
 mkdir -p $D
-timeout 600 python -m pytest tests -m gpu -x -q > $D/tests.log 2>&1; echo "tests rc=$?" >> $D/tests.log
-timeout 300 python bench.py --config c2 --no-cpu-baseline > $D/bench_c2.log 2>&1
-timeout 300 python bench.py --config c3 --no-cpu-baseline > $D/bench_c3.log 2>&1
-timeout 300 python bench.py --config c4 --no-cpu-baseline > $D/bench_c4.log 2>&1
-tail -3 $D/tests.log
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm --format=csv > $D/nvsmi.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q -s > $D/tests.log 2>&1; echo "tests rc=$?" >> $D/tests.log
+for c in "$@"; do timeout 400 python bench.py --config $c --no-cpu-baseline > $D/bench_$c.log 2>&1; done
+tail -5 $D/tests.log

@@ -47,6 +47,7 @@ EXPORTS = ["xpb200_fit_width", "xpb200_stats_width", "xpb200_workspace_bytes", "
            "xpb200_set_stage_timing", "xpb200_get_stage_ms", "xpb200_pack_records",
            "xpb200_debug_fill_smem", "xpb200_last_error", "xpb200_version",
            "xpb200_ingest_open", "xpb200_ingest_genes", "xpb200_ingest_copy", "xpb200_ingest_close",
+           "xpb200_ingest_encoding", "xpb200_ingest_copy_u16", "xpb200_host_alloc", "xpb200_host_free",
            "xpb200_ingest_last_error"]
 
 
@@ -115,6 +116,14 @@ def lib():
                                           C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.xpb200_ingest_copy.restype = C.c_int32
         L.xpb200_ingest_copy.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.xpb200_ingest_encoding.restype = C.c_int32
+        L.xpb200_ingest_encoding.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+        L.xpb200_ingest_copy_u16.restype = C.c_int32
+        L.xpb200_ingest_copy_u16.argtypes = [C.c_void_p, C.c_void_p]
+        L.xpb200_host_alloc.restype = C.c_void_p
+        L.xpb200_host_alloc.argtypes = [C.c_size_t]
+        L.xpb200_host_free.restype = None
+        L.xpb200_host_free.argtypes = [C.c_void_p]
         L.xpb200_ingest_close.restype = None
         L.xpb200_ingest_close.argtypes = [C.c_void_p]
         L.xpb200_ingest_last_error.restype = C.c_char_p

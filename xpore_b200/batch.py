@@ -87,6 +87,10 @@ class Batch:
     y_enc: np.ndarray | None = None
     y_format: int = 0
     y_scale: float = 1.0
+    # set by the native reader: lazily decoded keys, row of every position's k-mer in the model, deepest position
+    keys: object = None
+    kmer_row: np.ndarray | None = None
+    max_reads: int | None = None
 
     @property
     def n_positions(self) -> int:
@@ -100,9 +104,12 @@ class Batch:
         P, G = self.grp_len.shape
         assert G == self.layout.n_groups
         assert self.read_off.shape == (P + 1,) and self.read_off.dtype == np.int64
-        assert self.grp_len.dtype == np.int32 and self.y.dtype == np.float64
+        assert self.grp_len.dtype == np.int32
         assert (np.diff(self.read_off) == self.grp_len.sum(axis=1)).all()
-        assert self.y.shape[0] >= self.read_off[-1]
+        if self.y is None:  # staged batch: only the scaled-integer codes exist (NativeIngest.read(staging=...))
+            assert self.y_enc is not None and self.y_format != 0 and self.y_enc.shape[0] >= self.read_off[-1]
+        else:
+            assert self.y.dtype == np.float64 and self.y.shape[0] >= self.read_off[-1]
         assert self.kmer_mean.shape == (P,) and self.kmer_std.shape == (P,)
         return self
 

@@ -277,6 +277,18 @@ int32_t xpb200_fit_width(int32_t G) { return xpc::fit_width(G); }
 int32_t xpb200_stats_width(int32_t G, int32_t C) { return xpc::stats_width(G, C); }
 size_t xpb200_workspace_bytes(int32_t P) { return ws_fixed_bytes() + (size_t)std::max(P, 1) * 4; }
 
+void* xpb200_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        g_err = std::string("cudaHostAlloc: ") + cudaGetErrorString(cudaGetLastError());
+        return nullptr;
+    }
+    return p;
+}
+void xpb200_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 int32_t xpb200_deep_split(int32_t G) {
     if (G < 1 || G > xpk::kMaxGroups) return fail(XPB200_EINVAL, "n_groups must be 1..64");
     return deep_class_split(G);

@@ -197,6 +197,12 @@ XP_HD double np_lerp(double a, double b, double t) {
     const double d = b - a;
     return (t >= 0.5) ? (b - d * (1.0 - t)) : (a + d * t);
 }
+// gmm.py:39-44 picks the second start location by `loc0 < np.percentile(y, 50)`.  When the median of the reads equals
+// the k-mer mean mathematically (2-decimal reads around a 2-decimal model mean: it happens), the reference's choice
+// between P75 and P25 hangs on the rounding of numpy's lerp of the UNCENTRED order statistics - so that very expression
+// is evaluated here, on the uncentred values ya <= yb (for reads within a factor two of m0, y' + m0 restores y exactly;
+// any other median is far from the tie).
+XP_HD bool prior_below_median(double ya, double yb, double gamma, double m0) { return m0 < np_lerp(ya, yb, gamma); }
 // virtual index (n-1)*q is exact for q in {.25,.5,.75}
 XP_HD void percentile_index(int n, double q, int& lo, int& hi, double& gamma) {
     const double h = (double)(n - 1) * q;

@@ -309,13 +309,18 @@ __device__ void team_select2_u16(const unsigned short* q, int n, int r, const in
     team_sync<TW>(team);  // everybody is done with hist2 before it is cleared again
 }
 
+// The two start locations' inputs from centred reads (gmm.py:39-44): returns loc1' = P75 or P25 of y', chosen by the
+// reference's own comparison on the uncentred median (xp_core.cuh:prior_below_median).
 template <int TW, class YF>
-__device__ double team_percentile(YF yv, int n, double q, uint64_t kmin, uint64_t kmax, int* hist,
-                                  int lane, int tid, int team) {
+__device__ double team_second_location(YF yv, int n, double m0, uint64_t kmin, uint64_t kmax, int* hist,
+                                       int lane, int tid, int team) {
     int lo, hi;
     double gamma;
-    percentile_index(n, q, lo, hi, gamma);
+    percentile_index(n, 0.5, lo, hi, gamma);
     double a, b;
+    team_select2<TW>(yv, n, lo, kmin, kmax, hist, lane, tid, team, a, b);
+    const bool up = prior_below_median(a + m0, b + m0, gamma, m0);
+    percentile_index(n, up ? 0.75 : 0.25, lo, hi, gamma);
     team_select2<TW>(yv, n, lo, kmin, kmax, hist, lane, tid, team, a, b);
     return np_lerp(a, b, gamma);
 }
@@ -540,7 +545,7 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
         double* yv = slab;
         const double rscale = 1.0 / a.y_scale;
         constexpr int TT = TW * 32;
-        double med = 0.0, loc1 = 0.0;
+        double loc1 = 0.0;
         // read i of a streamed position, decoded and centred exactly as the resident flavour does it in place
         auto yg = [&](int i) -> double { return y_load_global(a.y, fmt, a.y_scale, rscale, off + i) - m0; };
         if (!STREAM && fmt == kYU16) {
@@ -557,8 +562,8 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
             unsigned qa, qb;
             percentile_index(n, 0.5, lo, hi, gamma);
             team_select2_u16<TW>(q, n, lo, hist1, hist2, lane, tid, team, qa, qb);
-            med = np_lerp(y_decode((double)qa, a.y_scale, rscale) - m0, y_decode((double)qb, a.y_scale, rscale) - m0, gamma);
-            percentile_index(n, (0.0 < med) ? 0.75 : 0.25, lo, hi, gamma);
+            const bool up = prior_below_median(y_decode((double)qa, a.y_scale, rscale), y_decode((double)qb, a.y_scale, rscale), gamma, m0);
+            percentile_index(n, up ? 0.75 : 0.25, lo, hi, gamma);
             team_select2_u16<TW>(q, n, lo, hist1, hist2, lane, tid, team, qa, qb);
             loc1 = np_lerp(y_decode((double)qa, a.y_scale, rscale) - m0, y_decode((double)qb, a.y_scale, rscale) - m0, gamma);
         }
@@ -638,13 +643,11 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
         // ---- initial locations (gmm.py:39-44) -------------------------------------------------------
         if (STREAM) {
             int* hist = reinterpret_cast<int*>(scratch);
-            med = team_percentile<TW>(yg, n, 0.5, kmin, kmax, hist, lane, tid, team);
-            loc1 = team_percentile<TW>(yg, n, (0.0 < med) ? 0.75 : 0.25, kmin, kmax, hist, lane, tid, team);
+            loc1 = team_second_location<TW>(yg, n, m0, kmin, kmax, hist, lane, tid, team);
         } else if (fmt != kYU16) {
             int* hist = reinterpret_cast<int*>(scratch);  // scratch is idle until the first sweep
             const auto ys = [yv](int i) -> double { return yv[i]; };
-            med = team_percentile<TW>(ys, n, 0.5, kmin, kmax, hist, lane, tid, team);
-            loc1 = team_percentile<TW>(ys, n, (0.0 < med) ? 0.75 : 0.25, kmin, kmax, hist, lane, tid, team);
+            loc1 = team_second_location<TW>(ys, n, m0, kmin, kmax, hist, lane, tid, team);
         }
         team_sync<TW>(team);
         // this thread's row of partial sums.  The groups a thread meets are the same in every sweep, so the

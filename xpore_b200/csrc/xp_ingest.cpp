@@ -40,6 +40,11 @@ struct ReadsRef {  // reads of one (position, kmer) in one run: a slice of the r
 
 struct RunGene {  // one gene of one run, parsed
     std::vector<double> pool;
+    // the same reads as scaled integers q = 100 y while every literal so far is a non-negative decimal with at most two
+    // fraction digits below 655.36 (what dataprep writes, dataprep.py:638): q / 100.0 is then the very double in `pool`
+    // (both are the correctly rounded value of the same rational), and the batch can travel as 2 bytes per read
+    std::vector<uint16_t> qpool;
+    bool all_q = true;
     // (position, kmer) -> slice; string_views point into the raw JSON text held by the caller
     std::map<std::pair<std::string_view, std::string_view>, ReadsRef> pairs;
 };
@@ -78,7 +83,7 @@ struct Cursor {
 // m / 10^k with m < 2^53 and 10^k exact in a double, so one IEEE division gives the correctly rounded
 // value - the same double strtod / Python's float() return.  Anything else (exponents, long
 // mantissas) goes through std::from_chars, which is correctly rounded as well.
-inline bool parse_number(const char*& p, const char* end, double& out) {
+inline bool parse_number(const char*& p, const char* end, double& out, uint32_t& qv, bool& q_ok) {
     static const double kPow10[] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
     const char* q = p;
     bool neg = false;
@@ -110,8 +115,12 @@ inline bool parse_number(const char*& p, const char* end, double& out) {
         const double v = (double)m / kPow10[frac];
         out = neg ? -v : v;
         p = q;
+        const unsigned long long scaled = frac == 0 ? m * 100 : frac == 1 ? m * 10 : m;
+        q_ok = !neg && frac <= 2 && scaled < 65536;
+        qv = (uint32_t)scaled;
         return true;
     }
+    q_ok = false;
     auto r = std::from_chars(p, end, out);
     if (r.ec != std::errc()) return false;
     p = r.ptr;
@@ -122,6 +131,7 @@ inline bool parse_number(const char*& p, const char* end, double& out) {
 bool parse_gene(const char* text, size_t len, RunGene& g, std::string& err) {
     Cursor c{text, text + len};
     g.pool.reserve(len / 6 + 16);
+    g.qpool.reserve(len / 6 + 16);
     std::string_view idx;
     if (!c.eat('{') || !c.str(idx) || !c.eat(':') || !c.eat('{')) {
         err = "data.json: expected {\"<idx>\":{";
@@ -146,11 +156,20 @@ bool parse_gene(const char* text, size_t len, RunGene& g, std::string& err) {
                         for (;;) {
                             c.ws();
                             double v;
-                            if (!parse_number(c.p, c.end, v)) {
+                            uint32_t qv = 0;
+                            bool q_ok = false;
+                            if (!parse_number(c.p, c.end, v, qv, q_ok)) {
                                 err = "data.json: bad number";
                                 return false;
                             }
                             g.pool.push_back(v);
+                            if (g.all_q) {
+                                if (q_ok) g.qpool.push_back((uint16_t)qv);
+                                else {
+                                    g.all_q = false;
+                                    g.qpool.clear();
+                                }
+                            }
                             if (c.eat(',')) continue;
                             if (c.eat(']')) break;
                             err = "data.json: expected , or ] in a read list";
@@ -193,6 +212,9 @@ bool all_digits(std::string_view s, long long& v) {
 
 struct GeneOut {  // selected positions of one gene
     std::vector<double> y;
+    std::vector<uint16_t> yq;       // the same reads as u16 codes when all_q
+    bool all_q = true;
+    int32_t max_reads = 0;
     std::vector<int32_t> grp_len;   // [npos * G]
     std::vector<int32_t> kmer_row;  // [npos]
     std::string strings;            // position \0 kmer \0 ...
@@ -207,6 +229,8 @@ struct Ingest {
     std::vector<int> fds;  // pread() is thread-safe: no lock around the reads
     std::unordered_map<std::string, int> kmer_row;
     std::vector<GeneOut> genes;
+    bool all_q = false;     // every read of the last xpb200_ingest_genes call has a u16 code
+    int32_t max_reads = 0;  // deepest position of that call
 };
 
 void process_gene(Ingest& in, const int64_t* starts, const int64_t* ends, GeneOut& out) {
@@ -231,6 +255,7 @@ void process_gene(Ingest& in, const int64_t* starts, const int64_t* ends, GeneOu
         have.push_back(r);
     }
     if (have.empty()) return;
+    for (int r : have) out.all_q = out.all_q && rg[r].all_q;
     // (position, kmer) pairs present in every run that has the gene (io.py:31-39), in table order
     struct Key {
         int cls;
@@ -291,19 +316,25 @@ void process_gene(Ingest& in, const int64_t* starts, const int64_t* ends, GeneOu
             return;
         }
         // reads: per group slot contiguous, slots in order; inside a slot run by run in config order
+        auto emit = [&](const std::pair<int, ReadsRef>& o) {
+            const RunGene& src = rg[o.first];
+            if (out.all_q)
+                out.yq.insert(out.yq.end(), src.qpool.begin() + (long)o.second.begin,
+                              src.qpool.begin() + (long)(o.second.begin + o.second.n));
+            else
+                out.y.insert(out.y.end(), src.pool.begin() + (long)o.second.begin,
+                             src.pool.begin() + (long)(o.second.begin + o.second.n));
+        };
         if (in.pooling) {
             for (int c = 0; c < C; ++c)
                 for (const auto& o : order)
-                    if (in.run_cond[o.first] == c && o.second.n)
-                        out.y.insert(out.y.end(), rg[o.first].pool.begin() + (long)o.second.begin,
-                                     rg[o.first].pool.begin() + (long)(o.second.begin + o.second.n));
+                    if (in.run_cond[o.first] == c && o.second.n) emit(o);
         } else {
             for (int s = 0; s < G; ++s)
                 for (const auto& o : order)
-                    if (in.run_slot[o.first] == s && o.second.n)
-                        out.y.insert(out.y.end(), rg[o.first].pool.begin() + (long)o.second.begin,
-                                     rg[o.first].pool.begin() + (long)(o.second.begin + o.second.n));
+                    if (in.run_slot[o.first] == s && o.second.n) emit(o);
         }
+        out.max_reads = std::max<long long>(out.max_reads, total);
         out.grp_len.insert(out.grp_len.end(), glen.begin(), glen.end());
         out.kmer_row.push_back(it->second);
         out.strings.append(k.pos.data(), k.pos.size());
@@ -380,14 +411,18 @@ int32_t xpb200_ingest_genes(void* handle, int32_t n_genes, const int64_t* starts
     work();
     for (auto& t : pool) t.join();
     int64_t P = 0, Rd = 0, S = 0;
+    in->all_q = true;
+    in->max_reads = 0;
     for (const GeneOut& g : in->genes) {
         if (!g.err.empty()) {
             g_ingest_err = g.err;
             return XPB200_EINVAL;
         }
         P += g.npos;
-        Rd += (int64_t)g.y.size();
+        Rd += (int64_t)(g.all_q ? g.yq.size() : g.y.size());
         S += (int64_t)g.strings.size();
+        in->all_q = in->all_q && g.all_q;
+        in->max_reads = std::max(in->max_reads, g.max_reads);
     }
     if (n_positions) *n_positions = P;
     if (n_reads) *n_reads = Rd;
@@ -407,7 +442,12 @@ int32_t xpb200_ingest_copy(void* handle, double* y, int64_t* read_off, int32_t* 
     read_off[0] = 0;
     for (size_t gi = 0; gi < in->genes.size(); ++gi) {
         const GeneOut& g = in->genes[gi];
-        if (y && !g.y.empty()) memcpy(y + r, g.y.data(), g.y.size() * sizeof(double));
+        const size_t nr = g.all_q ? g.yq.size() : g.y.size();
+        if (y) {
+            if (g.all_q)
+                for (size_t i = 0; i < nr; ++i) y[r + (int64_t)i] = (double)g.yq[i] / 100.0;
+            else if (nr) memcpy(y + r, g.y.data(), nr * sizeof(double));
+        }
         if (grp_len && g.npos) memcpy(grp_len + p * G, g.grp_len.data(), g.grp_len.size() * sizeof(int32_t));
         if (kmer_row && g.npos) memcpy(kmer_row + p, g.kmer_row.data(), g.kmer_row.size() * sizeof(int32_t));
         if (strings && !g.strings.empty()) memcpy(strings + s, g.strings.data(), g.strings.size());
@@ -420,8 +460,29 @@ int32_t xpb200_ingest_copy(void* handle, double* y, int64_t* read_off, int32_t* 
             if (gene_of_position) gene_of_position[p + k] = (int32_t)gi;
         }
         p += g.npos;
-        r += (int64_t)g.y.size();
+        r += (int64_t)nr;
         s += (int64_t)g.strings.size();
+    }
+    return XPB200_OK;
+}
+
+int32_t xpb200_ingest_encoding(void* handle, int32_t* max_reads) {
+    Ingest* in = static_cast<Ingest*>(handle);
+    if (!in) return XPB200_EINVAL;
+    if (max_reads) *max_reads = in->max_reads;
+    return in->all_q ? XPB200_Y_U16 : XPB200_Y_F64;
+}
+
+int32_t xpb200_ingest_copy_u16(void* handle, uint16_t* yq) {
+    Ingest* in = static_cast<Ingest*>(handle);
+    if (!in || !yq || !in->all_q) {
+        g_ingest_err = "xpb200_ingest_copy_u16: no u16 encoding of the last xpb200_ingest_genes call";
+        return XPB200_EINVAL;
+    }
+    int64_t r = 0;
+    for (const GeneOut& g : in->genes) {
+        if (!g.yq.empty()) memcpy(yq + r, g.yq.data(), g.yq.size() * sizeof(uint16_t));
+        r += (int64_t)g.yq.size();
     }
     return XPB200_OK;
 }

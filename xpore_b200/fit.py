@@ -111,6 +111,8 @@ class FitResult:
 
 
 def _max_reads(batch: Batch) -> int:
+    if getattr(batch, "max_reads", None) is not None:
+        return int(batch.max_reads)
     return int(np.diff(batch.read_off).max()) if batch.n_positions else 0
 
 
@@ -153,10 +155,12 @@ def fit_batch(batch: Batch, method: Method, device: int = 0) -> FitResult:
     return res
 
 
-def fit_rows(batch: Batch, method: Method, device: int = 0, capacity_rows: int | None = None):
+def fit_rows(batch: Batch, method: Method, device: int = 0, capacity_rows: int | None = None, staging=None):
     """Rows of ``diffmod.table`` only (``xpb200_fit_host_rows``): ``(records, n_fitted)`` with ``records`` the
     ``[n_rows, 4+FW+SW]`` matrix ``[position, status, n_iter, pval, fit, stats]`` of the positions that were
-    fitted and pass the reference's row filter, ascending by position (``dist.unpack_records`` splits it)."""
+    fitted and pass the reference's row filter, ascending by position (``dist.unpack_records`` splits it).
+    ``staging`` (:class:`xpore_b200.ingest.Staging`): take the record buffer from its page-locked memory - the
+    returned matrix is then a view that the next call with the same staging overwrites."""
     L = _lib.lib()
     P, G, Cn = batch.n_positions, batch.layout.n_groups, batch.layout.n_conditions
     y, yfmt, yscale = _y_buffer(batch)
@@ -167,7 +171,8 @@ def fit_rows(batch: Batch, method: Method, device: int = 0, capacity_rows: int |
     gc = np.ascontiguousarray(batch.layout.grp_cond, dtype=np.int32)
     W = 4 + fit_width(G) + stats_width(G, Cn)
     cap = P if capacity_rows is None else int(capacity_rows)
-    rows = np.empty((max(cap, 1), W), dtype=np.float64)
+    rows = staging.array("rows", np.float64, (max(cap, 1), W)) if staging is not None else \
+        np.empty((max(cap, 1), W), dtype=np.float64)
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
     b = _lib.XpBatch(P, G, Cn, _max_reads(batch), batch.n_reads, ptr(y), ptr(read_off), ptr(grp_len), ptr(km),
                      ptr(ks), ptr(gc), yfmt, 0, yscale)
