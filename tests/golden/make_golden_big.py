@@ -9,7 +9,7 @@ The inputs are not stored: they are regenerated from the seed by ``xpore_b200.sy
 * for every FITTED position: n_iterations, converged, location / lambda / alpha / beta, N[g][k] in this
   repository's slot order (NaN where a group is absent);
 * the rows ``io.generate_result_table`` emitted (the reference can only produce the rows that pass its filter,
-  io.py:363-367): position index + the numeric cells (NaN for empty cells) + mod_assignment.
+  io.py:363-367): position index + the numeric cells (row_none marks the empty ones) + mod_assignment.
 
 Runs only in the build container (needs ``/root/reference``):
 
@@ -170,7 +170,7 @@ def run_shape(name, spec, procs):
     converged = np.zeros(P, bool)
     params = np.full((P, 8), np.nan)
     N = np.full((P, G, 2), np.nan)
-    row_pos, row_vals, row_assign = [], [], []
+    row_pos, row_vals, row_assign, row_none = [], [], [], []
     num_cols = [i for i, h in enumerate(header) if i >= 3 and h != "mod_assignment"]
     a_col = header.index("mod_assignment")
     for gi, fits, rows, pvals in sorted(results, key=lambda t: t[0]):
@@ -190,6 +190,7 @@ def run_shape(name, spec, procs):
         for r in rows:
             row_pos.append(index_of[(r[1], r[2])])
             row_vals.append([np.nan if r[i] is None else float(r[i]) for i in num_cols])
+            row_none.append([r[i] is None for i in num_cols])
             row_assign.append(r[a_col])
     out = os.path.join(HERE, "big")
     os.makedirs(out, exist_ok=True)
@@ -197,6 +198,7 @@ def run_shape(name, spec, procs):
                         fitted=fitted, pval=pval, n_iter=n_iter, converged=converged, params=params, N=N,
                         row_pos=np.asarray(row_pos, np.int64), row_vals=np.asarray(row_vals, float).reshape(len(row_pos), len(num_cols)),
                         row_higher=np.asarray([a == "higher" for a in row_assign], bool),
+                        row_none=np.asarray(row_none, bool).reshape(len(row_pos), len(num_cols)),
                         versions=np.array([np.__version__, __import__("scipy").__version__]))
     print(name, "positions", P, "fitted", int(fitted.sum()), "rows", len(row_pos), "max sweeps", int(n_iter.max()))
 

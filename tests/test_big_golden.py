@@ -142,8 +142,8 @@ def test_cuda_path_on_big_golden(name):
     knife = bound = 0
     for j, p in enumerate(gold["row_pos"]):
         exp = list(row_of[int(p)][:3]) + [None] * (len(header) - 3)
-        for c, v in zip(num_cols, gold["row_vals"][j]):
-            exp[c] = None if np.isnan(v) else float(v)
+        for c, v, none in zip(num_cols, gold["row_vals"][j], gold["row_none"][j]):
+            exp[c] = None if none else float(v)
         exp[a_col] = "higher" if gold["row_higher"][j] else "lower"
         knife += compare_row_cells(exp[:3], header, row_of[int(p)], exp, lay, pm)
         bound += half_integer_tests(batch, int(p))

@@ -31,6 +31,8 @@ def parse_options(argv):
     p.add_argument("--csr_cache", dest="csr_cache", default=None,
                    help="binary CSR cache of the inputs (xpore_b200.csrcache): read instead of data.json when it "
                         "matches the inputs, written on first use otherwise.")
+    p.add_argument("--timing", dest="timing", default=None,
+                   help="write the wall-clock seconds of the pipeline stages (ingest / GPU call / rows / write) to this JSON file.")
     q = sub.add_parser("postprocessing", help="run mode for post-processing diffmod.table, the result table from "
                                               "differential modification analysis.")
     qreq = q.add_argument_group("required arguments")

@@ -75,23 +75,90 @@ def unpack_records(rec: np.ndarray, fit_w: int, stats_w: int):
 
 
 def gather_records(rec, rank: int, world: int, dst: int = 0):
-    """Gather per-rank record matrices [n_r, W] on ``dst`` (rows ordered by rank).  One tiny
-    all_gather of the counts, then one padded gather — the only collective on the path."""
+    """Gather per-rank record matrices [n_r, W] on ``dst`` (rows ordered by rank): one all-gather of the counts
+    (a single host read), then one padded ``gather`` into a buffer allocated once per call - the only collective on
+    the path.  ``gather_records.last_counts`` holds the per-rank row counts of the last call."""
     import torch
     import torch.distributed as dist
 
     if world == 1:
+        gather_records.last_counts = [int(rec.shape[0])]
         return rec
     n = torch.tensor([rec.shape[0]], dtype=torch.int64, device=rec.device)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n)
-    counts = [int(c.item()) for c in counts]
+    counts = torch.empty(world, dtype=torch.int64, device=rec.device)
+    dist.all_gather_into_tensor(counts, n)
+    counts = counts.tolist()
+    gather_records.last_counts = counts
     m = max(max(counts), 1)
-    pad = torch.zeros((m, rec.shape[1]), dtype=rec.dtype, device=rec.device)
-    pad[:rec.shape[0]] = rec
+    if rec.shape[0] == m:
+        pad = rec.contiguous()
+    else:
+        pad = torch.zeros((m, rec.shape[1]), dtype=rec.dtype, device=rec.device)
+        pad[:rec.shape[0]] = rec
     if rank == dst:
-        bufs = [torch.empty_like(pad) for _ in range(world)]
-        dist.gather(pad, bufs, dst=dst)
-        return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+        buf = torch.empty((world, m, rec.shape[1]), dtype=rec.dtype, device=rec.device)
+        dist.gather(pad, list(buf.unbind(0)), dst=dst)
+        return torch.cat([buf[r, :c] for r, c in enumerate(counts)], dim=0)
     dist.gather(pad, None, dst=dst)
     return None
+
+
+gather_records.last_counts = None
+
+
+class RowGatherer:
+    """The per-step result gather of a multi-GPU run without any host synchronisation on the sending ranks: every
+    rank holds its rows in a fixed-capacity device buffer [cap, W] with the counts {rows, fitted} beside it (what
+    ``xpb200_fit_host_rows_async`` / ``xpb200_pack_rows`` leave behind); ``gather`` ships both to ``dst`` with two
+    NCCL gathers into buffers allocated once; ``fetch`` (dst only) reads the counts - its single host
+    synchronisation - and copies exactly the rows to page-locked host memory."""
+
+    def __init__(self, cap: int, width: int, rank: int, world: int, device, dst: int = 0):
+        import torch
+        self.torch, self.rank, self.world, self.dst, self.cap, self.W = torch, rank, world, dst, int(cap), int(width)
+        self.rows = torch.zeros((self.cap, self.W), dtype=torch.float64, device=device)
+        self.counts = torch.zeros(2, dtype=torch.int32, device=device)
+        if rank == dst:
+            self.all_rows = torch.empty((world, self.cap, self.W), dtype=torch.float64, device=device)
+            self.all_counts = torch.zeros((world, 2), dtype=torch.int32, device=device)
+            self.host = torch.empty((world * self.cap, self.W), dtype=torch.float64).pin_memory() \
+                if torch.cuda.is_available() else torch.empty((world * self.cap, self.W), dtype=torch.float64)
+            self.host_counts = torch.zeros((world, 2), dtype=torch.int32)
+            if torch.cuda.is_available():
+                self.host_counts = self.host_counts.pin_memory()
+
+    def gather(self):
+        import torch.distributed as dist
+        if self.world == 1:
+            return
+        if self.rank == self.dst:
+            dist.gather(self.counts, list(self.all_counts.unbind(0)), dst=self.dst)
+            dist.gather(self.rows, list(self.all_rows.unbind(0)), dst=self.dst)
+        else:
+            dist.gather(self.counts, None, dst=self.dst)
+            dist.gather(self.rows, None, dst=self.dst)
+
+    def fetch(self):
+        """dst only: (host rows [n, W] view, per-rank counts, bytes copied device -> host)."""
+        torch = self.torch
+        if self.world == 1:
+            self.host_counts[0].copy_(self.counts)
+            if self.rows.is_cuda:
+                torch.cuda.current_stream().synchronize()
+            counts = self.host_counts[:1].tolist()
+            src = [self.rows]
+        else:
+            self.host_counts.copy_(self.all_counts, non_blocking=True)
+            if self.all_counts.is_cuda:
+                torch.cuda.current_stream().synchronize()
+            counts = self.host_counts.tolist()
+            src = list(self.all_rows.unbind(0))
+        o = 0
+        for r, (n, _) in enumerate(counts):
+            if n > self.cap:
+                raise RuntimeError("rank %d produced %d rows, capacity %d" % (r, n, self.cap))
+            self.host[o:o + n].copy_(src[r][:n], non_blocking=True)
+            o += n
+        if self.rows.is_cuda:
+            torch.cuda.current_stream().synchronize()
+        return self.host[:o], counts, o * self.W * 8 + 8 * len(counts)

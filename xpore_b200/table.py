@@ -44,47 +44,69 @@ def _cell(v):
     return repr(float(v))
 
 
+def _row(key, st, status, pval, present, cond_present, layout: Layout, pairs, prefilter_method):
+    """One table row (python values, ``None`` for empty cells) from a statistics record (io.py:346-361)."""
+    G, Cn = layout.n_groups, layout.n_conditions
+    o_pair = ST_RATE + 2 * G
+    o_ova = o_pair + 3 * len(pairs)
+    row = [key[0], key[1], key[2]]
+    for j, (a, b) in enumerate(pairs):
+        if cond_present[a] and cond_present[b]:
+            row += [float(v) for v in st[o_pair + 3 * j:o_pair + 3 * j + 3]]
+        else:
+            row += [None, None, None]
+    if Cn > 2:
+        for c in range(Cn):
+            if cond_present[c]:
+                row += [float(v) for v in st[o_ova + 3 * c:o_ova + 3 * c + 3]]
+            else:
+                row += [None, None, None]
+    row += [float(st[ST_RATE + g]) if present[g] else None for g in range(G)]
+    row += [float(st[ST_RATE + G + g]) if present[g] else None for g in range(G)]
+    row += [float(v) for v in st[ST_MU:ST_MU + 2]] + [float(v) for v in st[ST_S2:ST_S2 + 2]] + \
+           [float(v) for v in st[ST_CONF:ST_CONF + 2]]
+    row += ["higher" if (int(status) & HIGHER) else "lower"]
+    if prefilter_method:
+        row += [float(pval)]
+    return row
+
+
 def result_rows(batch: Batch, res: FitResult, prefilter_method: str | None, only_kept: bool = True):
     """Rows (lists of python values, ``None`` for empty cells) of the positions that pass the
     row filter — or of every fitted position with ``only_kept=False`` (the reference can only
     produce the filtered table)."""
     lay = batch.layout
-    G, Cn = lay.n_groups, lay.n_conditions
+    Cn = lay.n_conditions
     gc = lay.grp_cond
     present = batch.grp_len > 0  # [P, G]
     cond_present = np.stack([present[:, gc == c].any(axis=1) for c in range(Cn)], axis=1)  # [P, C]
     pairs = list(combinations(range(Cn), 2))
     mask = res.keep_row if only_kept else res.selected
-    rows = []
-    st = res.stats
-    o_pair = ST_RATE + 2 * G
-    o_ova = o_pair + 3 * len(pairs)
-    for p in np.nonzero(mask)[0]:
-        row = [batch.ids[p], batch.positions[p], batch.kmers[p]]
-        for j, (a, b) in enumerate(pairs):
-            if cond_present[p, a] and cond_present[p, b]:
-                row += [float(v) for v in st[p, o_pair + 3 * j:o_pair + 3 * j + 3]]
-            else:
-                row += [None, None, None]
-        if Cn > 2:
-            for c in range(Cn):
-                if cond_present[p, c]:
-                    row += [float(v) for v in st[p, o_ova + 3 * c:o_ova + 3 * c + 3]]
-                else:
-                    row += [None, None, None]
-        row += [float(st[p, ST_RATE + g]) if present[p, g] else None for g in range(G)]
-        row += [float(st[p, ST_RATE + G + g]) if present[p, g] else None for g in range(G)]
-        row += [float(v) for v in st[p, ST_MU:ST_MU + 2]] + [float(v) for v in st[p, ST_S2:ST_S2 + 2]] + \
-               [float(v) for v in st[p, ST_CONF:ST_CONF + 2]]
-        row += ["higher" if (res.status[p] & HIGHER) else "lower"]
-        if prefilter_method:
-            row += [float(res.pval[p])]
-        rows.append(row)
-    return rows
+    return [_row((batch.ids[p], batch.positions[p], batch.kmers[p]), res.stats[p], res.status[p], res.pval[p], present[p],
+                 cond_present[p], lay, pairs, prefilter_method) for p in np.nonzero(mask)[0]]
+
+
+def rows_from_records(records: np.ndarray, keys, present: np.ndarray, layout: Layout, prefilter_method: str | None):
+    """Rows from the compact records of ``xpb200_fit_host_rows`` (``[position, status, n_iter, pval, fit, stats]``;
+    every record is a row of the table): ``keys[i]`` = (id, position, kmer) and ``present[i]`` = the groups present
+    at the position of record i."""
+    from .fit import fit_width
+    G, Cn = layout.n_groups, layout.n_conditions
+    gc = layout.grp_cond
+    o_st = 4 + fit_width(G)
+    pairs = list(combinations(range(Cn), 2))
+    present = np.asarray(present, dtype=bool).reshape(len(records), G)
+    cond_present = np.stack([present[:, gc == c].any(axis=1) for c in range(Cn)], axis=1) if len(records) else present
+    return [_row(keys[i], rec[o_st:], int(rec[1]), rec[3], present[i], cond_present[i], layout, pairs, prefilter_method)
+            for i, rec in enumerate(records)]
 
 
 def write_rows(path: str, rows, mode: str = "a"):
     with open(path, mode, newline="") as f:
-        w = csv.writer(f, delimiter=",")  # default dialect (CRLF), as the reference writes it
-        for row in rows:
-            w.writerow([_cell(v) for v in row])
+        write_rows_to(f, rows)
+
+
+def write_rows_to(f, rows):
+    w = csv.writer(f, delimiter=",")  # default dialect (CRLF), as the reference writes it
+    for row in rows:
+        w.writerow([_cell(v) for v in row])
