@@ -250,7 +250,7 @@ def cli_e2e(spec, km, cores, local_rank, n_genes=None, with_reference=True):
     from xpore_b200.synth import make_batch  # noqa: F401
     per_pos = float(np.mean([spec.reads_lo, spec.reads_hi])) * sum(spec.conditions.values()) if not spec.loguniform_total \
         else 900.0
-    n_genes = n_genes or int(max(10, min(spec.n_genes, round(36e6 / per_pos / spec.pos_per_gene))))
+    n_genes = n_genes or int(max(10, min(spec.n_genes, round(108e6 / per_pos / spec.pos_per_gene))))
     root = scratch_dir("xpb200_cli_")
     out = {}
     try:
@@ -278,6 +278,9 @@ def cli_e2e(spec, km, cores, local_rank, n_genes=None, with_reference=True):
                          "stages_s": {"ingest": tm["ingest_s"], "gpu_call": tm["gpu_s"], "rows": tm["rows_s"],
                                       "write": tm["write_s"]},
                          "gpu_call_ms_per_chunk": tm["gpu_s"] * 1e3 / max(tm["chunks"], 1), "chunks": tm["chunks"],
+                         "gpu_call_ms_per_chunk_after_first": (tm["gpu_s"] - tm.get("gpu_first_chunk_s", 0.0)) * 1e3
+                         / max(tm["chunks"] - 1, 1) if tm["chunks"] > 1 else None,
+                         "cuda_init_s": tm.get("cuda_init_s"), "ingest_parse_s": tm.get("ingest_parse_s"),
                          "positions": tm["positions"], "fitted": tm["fitted"], "rows": rows})
         out["runs"] = runs
         best = min(runs, key=lambda x: x["wall_s"])

@@ -581,3 +581,35 @@ def test_understated_max_reads_is_flagged(torch_cuda):
     ok = ~too_deep
     assert not (bad.status[ok] & xf.NOT_FITTED).any()
     np.testing.assert_array_equal(bad.fit[ok], good.fit[ok])
+
+
+def test_cli_two_ranks_nccl(torch_cuda, tmp_path):
+    """The drop-in CLI under torchrun with one rank per GPU (needs two GPUs): ids split by data.index byte spans,
+    every rank runs its pipeline, the numeric row records are gathered on rank 0 over NCCL (dist.gather_records) -
+    the table must hold exactly the rows of the single-rank run, the log every id."""
+    import os
+    import subprocess
+    import sys
+
+    from conftest import load_case
+    from helpers import read_table
+    from xpore_b200 import cli
+    if torch_cuda.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name in ("g1_runs", "g5_ragged", "g7_six_conditions"):
+        (tmp_path / name).mkdir()
+        case = load_case(name, tmp_path / name)
+        out = os.path.join(os.path.dirname(case["config_path"]), "out")
+        cli.main(["xpore", "diffmod", "--config", case["config_path"]])
+        header1, rows1 = read_table(os.path.join(out, "diffmod.table"))
+        os.rename(os.path.join(out, "diffmod.table"), os.path.join(out, "single.table"))
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                            "--master-addr", "127.0.0.1", "--master-port", "29631", "-m", "xpore_b200.cli", "diffmod",
+                            "--config", case["config_path"], "--n_processes", "2"], cwd=repo, capture_output=True, text=True,
+                           timeout=600)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        header2, rows2 = read_table(os.path.join(out, "diffmod.table"))
+        assert header2 == header1 and rows2 == rows1 and len(rows1) > 0
+        lines = open(os.path.join(out, "diffmod.log")).read().splitlines()
+        assert sorted(lines[1:-1]) == sorted(case["expected"]["ids"]) and lines[-1] == "--- SUCCESSFULLY FINISHED ---"

@@ -144,6 +144,8 @@ class NativeIngest:
 
     def read(self, ids, f_index, n_threads: int = 1, staging: Staging | None = None) -> Batch:
         """Selected positions of ``ids`` (in that order) as one batch.  ``f_index``: {run: {idx: (start, end)}}."""
+        import time
+        t0 = time.perf_counter()
         n, R = len(ids), len(self.runs)
         starts = np.full((n, R), -1, dtype=np.int64)
         ends = np.zeros((n, R), dtype=np.int64)
@@ -162,6 +164,7 @@ class NativeIngest:
                 raise KeyError(msg)
             raise RuntimeError(msg)
         P, Rd, S = P.value, Rd.value, S.value
+        t1 = time.perf_counter()
         G = self.layout.n_groups
         max_reads = C.c_int32(0)
         enc = self.L.xpb200_ingest_encoding(self.handle, C.byref(max_reads))
@@ -191,4 +194,5 @@ class NativeIngest:
             if self.L.xpb200_ingest_copy_u16(self.handle, yq.ctypes.data) != 0:
                 raise RuntimeError(self.L.xpb200_ingest_last_error().decode())
             b.y_enc, b.y_format, b.y_scale = yq, 2, 100.0
+        self.last_times = {"parse_s": t1 - t0, "copy_s": time.perf_counter() - t1}
         return b.validate()

@@ -36,7 +36,9 @@ def position_nodes(batch: Batch, res: FitResult, p: int, prob0: np.ndarray, ln_p
     a, b = int(batch.read_off[p]), int(batch.read_off[p + 1])
     y = np.asarray(batch.y[a:b], dtype=np.float64)
     glen = batch.grp_len[p]
-    present = np.nonzero(glen > 0)[0]
+    # the reference's model groups are the columns of get_dummies: present groups in SORTED label order
+    # (io.py:12-18), while the reads stay run by run in config order (io.py:46-58) - as they are in the batch
+    present = np.asarray(sorted(np.nonzero(glen > 0)[0], key=lambda g: lay.group_names[g]), dtype=np.int64)
     group_of_read = np.repeat(np.arange(len(glen)), glen)
     col = {g: j for j, g in enumerate(present)}
     x = np.zeros((len(y), len(present)), dtype=bool)
@@ -51,7 +53,9 @@ def position_nodes(batch: Batch, res: FitResult, p: int, prob0: np.ndarray, ln_p
     var = Ninv * np.sum(prob * (y[:, None] - mean[None, :]) ** 2, axis=-2)
     run_names = np.asarray(lay.run_names if not lay.pooling else [])
     if lay.pooling:
-        # pooled batches keep one slot per condition; the per-read run names are not part of the batch
+        # Deviation from the reference's dump: pooled batches keep one slot per condition and their reads condition by
+        # condition; which run a read came from is not part of the batch, so `y_run_names` is not written, and the
+        # reads of a position are ordered by condition (the reference: run by run in config order, io.py:46-58).
         y_cond = np.asarray(lay.group_names)[group_of_read]
         y_run = None
     else:
