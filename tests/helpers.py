@@ -359,3 +359,14 @@ def compare_stats_with_oracle(batch, res, p, fit, present, data_info, prefilter_
         assert near, (key, got_keep, keep, extra["p_overlap"], extra["cdfs"])
     assert bool(res.status[p] & xf.MOD_IS_1) == (extra["mod"] == 1), key
     return knife
+
+
+def assert_same_rows(rows1, rows2):
+    """Two parsed tables hold the very same rows (NaN cells - e.g. the prefilter column of a position with more than two
+    conditions - compare equal)."""
+    assert set(rows1) == set(rows2)
+    for k, a in rows1.items():
+        b = rows2[k]
+        assert len(a) == len(b), k
+        for x, y in zip(a, b):
+            assert x == y or (isinstance(x, float) and isinstance(y, float) and x != x and y != y), (k, x, y)

@@ -12,7 +12,7 @@ from xpore_b200.batch import Layout
 from xpore_b200.config import Configurator
 
 from conftest import load_case
-from helpers import compare_tables, emul_fit_batch, load_emulator, read_table
+from helpers import assert_same_rows, compare_tables, emul_fit_batch, load_emulator, read_table
 
 
 def emul_fit_fn(batch, method):
@@ -75,17 +75,19 @@ def _rank_main(rank, world, config_path, port):
     dist.destroy_process_group()
 
 
-def test_two_ranks_gloo(tmp_path):
-    """N > 1 path on CPU: ids split by data.index byte spans, rows gathered on rank 0."""
+@pytest.mark.parametrize("name", ["g1_runs", "g7_six_conditions"])
+def test_two_ranks_gloo(tmp_path, name):
+    """N > 1 path on CPU: ids split by data.index byte spans, the numeric row records gathered on rank 0 (one gene and
+    18 group slots in the second case: a rank without work, NaN prefilter cells, absent-group masks)."""
     import torch.multiprocessing as mp
-    case = load_case("g1_runs", tmp_path)
+    case = load_case(name, tmp_path)
     table1, _ = run_cli(case["config_path"])
     _, rows1 = read_table(table1)
     os.rename(table1, table1 + ".single")
     mp.spawn(_rank_main, args=(2, case["config_path"], 29617), nprocs=2, join=True)
     out = Configurator(case["config_path"]).get_paths()["out_dir"]
     header, rows2 = read_table(os.path.join(out, "diffmod.table"))
-    assert rows2 == rows1
+    assert_same_rows(rows1, rows2)
     lines = open(os.path.join(out, "diffmod.log")).read().splitlines()
     assert sorted(lines[1:-1]) == case["expected"]["ids"] and lines[-1] == "--- SUCCESSFULLY FINISHED ---"
 
