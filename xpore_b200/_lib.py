@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.environ.get("XPB200_LIB") or os.path.join(HERE, "libxpore_b200.so")  # override: experiments only
 SOURCES = ["xp_api.cu", "xp_ingest.cpp"]
-HEADERS = ["xp_math.cuh", "xp_core.cuh", "xp_kernels.cuh", "xp_fit.cuh", "xp_tables.inc", os.path.join("..", "..", "include", "xpore_b200.h")]
+HEADERS = ["xp_math.cuh", "xp_core.cuh", "xp_kernels.cuh", "xp_fit.cuh", "xp_fit_tm.cuh", "xp_tables.inc", os.path.join("..", "..", "include", "xpore_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
 

@@ -93,21 +93,51 @@ int check_batch(const xpb200_batch* b, const xpb200_method* m) {
 // Launch geometry of one fit-kernel flavour: `tw` warps per team (position), `teams` teams per CTA.
 struct Geometry {
     int tw, teams, threads, maxt, cap, ctas_per_sm, sms, regs;
+    int np;  // > 0: the tensor-memory kernel of xp_fit_tm.cuh with np positions per warp; 0 = the kernels of xp_fit.cuh
     size_t smem;
     bool stream;
 };
 
 constexpr int kStreamWarps = 16;  // warps of a streaming team (one CTA, one position)
 
-template <int TW, int MAXT, bool STREAM = false>
-int prepare_kernel(Geometry* g) {
-    auto* k = xpk::xp_fit_kernel<TW, MAXT, STREAM>;
+int exp_int(const char* name, int dflt);
+
+template <class K>
+int prepare_kernel_fn(K* k, Geometry* g) {
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g->ctas_per_sm, k, g->threads, g->smem));
     cudaFuncAttributes fa;
     CK(cudaFuncGetAttributes(&fa, k));
     g->regs = fa.numRegs;
     return 0;
+}
+template <int TW, int MAXT, bool STREAM = false>
+int prepare_kernel(Geometry* g) {
+    return prepare_kernel_fn(xpk::xp_fit_kernel<TW, MAXT, STREAM>, g);
+}
+// the tensor-memory flavour of the single-warp class (u16 batches), by positions per warp and thread limit
+using FitKernelFn = void (*)(xpk::FitArgs);
+template <int NPW, int GT>
+FitKernelFn tm_kernel_g(int maxt) {
+    switch (maxt) {
+        case 640: return xpk::xp_fit_tm_kernel<NPW, 640, GT>;
+        case 768: return xpk::xp_fit_tm_kernel<NPW, 768, GT>;
+        case 896: return xpk::xp_fit_tm_kernel<NPW, 896, GT>;
+        default: return xpk::xp_fit_tm_kernel<NPW, 1024, GT>;
+    }
+}
+// two positions per warp always run 28 warps (their warp regions are small); the designs of the named workloads
+// (G = 2 pooled two-condition, 4 = 2 x 2 runs, 6 = 2 x 3 runs) have the group count compiled in
+FitKernelFn tm_kernel(int npw, int maxt, int G) {
+    if (npw == 2) {
+        if (maxt == 896 && exp_int("XPB200_TM_GT", 1)) {
+            if (G == 2) return xpk::xp_fit_tm_kernel<2, 896, 2>;
+            if (G == 4) return xpk::xp_fit_tm_kernel<2, 896, 4>;
+            if (G == 6) return xpk::xp_fit_tm_kernel<2, 896, 6>;
+        }
+        return tm_kernel_g<2, 0>(maxt);
+    }
+    return tm_kernel_g<1, 0>(maxt);
 }
 
 constexpr int kFitWarpsDefault = 28;
@@ -133,6 +163,7 @@ int fit_geometry(int G, int cap_reads, int tw, Geometry* g) {
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&g->sms, cudaDevAttrMultiProcessorCount, dev));
     g->tw = tw;
+    g->np = 0;
     g->stream = (tw == kStreamWarps);
     g->cap = std::max(32, (cap_reads + 1 + 7) & ~7);
     const size_t per_team = xpk::fit_team_smem_bytes(g->cap, G, tw, g->stream);
@@ -165,6 +196,44 @@ int fit_geometry(int G, int cap_reads, int tw, Geometry* g) {
         }
     } else rc = prepare_kernel<4, 512>(g);
     if (rc) return rc;
+    if (g->ctas_per_sm < 1) return fail(XPB200_ECUDA, "fit kernel does not fit on an SM");
+    return 0;
+}
+
+// Positions per warp of the tensor-memory kernel: two when their 2G + 4 scalar-phase slots fit half a warp each - unless
+// the batch is a deep one (positions for the 4-warp teams anyway): two positions per warp hold 576 reads each, and
+// handing the teams everything from there up costs more than the shared scalar phase saves (c4: 8.3 against 7.6 ms).
+int tm_positions_per_warp(int G, int max_reads) {
+    return exp_int("XPB200_TM_NPW", (2 * G + 4 <= 16 && max_reads < kSplitReads) ? 2 : 1);
+}
+// Reads the tensor-memory kernel can hold per position with 28 warps resident (7 column blocks per TMEM quadrant):
+// 576 with two positions per warp, 1152 with one.  Its class takes the positions below min(kSplitReads, that).
+int tm_class_split(int npw) {
+    const int cols = (xpk::kTmColumns / (7 * npw)) & ~1;  // columns per position
+    return std::min(kSplitReads, (cols / 2) * 32);
+}
+// Launch geometry of xp_fit_tm_kernel: one warp per `np` positions, reads in tensor memory.
+int fit_tm_geometry(int G, int cap_reads, int npw, Geometry* g) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&g->sms, cudaDevAttrMultiProcessorCount, dev));
+    g->tw = 1;
+    g->np = npw;
+    g->stream = false;
+    g->cap = std::max(32, (cap_reads + 31) & ~31);
+    const size_t per_warp = xpk::fit_tm_warp_bytes(g->cap, G, npw);
+    int warps = (int)((kMaxSmemPerCta - xpk::kTmTableBytes) / per_warp);
+    warps = std::min(warps, std::max(1, exp_int("XPB200_FIT_WARPS", kFitWarpsDefault)));
+    warps = std::min(warps, 32);
+    // tensor-memory columns: ceil(warps / 4) column blocks of npw positions each per quadrant
+    const int blocks = xpk::kTmColumns / (npw * xpk::fit_tm_cols(g->cap));
+    warps = std::min(warps, 4 * blocks);
+    if (warps < 1) return fail(XPB200_EINVAL, "internal: tensor-memory class with a position too deep for it");
+    g->maxt = warps <= 20 ? 640 : warps <= 24 ? 768 : warps <= 28 ? 896 : 1024;
+    g->teams = warps * npw;  // positions in flight per CTA
+    g->threads = warps * 32;
+    g->smem = xpk::kTmTableBytes + per_warp * warps;
+    if (int rc = prepare_kernel_fn(tm_kernel(npw, g->maxt, G), g)) return rc;
     if (g->ctas_per_sm < 1) return fail(XPB200_ECUDA, "fit kernel does not fit on an SM");
     return 0;
 }
@@ -213,10 +282,12 @@ int deep_class_split(int G) {
 
 int launch_fit(const Geometry& g, const xpk::FitArgs& fa_in, int max_teams_needed, cudaStream_t st) {
     xpk::FitArgs fa = fa_in;
-    xpk::fit_fill_layout(fa, g.tw, g.stream);
+    if (g.np > 0) xpk::fit_tm_fill_layout(fa, g.np);
+    else xpk::fit_fill_layout(fa, g.tw, g.stream);
     const int need = (max_teams_needed + g.teams - 1) / g.teams;
     const int grid = std::max(1, std::min(g.sms * g.ctas_per_sm, need));
-    if (g.stream) xpk::xp_fit_kernel<kStreamWarps, kStreamWarps * 32, true><<<grid, g.threads, g.smem, st>>>(fa);
+    if (g.np > 0) tm_kernel(g.np, g.maxt, fa.G)<<<grid, g.threads, g.smem, st>>>(fa);
+    else if (g.stream) xpk::xp_fit_kernel<kStreamWarps, kStreamWarps * 32, true><<<grid, g.threads, g.smem, st>>>(fa);
     else if (g.tw == 1) {
         switch (g.maxt) {
             case 640: xpk::xp_fit_kernel<1, 640><<<grid, g.threads, g.smem, st>>>(fa); break;
@@ -348,15 +419,22 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
     wa.n_work = ws.n_work; wa.worklist = ws.worklist; wa.n_large = ws.n_large;
     // Three classes by depth, each with its own launch: n >= deep_split reads -> streaming CTAs (reads stay in global
     // memory: no cap), n >= kSplitReads -> 4-warp teams, the rest -> one warp per position.
+    // u16 batches: the single-warp class runs on the tensor-memory kernel, which holds fewer reads per position when
+    // two positions share a warp
+    const int npw = tm_positions_per_warp(b->n_groups, b->max_reads);
+    const bool use_tm = b->y_format == XPB200_Y_U16 && exp_int("XPB200_TM", 1) != 0;
+    const int split1 = use_tm ? tm_class_split(npw) : kSplitReads;
     const int deep_split = deep_class_split(b->n_groups);
     const bool has_deep = b->max_reads >= deep_split;
-    const bool two_class = b->max_reads >= kSplitReads;
-    wa.split = two_class ? kSplitReads : 0;
+    const bool two_class = b->max_reads >= split1;
+    wa.split = two_class ? split1 : 0;
     wa.n_deep = ws.n_deep;
     wa.split_deep = has_deep ? deep_split : 0;
-    const int tw1_reads = two_class ? kSplitReads - 1 : b->max_reads;
+    const int tw1_reads = two_class ? split1 - 1 : b->max_reads;
     Geometry g;
-    if (int rc = fit_geometry(b->n_groups, tw1_reads, 1, &g)) return rc;
+    if (use_tm) {
+        if (int rc = fit_tm_geometry(b->n_groups, tw1_reads, npw, &g)) return rc;
+    } else if (int rc = fit_geometry(b->n_groups, tw1_reads, 1, &g)) return rc;
     const int wthreads = 256;
     const int wblocks = std::min((P + wthreads - 1) / wthreads, 1184);
     xpk::xp_worklist_count<<<wblocks, wthreads, 0, st>>>(wa);

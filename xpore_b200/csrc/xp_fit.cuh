@@ -83,6 +83,9 @@ struct FitArgs {
     // byte offsets inside a team's shared-memory region and its size, filled by fit_fill_layout: the kernel adds
     // them to the team base as constant-bank operands instead of re-deriving them from G and cap
     int team_bytes, off_tot, off_asm, off_dps, off_goff, off_slab, off_gid;
+    // xp_fit_tm.cuh (reads resident in tensor memory): bytes of one position's header, offset of the warp's scratch
+    // columns inside the warp's region, tensor-memory columns per position
+    int hdr_bytes, off_scratch, tm_cols;
 };
 
 constexpr int kTabExpDoubles = 256;
@@ -123,17 +126,20 @@ inline void fit_fill_layout(FitArgs& a, int TW, bool stream = false) {
     a.off_gid = a.off_slab + (a.cap + 2) * 8;
 }
 
-// shared-memory tables, addressed through the 32-bit shared window
-struct SmemTab;
+// shared-memory tables, addressed through the 32-bit shared window.  ES / LS: bytes between consecutive entries
+// (8 / 16: one copy of each table; 128 / 128: the lane-replicated, bank-conflict-free copies of xp_fit_tm.cuh, where
+// e2 and lg already carry the lane's offset inside an entry's row)
 __device__ __forceinline__ void lds_tab2(uint32_t a, double& x, double& y);
-struct SmemTab {
-    uint32_t e2;  // 2^(j/256), 8 bytes per entry
-    uint32_t lg;  // {1/c, ln c}, 16 bytes per entry, biased so that entry i of u = 1 + t in [1, 2] is found
-                  // at lg + 16 * (hi32(u) >> 13)
+template <unsigned ES, unsigned LS>
+struct SmemTabT {
+    static constexpr unsigned kES = ES, kLS = LS;
+    uint32_t e2;  // 2^(j/256), entry j at e2 + ES * j
+    uint32_t lg;  // {1/c, ln c}, biased so that entry i of u = 1 + t in [1, 2] is found at lg + LS * (hi32(u) >> 13)
     __device__ __forceinline__ void logc(int i, double& ic, double& lc) const {  // entry i (xlog_tab)
-        lds_tab2(lg + ((0x3ff00000u >> 13) + (unsigned)i) * 16u, ic, lc);
+        lds_tab2(lg + ((0x3ff00000u >> 13) + (unsigned)i) * LS, ic, lc);
     }
 };
+using SmemTab = SmemTabT<8u, 16u>;
 __device__ __forceinline__ double lds_tab(uint32_t a) {  // tables are immutable after the prologue
     double v;
     asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
@@ -342,7 +348,8 @@ struct EConst {
 };
 
 // E-step of one read given d (device flavour of xpc::estep_read: same operations, same order).
-__device__ __forceinline__ void estep_dev(const SmemTab& tab, const EConst& K, double d, double& r0, double& h) {
+template <class Tab>
+__device__ __forceinline__ void estep_dev(const Tab& tab, const EConst& K, double d, double& r0, double& h) {
     const int dhi = __double2hiint(d);
     int ahi = dhi & 0x7fffffff;
     ahi = min(ahi, 0x407f4000);  // |d| clipped at 500 (gmm.py:240); low word kept: [500, 500 + 2^-12)
@@ -357,11 +364,11 @@ __device__ __forceinline__ void estep_dev(const SmemTab& tab, const EConst& K, d
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    double t = lds_tab(mad_u32(k & 255u, 8u, tab.e2)) * p;
+    double t = lds_tab(mad_u32(k & 255u, Tab::kES, tab.e2)) * p;
     t = __hiloint2double((int)mad_u32(k & ~255u, 4096u, (unsigned)__double2hiint(t)), __double2loint(t));  // * 2^(k >> 8)
     const double u = 1.0 + t;
     double ic, lc;
-    lds_tab2(mad_u32((unsigned)__double2hiint(u) >> 13, 16u, tab.lg), ic, lc);  // top seven mantissa bits; u == 2 -> entry 128
+    lds_tab2(mad_u32((unsigned)__double2hiint(u) >> 13, Tab::kLS, tab.lg), ic, lc);  // top seven mantissa bits; u == 2 -> entry 128
     const double rr = fma(u, ic, -1.0);
     double q = fma(kLogC5, rr, -0.25);
     q = fma(q, rr, K.l3);

@@ -506,6 +506,7 @@ __global__ void xp_worklist_scatter(WorklistArgs a) {
 
 }  // namespace xpk
 #include "xp_fit.cuh"  // K3: variational EM
+#include "xp_fit_tm.cuh"  // K3 for u16 batches: reads resident in tensor memory, two positions per warp
 namespace xpk {
 
 // ------------------------------------------------------------------------------------------
