@@ -135,7 +135,7 @@ def write_files(spec, km, n_genes, root):
     batch = make_batch(rs, km, n_positions=n_genes * spec.pos_per_gene, keys=True)
     full = type(spec)(spec.conditions, spec.ko_like, spec.n_genes, spec.pos_per_gene, spec.reads_lo, spec.reads_hi,
                       spec.f_mod, spec.seed, spec.loguniform_total, spec.method, spec.criteria)
-    cfg = write_dataset_from_batch(root, full, batch, km)
+    cfg = write_dataset_from_batch(root, full, batch, km, n_workers=len(os.sched_getaffinity(0)))
     nbytes = sum(os.path.getsize(os.path.join(dp, f)) for dp, _, fs in os.walk(root) for f in fs if f == "data.json")
     return cfg, batch, nbytes
 
@@ -250,7 +250,9 @@ def cli_e2e(spec, km, cores, local_rank, n_genes=None, with_reference=True):
     from xpore_b200.synth import make_batch  # noqa: F401
     per_pos = float(np.mean([spec.reads_lo, spec.reads_hi])) * sum(spec.conditions.values()) if not spec.loguniform_total \
         else 900.0
-    n_genes = n_genes or int(max(10, min(spec.n_genes, round(108e6 / per_pos / spec.pos_per_gene))))
+    # ~1.4e8 reads of text (c2: 4000 genes = 400k positions, 0.95 GB of data.json): large enough that interpreter start,
+    # imports and the CUDA context (about 1 s together) do not decide the rate
+    n_genes = n_genes or int(max(10, min(spec.n_genes, round(144e6 / per_pos / spec.pos_per_gene))))
     root = scratch_dir("xpb200_cli_")
     out = {}
     try:
@@ -280,7 +282,8 @@ def cli_e2e(spec, km, cores, local_rank, n_genes=None, with_reference=True):
                          "gpu_call_ms_per_chunk": tm["gpu_s"] * 1e3 / max(tm["chunks"], 1), "chunks": tm["chunks"],
                          "gpu_call_ms_per_chunk_after_first": (tm["gpu_s"] - tm.get("gpu_first_chunk_s", 0.0)) * 1e3
                          / max(tm["chunks"] - 1, 1) if tm["chunks"] > 1 else None,
-                         "cuda_init_s": tm.get("cuda_init_s"), "ingest_parse_s": tm.get("ingest_parse_s"),
+                         "cuda_init_s": tm.get("cuda_init_s"), "cuda_init_wait_s": tm.get("cuda_init_wait_s"),
+                         "ingest_parse_s": tm.get("ingest_parse_s"),
                          "positions": tm["positions"], "fitted": tm["fitted"], "rows": rows})
         out["runs"] = runs
         best = min(runs, key=lambda x: x["wall_s"])
@@ -290,7 +293,7 @@ def cli_e2e(spec, km, cores, local_rank, n_genes=None, with_reference=True):
                            "around it: interpreter start, imports, CUDA context, data.json -> diffmod.table)"})
         table_ours = open(os.path.join(root, "out", "diffmod.table")).read().splitlines()
         if with_reference and reference_available():
-            g_ref = min(n_genes, reference_genes_for(spec, cores, seconds=6.0))
+            g_ref = min(n_genes, reference_genes_for(spec, cores, seconds=10.0))
             ids = sorted(set(batch.ids))[:g_ref]
             wall, rows = run_reference_cli(cfg, ids, cores)
             by_id = count_fitted_numpy(batch, spec)
@@ -677,7 +680,7 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         info = _lib.XpLaunchInfo()
-        _lib.check(L.xpb200_fit_launch_info(local_rank, db.G, db.max_reads, C.byref(info)))
+        _lib.check(L.xpb200_fit_launch_info(local_rank, db.G, db.max_reads, db.y_format, C.byref(info)))
         theo = FP64_THEORETICAL(info.sm_count, (clocks or {}).get("sm_max_mhz") or 1965.0)
         pf_ms = float(np.median(stage_ms[:, 0]))
         pf_bytes = db.R * ybytes + db.P * (8 + 4 * G + 8 + 12)
@@ -706,7 +709,7 @@ def main():
                            "exactly the rows to pinned host memory"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "xp_fit_kernel", "bound": "fp64", "achieved": achieved, "peak": peak.value,
+            "roofline": {"kernel": "xp_fit_tm_kernel" if info.tmem_columns else "xp_fit_kernel", "bound": "fp64", "achieved": achieved, "peak": peak.value,
                          "unit": "TFLOP/s", "frac": achieved / peak.value,
                          "peak_source": "measured here: xpb200_measure_fp64_peak (8 independent DFMA chains per "
                                         "thread, 8 CTAs x 256 threads per SM, best of 5); committed record with clocks: "
@@ -728,7 +731,9 @@ def main():
                               "peak_gbs": hbm_peak, "frac": pf_bytes / (pf_ms * 1e-3) / 1e9 / hbm_peak if pf_ms > 0 else None},
             "launch": {"sm_count": info.sm_count, "ctas_per_sm": info.ctas_per_sm, "warps_per_cta": info.warps_per_cta,
                        "smem_per_cta": info.smem_per_cta, "slab_reads": info.slab_reads,
-                       "regs_per_thread": info.regs_per_thread},
+                       "regs_per_thread": info.regs_per_thread, "positions_per_warp": info.positions_per_warp,
+                       "tmem_columns_per_position": info.tmem_columns,
+                       "kernel": "xp_fit_tm_kernel (reads in tensor memory)" if info.tmem_columns else "xp_fit_kernel (reads in shared memory)"},
             "cpu_baseline": cpu,
             "cli_e2e": cli,
             "host_cores": cores, "cpus_bound_to_gpu": bound_cpus,

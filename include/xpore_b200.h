@@ -153,6 +153,10 @@ int32_t xpb200_fit_host_rows_async(int32_t device, const xpb200_batch* batch, co
  * full PCIe rate); NULL when no CUDA device is usable.  Free with xpb200_host_free. */
 void* xpb200_host_alloc(size_t bytes);
 void xpb200_host_free(void* p);
+/* The CUDA device of the calling host thread (cudaSetDevice): xpb200_host_alloc and the first call of a thread create
+ * their context there.  A driver calls it once per worker thread with its rank's device, e.g. from a thread started
+ * at process entry, so that the CUDA context (0.3 - 1 s) comes up while the inputs are being parsed. */
+int32_t xpb200_set_device(int32_t device);
 
 /* Release the cached device buffers of xpb200_fit_host (all devices). */
 void xpb200_release(void);
@@ -185,11 +189,15 @@ int32_t xpb200_pack_rows(const xpb200_result* result, int32_t n_positions, int32
                          void* workspace, int64_t index_offset, double* out, int64_t capacity_rows,
                          uint32_t* n_rows_dev, void* cuda_stream);
 
-/* Launch geometry the fit kernel would use for this batch (for reporting): */
+/* Launch geometry of the class that fits the positions below the team split of such a batch (for reporting).
+ * positions_per_warp and tmem_columns are 0 for the shared-memory kernels (f64 / i32 reads); u16 batches run the
+ * tensor-memory kernel: slab_reads = reads a position may have there, tmem_columns = columns per position. */
 typedef struct xpb200_launch_info {
     int32_t sm_count, ctas_per_sm, warps_per_cta, smem_per_cta, slab_reads, regs_per_thread;
+    int32_t positions_per_warp, tmem_columns;
 } xpb200_launch_info;
-int32_t xpb200_fit_launch_info(int32_t device, int32_t n_groups, int32_t max_reads, xpb200_launch_info* out);
+int32_t xpb200_fit_launch_info(int32_t device, int32_t n_groups, int32_t max_reads, int32_t y_format,
+                               xpb200_launch_info* out);
 
 /* Positions with at least this many reads are fitted by the streaming class (reads re-read from global memory in
  * every sweep) instead of being held in shared memory; depends on the number of group slots only. */

@@ -45,7 +45,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.XpBatch) == 4 * 4 + 8 + 6 * 8 + 2 * 4 + 8
     assert C.sizeof(_lib.XpMethod) == 2 * 4 + 3 * 8
     assert C.sizeof(_lib.XpResult) == 6 * 8  # status n_iter pval fit stats coef
-    assert C.sizeof(_lib.XpLaunchInfo) == 6 * 4
+    assert C.sizeof(_lib.XpLaunchInfo) == 8 * 4
 
 
 def test_argument_validation_without_gpu(library):

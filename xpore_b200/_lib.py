@@ -38,7 +38,8 @@ class XpResult(C.Structure):
 
 class XpLaunchInfo(C.Structure):
     _fields_ = [("sm_count", C.c_int32), ("ctas_per_sm", C.c_int32), ("warps_per_cta", C.c_int32),
-                ("smem_per_cta", C.c_int32), ("slab_reads", C.c_int32), ("regs_per_thread", C.c_int32)]
+                ("smem_per_cta", C.c_int32), ("slab_reads", C.c_int32), ("regs_per_thread", C.c_int32),
+                ("positions_per_warp", C.c_int32), ("tmem_columns", C.c_int32)]
 
 
 EXPORTS = ["xpb200_fit_width", "xpb200_stats_width", "xpb200_workspace_bytes", "xpb200_fit_device",
@@ -47,7 +48,7 @@ EXPORTS = ["xpb200_fit_width", "xpb200_stats_width", "xpb200_workspace_bytes", "
            "xpb200_set_stage_timing", "xpb200_get_stage_ms", "xpb200_pack_records",
            "xpb200_debug_fill_smem", "xpb200_last_error", "xpb200_version",
            "xpb200_ingest_open", "xpb200_ingest_genes", "xpb200_ingest_copy", "xpb200_ingest_close",
-           "xpb200_ingest_encoding", "xpb200_ingest_copy_u16", "xpb200_host_alloc", "xpb200_host_free",
+           "xpb200_ingest_encoding", "xpb200_ingest_copy_u16", "xpb200_host_alloc", "xpb200_host_free", "xpb200_set_device",
            "xpb200_ingest_last_error"]
 
 
@@ -124,6 +125,8 @@ def lib():
         L.xpb200_host_alloc.argtypes = [C.c_size_t]
         L.xpb200_host_free.restype = None
         L.xpb200_host_free.argtypes = [C.c_void_p]
+        L.xpb200_set_device.restype = C.c_int32
+        L.xpb200_set_device.argtypes = [C.c_int32]
         L.xpb200_ingest_close.restype = None
         L.xpb200_ingest_close.argtypes = [C.c_void_p]
         L.xpb200_ingest_last_error.restype = C.c_char_p
@@ -138,7 +141,7 @@ def lib():
         L.xpb200_posterior_device.argtypes = [C.POINTER(XpBatch), C.POINTER(XpResult), C.c_void_p, C.c_void_p,
                                               C.c_void_p]
         L.xpb200_fit_launch_info.restype = C.c_int32
-        L.xpb200_fit_launch_info.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(XpLaunchInfo)]
+        L.xpb200_fit_launch_info.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(XpLaunchInfo)]
         L.xpb200_deep_split.restype = C.c_int32
         L.xpb200_deep_split.argtypes = [C.c_int32]
         L.xpb200_launch_count.restype = C.c_uint64
@@ -157,6 +160,41 @@ def lib():
         L.xpb200_version.restype = C.c_char_p
         _lib = L
     return _lib
+
+
+_warm = {"thread": None, "seconds": None, "device": None}
+
+
+def warm_up_async(device: int = 0):
+    """Create the CUDA context of ``device`` on a background thread (ctypes releases the GIL), so that interpreter
+    work - imports, reading ``data.index``, parsing the first chunk - overlaps the 0.3 - 1 s it takes.  No-op when the
+    library is missing or no device is usable; the compute entry points report that themselves."""
+    import threading
+    import time
+
+    if _warm["thread"] is not None or not os.path.exists(LIB_PATH):
+        return
+
+    def run():
+        t0 = time.perf_counter()
+        try:
+            L = lib()
+            if L.xpb200_set_device(int(device)) == 0:
+                L.xpb200_host_free(L.xpb200_host_alloc(4096))
+        except Exception:  # noqa: BLE001  (the real call sites raise)
+            pass
+        _warm["seconds"] = time.perf_counter() - t0
+
+    _warm["device"] = int(device)
+    _warm["thread"] = threading.Thread(target=run, name="xpb200-cuda-init", daemon=True)
+    _warm["thread"].start()
+
+
+def warm_up_wait():
+    """Seconds the background context creation took (None if it was never started)."""
+    if _warm["thread"] is not None:
+        _warm["thread"].join()
+    return _warm["seconds"]
 
 
 def check(rc: int):

@@ -45,6 +45,10 @@ def main(argv=None):
     argv = sys.argv if argv is None else argv
     options = parse_options(argv)
     if options.cmd == "diffmod":
+        import os
+        from . import _lib
+        # the CUDA context comes up on a background thread from here on, under the imports and the index reads
+        _lib.warm_up_async(int(os.environ.get("LOCAL_RANK", "0")))
         from .diffmod import diffmod
         diffmod(options)
     elif options.cmd == "postprocessing":

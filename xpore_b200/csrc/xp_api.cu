@@ -359,18 +359,34 @@ void* xpb200_host_alloc(size_t bytes) {
 void xpb200_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
+int32_t xpb200_set_device(int32_t device) {
+    CK(cudaSetDevice(device));
+    return 0;
+}
 
 int32_t xpb200_deep_split(int32_t G) {
     if (G < 1 || G > xpk::kMaxGroups) return fail(XPB200_EINVAL, "n_groups must be 1..64");
     return deep_class_split(G);
 }
 
-int32_t xpb200_fit_launch_info(int32_t device, int32_t G, int32_t max_reads, xpb200_launch_info* out) {
+int32_t xpb200_fit_launch_info(int32_t device, int32_t G, int32_t max_reads, int32_t y_format, xpb200_launch_info* out) {
     if (!out) return fail(XPB200_EINVAL, "null out");
+    if (G < 1 || G > xpk::kMaxGroups) return fail(XPB200_EINVAL, "n_groups must be 1..64");
     CK(cudaSetDevice(device));
-    Geometry g;  // the single-warp flavour (the 4-warp teams only take positions >= kSplitReads reads)
-    if (int rc = fit_geometry(G, std::min(max_reads, kSplitReads - 1), 1, &g)) return rc;
-    out->sm_count = g.sms; out->ctas_per_sm = g.ctas_per_sm; out->warps_per_cta = g.teams;
+    Geometry g;  // the class below the team split
+    if (y_format == XPB200_Y_U16) {
+        const int npw = tm_positions_per_warp(G, max_reads);
+        if (int rc = fit_tm_geometry(G, std::min(max_reads, tm_class_split(npw) - 1), npw, &g)) return rc;
+        out->warps_per_cta = g.threads / 32;
+        out->positions_per_warp = npw;
+        out->tmem_columns = xpk::fit_tm_cols(g.cap);
+    } else {
+        if (int rc = fit_geometry(G, std::min(max_reads, kSplitReads - 1), 1, &g)) return rc;
+        out->warps_per_cta = g.teams;
+        out->positions_per_warp = 0;
+        out->tmem_columns = 0;
+    }
+    out->sm_count = g.sms; out->ctas_per_sm = g.ctas_per_sm;
     out->smem_per_cta = (int32_t)g.smem; out->slab_reads = g.cap; out->regs_per_thread = g.regs;
     return 0;
 }

@@ -142,6 +142,9 @@ struct PrefilterArgs {
 // conditions present.  A two-step shuffle reduction over the four lanes and one shuffle hand the
 // moments of position j to lane j; after the four rounds all 32 lanes evaluate their Student-t
 // p-value in parallel.  Fixed summation order: results are deterministic.
+#ifndef XP_PF_MINB
+#define XP_PF_MINB 6
+#endif
 constexpr int kPfLanes = 4;                 // lanes per position
 constexpr int kPfPerRound = 32 / kPfLanes;  // positions per round
 
@@ -162,7 +165,7 @@ constexpr int kPfIntMaxReads = 32767;
 // U16X: the batch is u16-encoded and no position has more than kPfIntMaxReads reads (the host checks
 // max_reads), so every position takes the exact-integer path and the FP accumulation is compiled out.
 template <int WARPS, bool U16X>
-__global__ void __launch_bounds__(WARPS * 32, 6) xp_prefilter_kernel(PrefilterArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, XP_PF_MINB) xp_prefilter_kernel(PrefilterArgs a) {
     __shared__ int s_cond[kMaxGroups];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = a.G;

@@ -261,14 +261,25 @@ def diffmod(args, fit_fn=None):
         free_q.put(Staging() if staged else None)
     work_q = queue.Queue(maxsize=n_sets)
 
+    ingest_state = {"device_set": False}
+
     def ingest_stage(item):
         chunk_ids, nb = item
         st = free_q.get()
         t0 = time.perf_counter()
+
+        def before_alloc():  # after the parse, before the first page-locked allocation of this thread
+            if staged and not ingest_state["device_set"]:
+                from . import _lib
+                t1 = time.perf_counter()
+                timing["cuda_init_s"] = _lib.warm_up_wait()  # the context exists (created under the imports and the parse)
+                timing["cuda_init_wait_s"] = time.perf_counter() - t1
+                _lib.lib().xpb200_set_device(local_rank)  # this thread's allocations belong to this rank's GPU
+                ingest_state["device_set"] = True
         if cache is not None and all(i in cache.index_of for i in chunk_ids):
             batch = cache.batch(chunk_ids, layout)
         else:
-            batch = reader.read(chunk_ids, f_index, n_threads=n_proc, staging=st)
+            batch = reader.read(chunk_ids, f_index, n_threads=n_proc, staging=st, before_alloc=before_alloc)
             timing["ingest_parse_s"] = timing.get("ingest_parse_s", 0.0) + reader.last_times["parse_s"]
             timing["ingest_copy_s"] = timing.get("ingest_copy_s", 0.0) + reader.last_times["copy_s"]
             if batch.y is not None:
@@ -277,20 +288,18 @@ def diffmod(args, fit_fn=None):
         timing["text_bytes"] += nb
         work_q.put((chunk_ids, batch, st))
 
+    if staged and chunks:
+        # the CUDA context (0.3 - 1.5 s to create) comes up on a background thread - started at process entry by the CLI,
+        # here otherwise - while the ingest thread parses the first chunk
+        from . import _lib
+        _lib.warm_up_async(local_rank)
+
     ingest_q = queue.Queue()
     ingester = _Stage(ingest_stage, ingest_q, "xpb200-ingest")
     ingester.start()
     for c in chunks:
         ingest_q.put(c)
     ingest_q.put(None)
-    if staged and chunks:
-        # the CUDA context (0.5 - 1.5 s to create) comes up in this thread while the ingest thread parses the first
-        # chunk, instead of at the first page-locked allocation after the parse
-        t0 = time.perf_counter()
-        from . import _lib
-        _lib.lib().xpb200_host_free(_lib.lib().xpb200_host_alloc(4096))
-        timing["cuda_init_s"] = time.perf_counter() - t0
-
     # ---- stage 2: the GPU call (this thread) -----------------------------------------------------------
     def gpu_stage(chunk_ids, batch, st):
         from .fit import fit_rows

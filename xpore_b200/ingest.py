@@ -142,8 +142,10 @@ class NativeIngest:
         except Exception:
             pass
 
-    def read(self, ids, f_index, n_threads: int = 1, staging: Staging | None = None) -> Batch:
-        """Selected positions of ``ids`` (in that order) as one batch.  ``f_index``: {run: {idx: (start, end)}}."""
+    def read(self, ids, f_index, n_threads: int = 1, staging: Staging | None = None, before_alloc=None) -> Batch:
+        """Selected positions of ``ids`` (in that order) as one batch.  ``f_index``: {run: {idx: (start, end)}}.
+        ``before_alloc`` is called between the parse and the first allocation of result buffers (the driver waits for
+        its CUDA context there: page-locked staging needs it, the parse does not)."""
         import time
         t0 = time.perf_counter()
         n, R = len(ids), len(self.runs)
@@ -165,6 +167,8 @@ class NativeIngest:
             raise RuntimeError(msg)
         P, Rd, S = P.value, Rd.value, S.value
         t1 = time.perf_counter()
+        if before_alloc is not None:
+            before_alloc()
         G = self.layout.n_groups
         max_reads = C.c_int32(0)
         enc = self.L.xpb200_ingest_encoding(self.handle, C.byref(max_reads))

@@ -149,7 +149,80 @@ def write_dataset(root: str, spec: Spec, km: KmerModel | None = None, first_pos:
     return path
 
 
-def write_dataset_from_batch(root: str, spec: Spec, batch: Batch, km: KmerModel | None = None, first_pos: int = 100) -> str:
+def write_dataset_from_batch(root: str, spec: Spec, batch: Batch, km: KmerModel | None = None, first_pos: int = 100,
+                             n_workers: int = 1) -> str:
+    """``data.json`` / ``data.index`` per run and ``config.yml`` holding exactly the reads of a run-grouped ``batch``
+    (``make_batch(..., keys=True)`` of a spec without pooling): the fast producer for the CLI benchmark - the text of
+    10^5 positions in seconds, where :func:`write_dataset` formats every float in Python.  Every read must be a
+    non-negative 2-decimal value below 655.36 (``dataprep.py:638`` rounds to 2 decimals); numbers are written as
+    ``json.dump`` / ``repr`` would write them."""
+    km = km or KmerModel.load()
+    assert not batch.layout.pooling and batch.ids and batch.positions and batch.kmers
+    info = spec.data_info(root)
+    q = np.rint(batch.y[:batch.n_reads] * 100.0).astype(np.int64)
+    assert q.min() >= 0 and q.max() < 65536 and np.array_equal(q / 100.0, batch.y[:batch.n_reads])
+    text = np.empty(65536, dtype=object)
+    for code in np.unique(q):
+        text[int(code)] = repr(int(code) / 100.0)
+    words = text[q]  # one python str per read
+    G = batch.layout.n_groups
+    starts = batch.read_off[:-1, None] + np.concatenate([np.zeros((batch.n_positions, 1), np.int64),
+                                                         np.cumsum(batch.grp_len, axis=1)[:, :-1]], axis=1)  # [P, G]
+    gene_first = [0] + [p for p in range(1, batch.n_positions) if batch.ids[p] != batch.ids[p - 1]] + [batch.n_positions]
+    runs = [(c, run) for c, rd in info.items() for run in rd]
+    assert len(runs) == G
+
+    def write_run(g):
+        c, run = runs[g]
+        d = info[c][run]
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "data.json"), "w") as fj, open(os.path.join(d, "data.index"), "w") as fi:
+            fi.write("idx,start,end\n")
+            off = 0
+            for a, b in zip(gene_first[:-1], gene_first[1:]):
+                idx = batch.ids[a]
+                parts = ['{"%s":{' % idx]
+                for p in range(a, b):
+                    s0 = int(starts[p, g])
+                    parts.append('%s"%s":{"%s":[%s]}' % ("," if p > a else "", batch.positions[p], batch.kmers[p],
+                                                          ",".join(words[s0:s0 + int(batch.grp_len[p, g])])))
+                parts.append("}}\n")
+                line = "".join(parts)
+                fj.write(line)
+                fi.write("%s,%d,%d\n" % (idx, off, off + len(line)))
+                off += len(line)
+
+    # one forked writer per run (the arrays are shared copy-on-write); in-process when fork is not an option
+    workers = min(G, int(n_workers) if n_workers else 1)
+    if workers > 1:
+        import multiprocessing as mp
+        procs = [mp.get_context("fork").Process(target=write_run, args=(g,)) for g in range(G)]
+        live = []
+        for pr in procs:
+            pr.start()
+            live.append(pr)
+            if len(live) >= workers:
+                live.pop(0).join()
+        for pr in live:
+            pr.join()
+        assert all(pr.exitcode == 0 for pr in procs), [pr.exitcode for pr in procs]
+    else:
+        for g in range(G):
+            write_run(g)
+    cfg = {"data": {c: {run.split("-", 1)[1]: d for run, d in rd.items()} for c, rd in info.items()},
+           "out": os.path.join(root, "out")}
+    if spec.method:
+        cfg["method"] = dict(spec.method)
+    if spec.criteria:
+        cfg["criteria"] = dict(spec.criteria)
+    path = os.path.join(root, "config.yml")
+    with open(path, "w") as f:
+        yaml.safe_dump(cfg, f, sort_keys=False)
+    return path
+
+
+def write_dataset_from_batch(root: str, spec: Spec, batch: Batch, km: KmerModel | None = None, first_pos: int = 100,
+                             n_workers: int = 1) -> str:
     """``data.json`` / ``data.index`` per run and ``config.yml`` holding exactly the reads of a run-grouped ``batch``
     (``make_batch(..., keys=True)`` of a spec without pooling): the fast producer for the CLI benchmark - the text of
     10^5 positions in seconds, where :func:`write_dataset` formats every float in Python.  Every read must be a
