@@ -137,6 +137,10 @@ FitKernelFn tm_kernel(int npw, int maxt, int G) {
         }
         return tm_kernel_g<2, 0>(maxt);
     }
+    if (exp_int("XPB200_TM_GT", 1)) {  // 6 x 3 runs (c5: 19 warps), 2 x 2 runs of a deep batch (c4: 20 warps)
+        if (G == 18 && maxt == 640) return xpk::xp_fit_tm_kernel<1, 640, 18>;
+        if (G == 4 && maxt == 640) return xpk::xp_fit_tm_kernel<1, 640, 4>;
+    }
     return tm_kernel_g<1, 0>(maxt);
 }
 
@@ -206,12 +210,13 @@ int fit_geometry(int G, int cap_reads, int tw, Geometry* g) {
 int tm_positions_per_warp(int G, int max_reads) {
     return exp_int("XPB200_TM_NPW", (2 * G + 4 <= 16 && max_reads < kSplitReads) ? 2 : 1);
 }
-// Reads the tensor-memory kernel can hold per position with 28 warps resident (7 column blocks per TMEM quadrant):
-// 576 with two positions per warp, 1152 with one.  Its class takes the positions below min(kSplitReads, that).
-int tm_class_split(int npw) {
-    const int cols = (xpk::kTmColumns / (7 * npw)) & ~1;  // columns per position
-    return std::min(kSplitReads, (cols / 2) * 32);
-}
+// First read count of the 4-warp teams' class when the single-warp class runs on the tensor-memory kernel (a bucket
+// boundary of the worklist).  Two positions per warp: 576 (2 x 36 columns x 7 column blocks per quadrant = 504 of 512
+// columns keep 28 warps resident).  One position per warp: 1536 - a warp is the more efficient unit for a position
+// well beyond the former 1024 (no warps idling through a leader's scalar phase), although 96 columns per position leave
+// only 5 column blocks per quadrant = 20 warps (c4: 7.62 ms at 1024 / 28 warps, 7.47 at 1152 / 28, 7.37 at 1536 / 20,
+// 7.46 at 2048 / 16).
+int tm_class_split(int npw) { return exp_int("XPB200_TM_SPLIT", npw == 2 ? 576 : 1536); }
 // Launch geometry of xp_fit_tm_kernel: one warp per `np` positions, reads in tensor memory.
 int fit_tm_geometry(int G, int cap_reads, int npw, Geometry* g) {
     int dev = 0;

@@ -51,14 +51,8 @@
 #ifndef XP_FIT_FLOOR
 #define XP_FIT_FLOOR 0
 #endif
-#ifndef XP_FIT_PARK
-#define XP_FIT_PARK 1
-#endif
-#if XP_FIT_PARK
+// per-position values the leader needs once per sweep are parked in shared memory (pc[]): XP_PK(i, name) re-reads slot i
 #define XP_PK(i, var) parked(pc + (i))
-#else
-#define XP_PK(i, var) (var)
-#endif
 
 namespace xpk {
 
@@ -670,7 +664,7 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
         if (kpar) c.mp = loc1;
         double Hent = 0.0;
         double elbo = -INFINITY, elbo_old = -INFINITY;
-        if (XP_FIT_PARK && leader && lane == 0) {
+        if (leader && lane == 0) {
             pc[0] = m0;
             pc[1] = a0;
             pc[2] = b0;
@@ -758,7 +752,7 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_kernel(FitArgs a) {
                         go = false;
                     } else {
                         elbo_old = elbo;
-                        if (XP_FIT_PARK && lane == 0) pc[7] = elbo;
+                        if (lane == 0) pc[7] = elbo;
                         if (rule == 1) {
                             st |= STATUS_CONVERGED;
                             go = false;
