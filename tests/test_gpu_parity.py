@@ -326,14 +326,16 @@ def test_pack_records_device(torch_cuda):
 def test_scaled_integer_decode_exhaustive(torch_cuda):
     """The division-free decode of u16/i32 reads equals IEEE q/100 for every u16 value and for random
     i32 values (prefilter p-values of single-value positions would differ otherwise); checked through
-    the fit of a batch whose reads enumerate all u16 codes."""
+    the fit of a batch whose reads enumerate all u16 codes.  512 reads per position: one warp per position in either
+    encoding (the tensor-memory kernel for u16, the shared-memory one for f64 / i32), whose summation orders are the
+    same - the records can only be bit-identical if every decoded read is."""
     torch = torch_cuda
     from xpore_b200.batch import Batch, Layout
     lay = Layout(["A", "B"], ["A-r1", "B-r1"], [0, 1], False)
     rng = np.random.default_rng(3)
     for fmt, q in ((2, np.arange(65536, dtype=np.int64)), (1, rng.integers(-2 ** 31 + 2, 2 ** 31 - 2, 65536))):
         y = q / 100.0
-        P = 64
+        P = 128
         per = len(y) // P
         grp_len = np.full((P, 2), per // 2, dtype=np.int32)
         read_off = np.arange(P + 1, dtype=np.int64) * per
@@ -418,7 +420,8 @@ def test_edge_case_positions_vs_oracle(torch_cuda):
     """Hand-made positions at the corners of the input space, one batch, every position against the
     oracle: identical reads (zero variance), two far-apart clusters (|d| beyond the +-500 clip of
     gmm.py:240), reads far from the k-mer mean, the smallest groups the selection lets through, a run
-    missing at a position, and read counts on both sides of the 1-warp / 4-warp split (1023 / 1024)."""
+    missing at a position, and read counts on both sides of the 1-warp / 4-warp split (1023 / 1024 for f64 reads,
+    1535 / 1536 for the one-position-per-warp tensor-memory kernel of a deep u16 batch)."""
     from xpore_b200.batch import Batch, Layout
     rng = np.random.default_rng(11)
     lay = Layout(["KO", "WT"], ["KO-r1", "KO-r2", "WT-r1", "WT-r2"], [0, 0, 1, 1], False)
@@ -434,7 +437,7 @@ def test_edge_case_positions_vs_oracle(torch_cuda):
     add([rng.normal(30, 2, 25) for _ in range(4)], kmean=120.0, kstd=2.0)        # all reads 45 sigma off the prior
     add([rng.normal(100, 3, 2), rng.normal(100, 3, 2), rng.normal(108, 4, 2), rng.normal(108, 4, 2)])   # 2 reads per run
     add([rng.normal(100, 3, 30), [], rng.normal(106, 4, 30), rng.normal(106, 4, 31)])                    # a run absent
-    for n in (1023, 1024, 1025):                                                  # single-warp / 4-warp team split
+    for n in (1023, 1024, 1025, 1535, 1536, 1537):                                # single-warp / 4-warp team splits
         per = [n // 4 + (1 if j < n % 4 else 0) for j in range(4)]
         add([np.r_[rng.normal(100, 3, m - m // 3), rng.normal(109, 4, m // 3)] if j >= 2 else rng.normal(100, 3, m)
              for j, m in enumerate(per)])
@@ -459,6 +462,49 @@ def test_edge_case_positions_vs_oracle(torch_cuda):
             np.testing.assert_allclose(res.alpha[p], f["alpha"], rtol=1e-5, err_msg=str(p))
             np.testing.assert_allclose(res.beta[p], f["beta"], rtol=1e-5, err_msg=str(p))
             np.testing.assert_allclose(res.N[p][present], f["N"], rtol=1e-5, atol=1e-9, err_msg=str(p))
+
+
+def test_pair_class_boundary_vs_oracle(torch_cuda):
+    """A u16 batch without deep positions runs two positions per warp (576 reads each in tensor memory); positions from
+    576 reads up go to the 4-warp teams.  Read counts on both sides of that split, an odd number of positions (one warp
+    ends up with a single position) and a warp whose two positions stop many sweeps apart - every position against the
+    oracle; then the f64 twin (one position per warp in shared memory): bit-identical below the split."""
+    from xpore_b200.batch import Batch, Layout
+    rng = np.random.default_rng(23)
+    lay = Layout(["KO", "WT"], ["KO-r1", "KO-r2", "KO-r3", "WT-r1", "WT-r2", "WT-r3"], [0, 0, 0, 1, 1, 1], False)
+    G = 6
+    km, ks = 100.0, 3.0
+    sizes = [575, 576, 577, 600, 64, 33, 130, 511, 512, 513, 96]
+    groups = []
+    for q, n in enumerate(sizes):
+        per = [n // G + (1 if j < n % G else 0) for j in range(G)]
+        shift = 0.4 if q % 3 == 0 else 8.0  # barely separated mixtures take many sweeps, clear ones few
+        groups.append([np.round(np.r_[rng.normal(km, ks, m - m // 3), rng.normal(km + shift, ks, m // 3)] if j >= 3
+                                else rng.normal(km, ks, m), 2) for j, m in enumerate(per)])
+    y = np.concatenate([np.concatenate(g) for g in groups])
+    glen = np.asarray([[len(x) for x in g] for g in groups], dtype=np.int32)
+    off = np.zeros(len(sizes) + 1, dtype=np.int64)
+    np.cumsum(glen.sum(axis=1), out=off[1:])
+    batch = Batch(lay, y, off, glen, np.full(len(sizes), km), np.full(len(sizes), ks))
+    method = xf.Method()
+    ref = xf.fit_batch(batch, method)  # f64: shared-memory kernel
+    assert batch.encode_reads() == 2
+    res = xf.fit_batch(batch, method)  # u16: tensor-memory kernel, two positions per warp
+    assert res.n_fitted == len(sizes)
+    assert len(set(res.n_iter.tolist())) > 3
+    for p in range(len(sizes)):
+        f, present = _oracle_fit(batch, p, method)
+        assert res.n_iter[p] == f["n_iterations"], (p, sizes[p], res.n_iter[p], f["n_iterations"])
+        assert bool(res.status[p] & xf.CONVERGED) == f["converged"], p
+        np.testing.assert_allclose(res.mu[p], f["location"], rtol=1e-5, err_msg=str(p))
+        np.testing.assert_allclose(res.alpha[p], f["alpha"], rtol=1e-5, err_msg=str(p))
+        np.testing.assert_allclose(res.beta[p], f["beta"], rtol=1e-5, err_msg=str(p))
+        np.testing.assert_allclose(res.N[p][present], f["N"], rtol=1e-5, atol=1e-9, err_msg=str(p))
+    below = np.asarray(sizes) < 576
+    np.testing.assert_array_equal(res.n_iter, ref.n_iter)
+    np.testing.assert_array_equal(res.fit[below], ref.fit[below])
+    np.testing.assert_array_equal(res.stats[below], ref.stats[below])
+    np.testing.assert_allclose(res.fit, ref.fit, rtol=1e-11, atol=0)
 
 
 def test_fit_host_rows_equals_dense_records(torch_cuda):
@@ -549,10 +595,14 @@ def test_deep_positions_vs_oracle(torch_cuda, grouping):
                 np.testing.assert_allclose(res.pval[p], pv, rtol=1e-8, atol=1e-300)
         if ref is None:
             ref = res
-        else:  # the encoding changes nothing but the bytes moved
+        else:  # the encoding changes the bytes moved - and the class of the 1500-read position (u16: one warp with its
+            # reads in tensor memory, f64: a 4-warp team), i.e. the order of its sums; nothing else
             np.testing.assert_array_equal(res.n_iter, ref.n_iter)
-            np.testing.assert_array_equal(res.fit, ref.fit)
-            np.testing.assert_array_equal(res.stats, ref.stats)
+            same = np.asarray([not (1024 <= n < 1536) for n in sizes])
+            np.testing.assert_array_equal(res.fit[same], ref.fit[same])
+            np.testing.assert_array_equal(res.stats[same], ref.stats[same])
+            np.testing.assert_allclose(res.fit, ref.fit, rtol=1e-11, atol=0)
+            np.testing.assert_allclose(res.stats, ref.stats, rtol=1e-9, atol=1e-300, equal_nan=True)
     # the same batch resident on the device, and as rows
     out = xf.fit_device(xf.DeviceBatch(batch), method)
     torch_cuda.cuda.synchronize()

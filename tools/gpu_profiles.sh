@@ -29,6 +29,9 @@ cap() { # config positions count
   pos=""; [ "$np" != "0" ] && pos="--positions $np"
   timeout 1200 ncu --set full --import-source on --clock-control none -k regex:"xp_(prefilter|worklist|fit|stats)" -c $cnt -f -o $D/step_$cfg \
     python bench.py --config $cfg $pos --steps 1 --warmup 0 --no-cpu-baseline --no-cli > $D/ncu_step_$cfg.log 2>&1; echo "ncu $cfg rc=$?"
+    # summarised on the box: the reports of four configurations exceed what gpurun copies back
+    python tools/ncu_summary.py $D/step_$cfg.ncu-rep > $D/step_$cfg.ncu_summary.txt 2>&1
+    rm -f $D/step_$cfg.ncu-rep
 }
 cap c2 0 7
 cap c3 0 7
@@ -36,6 +39,10 @@ cap c4 0 8
 cap c5 1000000 8
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:"xp_(pack|count|concat)" -c 4 -f -o $D/pack_c2 \
   python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-cli > $D/ncu_pack_c2.log 2>&1; echo "ncu pack rc=$?"
+python tools/ncu_summary.py $D/pack_c2.ncu-rep > $D/pack_c2.ncu_summary.txt 2>&1
+rm -f $D/pack_c2.ncu-rep
 ls -la $D
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "edge_case or encoded_reads or device_path_vs_oracle" > $D/sanitizer.log 2>&1; echo "sanitizer rc=$?"
-tail -3 $D/sanitizer.log
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:"xp_fit_tm" -c 1 -f -o $D/fit_tm_c2 \
+  python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-cli > $D/ncu_fit_tm_c2.log 2>&1; echo "ncu fit_tm rc=$?"
+python tools/ncu_loops.py $D/fit_tm_c2.ncu-rep 2.0 > $D/fit_tm_c2.loops.txt 2>&1
+du -sh $D

@@ -498,12 +498,22 @@ __global__ void xp_worklist_scan(WorklistArgs a) {  // <<<1, kBuckets>>>
     }
 }
 
+// Warp-aggregated: the lanes of a warp that fall into the same bucket take their slots with one atomic (a design
+// with similar coverage everywhere - pooled c3, c5 - puts a whole batch into a handful of buckets, and a million
+// single atomics on three addresses ran 0.2 - 0.26 ms at 0.5 % issue utilisation).
 __global__ void xp_worklist_scatter(WorklistArgs a) {
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < a.P; p += gridDim.x * blockDim.x) {
-        if (a.status && !(a.status[p] & STATUS_SELECTED)) continue;
-        const int b = cost_bucket((int)(a.read_off[p + 1] - a.read_off[p]));
-        const uint32_t slot = atomicAdd(&a.cursor[b], 1u);
-        a.worklist[slot] = p;
+    const int lane = threadIdx.x & 31;
+    const int stride = gridDim.x * blockDim.x;
+    for (int p0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); p0 < a.P; p0 += stride) {  // warp-uniform trip count
+        const int p = p0 + lane;
+        const bool sel = p < a.P && !(a.status && !(a.status[p] & STATUS_SELECTED));
+        const int b = sel ? cost_bucket((int)(a.read_off[p + 1] - a.read_off[p])) : -1 - lane;  // unselected: a group of one
+        const unsigned peers = __match_any_sync(kFull, b);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (sel && lane == leader) base = atomicAdd(&a.cursor[b], (uint32_t)__popc(peers));
+        base = __shfl_sync(kFull, base, leader);
+        if (sel) a.worklist[base + __popc(peers & ((1u << lane) - 1u))] = p;
     }
 }
 
