@@ -344,8 +344,9 @@ def test_scaled_integer_decode_exhaustive(torch_cuda):
         ref = xf.fit_batch(b, m)
         assert b.encode_reads() == fmt
         enc = xf.fit_batch(b, m)
-        if fmt == 2:  # the u16 prefilter sums integers exactly: equal to rounding; the fit decodes every read
-            np.testing.assert_allclose(enc.pval, ref.pval, rtol=1e-11, atol=0, equal_nan=True)
+        if fmt == 2:  # the u16 prefilter sums integers exactly: equal to the rounding of the t statistic, which a p-value of
+            # 1e-155 (512 reads on either side, far apart) magnifies by its logarithmic slope; the fit decodes every read
+            np.testing.assert_allclose(enc.pval, ref.pval, rtol=1e-6, atol=0, equal_nan=True)
         else:
             np.testing.assert_array_equal(ref.pval, enc.pval)
         np.testing.assert_array_equal(ref.fit, enc.fit)
@@ -603,12 +604,12 @@ def test_deep_positions_vs_oracle(torch_cuda, grouping):
             np.testing.assert_array_equal(res.stats[same], ref.stats[same])
             np.testing.assert_allclose(res.fit, ref.fit, rtol=1e-11, atol=0)
             np.testing.assert_allclose(res.stats, ref.stats, rtol=1e-9, atol=1e-300, equal_nan=True)
-    # the same batch resident on the device, and as rows
+    # the same (u16) batch resident on the device, and as rows
     out = xf.fit_device(xf.DeviceBatch(batch), method)
     torch_cuda.cuda.synchronize()
     dev = out.to_host()
-    np.testing.assert_array_equal(dev.n_iter, ref.n_iter)
-    np.testing.assert_array_equal(dev.fit, ref.fit)
+    np.testing.assert_array_equal(dev.n_iter, res.n_iter)
+    np.testing.assert_array_equal(dev.fit, res.fit)
 
 
 def test_understated_max_reads_is_flagged(torch_cuda):
