@@ -687,8 +687,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     }
     const int nchunks = (int)cut.size() - 1;
     ++dc->calls;
-    const char* trace_env = getenv("XPB200_TRACE");  // diagnostic only: timed events per chunk, printed to stderr
-    const bool trace = trace_env && *trace_env && atoi(trace_env) != 0 && !async;
+    const bool trace = exp_int("XPB200_TRACE", 0) != 0 && !async;  // experiment builds: timed events per chunk, printed to stderr
     if (trace && !dc->t_0) {
         CK(cudaEventCreate(&dc->t_0));
         for (int i = 0; i < kMaxChunks; ++i) {
