@@ -64,3 +64,23 @@ def test_no_cpu_fallback_in_product():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(root, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "xp_emul" not in src, f
+
+
+def test_torch_custom_op_registered_and_has_no_cpu_path():
+    """`torch.ops.xpore_b200.fit` exists after importing xpore_b200.torch_op; shapes follow from the fake kernel; CPU tensors
+    are refused (the operator has a CUDA implementation only - no fallback)."""
+    import pytest
+    import torch
+    import xpore_b200.torch_op  # noqa: F401
+    from xpore_b200.fit import fit_width, stats_width
+    op = torch.ops.xpore_b200.fit
+    P, G, Cn = 5, 4, 2
+    args = (torch.zeros(40, dtype=torch.float64), torch.arange(0, 48, 8, dtype=torch.int64),
+            torch.full((P * G,), 2, dtype=torch.int32), torch.full((P,), 100.0, dtype=torch.float64),
+            torch.full((P,), 3.0, dtype=torch.float64), torch.tensor([0, 0, 1, 1], dtype=torch.int32), Cn, 8, 500, 1e-5, 1, 0.1,
+            0.001)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        op(*args)
+    meta = tuple(a.to("meta") if isinstance(a, torch.Tensor) else a for a in args)
+    out = op(*meta)
+    assert [tuple(t.shape) for t in out] == [(P,), (P,), (P,), (P, fit_width(G)), (P, stats_width(G, Cn)), (1,)]

@@ -665,3 +665,32 @@ def test_cli_two_ranks_nccl(torch_cuda, tmp_path):
         assert_same_rows(rows1, rows2)
         lines = open(os.path.join(out, "diffmod.log")).read().splitlines()
         assert sorted(lines[1:-1]) == sorted(case["expected"]["ids"]) and lines[-1] == "--- SUCCESSFULLY FINISHED ---"
+
+
+@pytest.mark.gpu
+def test_torch_custom_op_equals_fit_device(torch_cuda):
+    """torch.ops.xpore_b200.fit (xpore_b200/torch_op.py) returns what fit_device returns, for f64 and u16 reads."""
+    import xpore_b200.torch_op  # noqa: F401
+    torch = torch_cuda
+    spec = Spec({"KO": 3, "WT": 3}, reads_lo=20, reads_hi=100, f_mod=0.3, seed=77,
+                method={"prefiltering": {"method": "t-test", "threshold": 0.1}})
+    batch = make_batch(spec, KmerModel.load(), n_positions=4000)
+    method = xf.Method.from_dict(spec.method)
+    for encode in (False, True):
+        if encode:
+            assert batch.encode_reads() == 2
+        db = xf.DeviceBatch(batch)
+        ref = xf.fit_device(db, method).to_host()
+        d = db.dev
+        m = method.c_struct()
+        status, n_iter, pval, fit, stats, n_fitted = torch.ops.xpore_b200.fit(
+            d["y"], d["read_off"], d["grp_len"], d["kmer_mean"], d["kmer_std"], d["grp_cond"], db.C, db.max_reads,
+            m.max_iters, m.stopping_criteria, m.prefilter, m.prefilter_threshold, m.dirichlet_conc)
+        torch.cuda.synchronize()
+        assert int(n_fitted.item()) == ref.n_fitted > 100
+        np.testing.assert_array_equal(status.cpu().numpy().view(np.uint32), ref.status)
+        np.testing.assert_array_equal(n_iter.cpu().numpy(), ref.n_iter)
+        np.testing.assert_array_equal(pval.cpu().numpy(), ref.pval)
+        sel = ref.selected
+        np.testing.assert_array_equal(fit.cpu().numpy()[sel], ref.fit[sel])
+        np.testing.assert_array_equal(stats.cpu().numpy()[sel], ref.stats[sel])
