@@ -438,6 +438,7 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
     xpk::WorklistArgs wa;
     wa.status = sel; wa.read_off = b->read_off; wa.P = P; wa.hist = ws.hist; wa.cursor = ws.cursor;
     wa.n_work = ws.n_work; wa.worklist = ws.worklist; wa.n_large = ws.n_large;
+    wa.pval = (m->prefilter && exp_int("XPB200_LPT", 1)) ? r->pval : nullptr;
     // Three classes by depth, each with its own launch: n >= deep_split reads -> streaming CTAs (reads stay in global
     // memory: no cap), n >= kSplitReads -> 4-warp teams, the rest -> one warp per position.
     // u16 batches: the single-warp class runs on the tensor-memory kernel, which holds fewer reads per position when

@@ -21,7 +21,7 @@ using namespace xpc;
 
 constexpr int kMaxGroups = 64;
 constexpr int kMaxConditions = 32;
-constexpr int kBuckets = 512;
+constexpr int kBuckets = 1024;   // worklist buckets: [0, 512) by read count, [512, 1024) single-warp class by expected sweeps x read count
 constexpr unsigned kFull = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------
@@ -439,15 +439,27 @@ __global__ void __launch_bounds__(WARPS * 32, XP_PF_MINB) xp_prefilter_kernel(Pr
 // Worklist: selected positions ordered by descending read count (semi-log buckets), so the
 // persistent fit kernel starts the longest positions first.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int cost_bucket(int n) {  // larger n -> smaller bucket id
+constexpr int kCostBuckets = 512;  // semi-log read-count classes (16 per octave)
+__device__ __forceinline__ int cost_class(int n) {
     int cls;
     if (n < 16) cls = n < 0 ? 0 : n;
     else {
         const int e = 31 - __clz(n);
         cls = 16 + (e - 4) * 16 + ((n >> (e - 4)) & 15);
     }
-    cls = min(cls, kBuckets - 1);
-    return kBuckets - 1 - cls;
+    return min(cls, kCostBuckets - 1);
+}
+__device__ __forceinline__ int cost_bucket(int n) { return kCostBuckets - 1 - cost_class(n); }  // larger n -> smaller bucket id
+// Bucket of a position in the worklist.  Positions of the team / streaming classes (n >= split > 0) are ordered by read
+// count alone, deepest first: buckets [0, 512), the class boundaries are bucket boundaries.  The single-warp class follows
+// in [512, 1024), ordered by how long a position is expected to sweep, then by read count: VB-EM needs the more sweeps
+// the less the two conditions differ (c2: 66 sweeps on average, up to 270, where the prefilter's p >= 1e-2; 34, up to 92,
+// where p < 1e-10), so the prefilter's p-value sorts the long runners to the front and the persistent kernel's tail is made
+// of short positions (longest-processing-time-first scheduling; the order changes no result).
+__device__ __forceinline__ int worklist_bucket(int n, int split, double pval) {
+    if (split > 0 && n >= split) return cost_bucket(n);
+    const int pc = !(pval < 1e-2) ? 0 : !(pval < 1e-5) ? 1 : !(pval < 1e-10) ? 2 : 3;  // NaN (no test): class 0
+    return kCostBuckets + pc * 128 + (127 - min(cost_class(n), 127));
 }
 
 struct WorklistArgs {
@@ -462,6 +474,7 @@ struct WorklistArgs {
     int split;           // a bucket boundary (see cost_bucket), or 0: no large class
     uint32_t* n_deep;    // [1] entries with at least `split_deep` reads (the first ones of the worklist)
     int split_deep;      // a bucket boundary above `split`, or 0: no streaming class
+    const double* pval;  // prefilter p-values (null: none), see worklist_bucket
 };
 
 __global__ void xp_worklist_count(WorklistArgs a) {
@@ -470,7 +483,7 @@ __global__ void xp_worklist_count(WorklistArgs a) {
     __syncthreads();
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < a.P; p += gridDim.x * blockDim.x) {
         if (a.status && !(a.status[p] & STATUS_SELECTED)) continue;
-        atomicAdd(&h[cost_bucket((int)(a.read_off[p + 1] - a.read_off[p]))], 1u);
+        atomicAdd(&h[worklist_bucket((int)(a.read_off[p + 1] - a.read_off[p]), a.split, a.pval ? a.pval[p] : NAN)], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < kBuckets; i += blockDim.x)
@@ -507,7 +520,8 @@ __global__ void xp_worklist_scatter(WorklistArgs a) {
     for (int p0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); p0 < a.P; p0 += stride) {  // warp-uniform trip count
         const int p = p0 + lane;
         const bool sel = p < a.P && !(a.status && !(a.status[p] & STATUS_SELECTED));
-        const int b = sel ? cost_bucket((int)(a.read_off[p + 1] - a.read_off[p])) : -1 - lane;  // unselected: a group of one
+        const int b = sel ? worklist_bucket((int)(a.read_off[p + 1] - a.read_off[p]), a.split, a.pval ? a.pval[p] : NAN)
+                          : -1 - lane;  // unselected: a group of one
         const unsigned peers = __match_any_sync(kFull, b);
         const int leader = __ffs(peers) - 1;
         uint32_t base = 0;
