@@ -58,3 +58,10 @@ def main(argv=None):
 
 if __name__ == "__main__":
     main(sys.argv)
+    # Single-process runs leave without tearing down: the outputs are closed, and unwinding the CUDA context and some
+    # hundred MB of page-locked staging buffers costs 0.3 - 0.8 s of wall clock that the operating system does for free.
+    import os
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
