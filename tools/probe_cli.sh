@@ -21,12 +21,5 @@ import json; t=json.load(open('/dev/shm/probe/t.json'))
 print({k:(round(v,3) if isinstance(v,float) else v) for k,v in t.items() if k.endswith('_s') or k=='ingest_threads'})"
   done
 }
-echo "== no other context"; run 1 16 16 8
-python -c "
-import ctypes, time
-L=ctypes.CDLL('xpore_b200/libxpore_b200.so'); L.xpb200_host_alloc.restype=ctypes.c_void_p; L.xpb200_host_alloc(4096); print('holder up', flush=True); time.sleep(60)" &
-HP=$!
-sleep 5
-echo "== another process holds a context"; run 1 16 16 8
-kill $HP
+echo "== no other context"; run 16 8 16 8 16
 rm -rf /dev/shm/probe
