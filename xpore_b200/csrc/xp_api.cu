@@ -319,9 +319,14 @@ int launch_prefilter(const xpb200_batch* b, const xpb200_method* m, uint32_t* st
     constexpr int W = 4;
     const int tiles = (b->n_positions + 31) / 32;
     const int grid = (tiles + W - 1) / W;
-    if (b->y_format == XPB200_Y_U16 && b->max_reads <= xpk::kPfIntMaxReads)
+    if (b->y_format == XPB200_Y_U16 && b->max_reads <= xpk::kPfIntMaxReads) {
+        // exact integer sums.  Group slots blocked by condition (every batch builder's order): the first kernel; slots
+        // interleaved by condition: the second.  Each returns at once in the other's case - grp_cond is device memory
+        // and this entry point does not synchronise, so the choice is made on the device.
+        xpk::xp_prefilter_u16_kernel<W><<<grid, W * 32, 0, st>>>(a);
         xpk::xp_prefilter_kernel<W, true><<<grid, W * 32, 0, st>>>(a);
-    else
+        ++g_launches;
+    } else
         xpk::xp_prefilter_kernel<W, false><<<grid, W * 32, 0, st>>>(a);
     ++g_launches;
     CK(cudaGetLastError());

@@ -162,6 +162,19 @@ struct PfIntMoments {
 };
 constexpr int kPfIntMaxReads = 32767;
 
+// group slots blocked by condition: every condition's slots are adjacent
+__device__ __forceinline__ bool pf_cond_sorted(const int* s_cond, int G) {
+    bool sorted = true;
+    unsigned seen = 1u << s_cond[0];
+    for (int g = 1; g < G; ++g) {
+        if (s_cond[g] != s_cond[g - 1]) {
+            sorted = sorted && !((seen >> s_cond[g]) & 1u);
+            seen |= 1u << s_cond[g];
+        }
+    }
+    return sorted;
+}
+
 // U16X: the batch is u16-encoded and no position has more than kPfIntMaxReads reads (the host checks
 // max_reads), so every position takes the exact-integer path and the FP accumulation is compiled out.
 template <int WARPS, bool U16X>
@@ -171,19 +184,9 @@ __global__ void __launch_bounds__(WARPS * 32, XP_PF_MINB) xp_prefilter_kernel(Pr
     const int G = a.G;
     for (int g = threadIdx.x; g < G; g += blockDim.x) s_cond[g] = a.grp_cond[g];
     __syncthreads();
-    // Group slots blocked by condition (every condition's slots are adjacent - the batch builders emit the runs
-    // condition by condition): at a position with exactly two conditions present the reads of the condition whose
-    // block comes first are a prefix of the position, and the streaming loop needs no group walk.
-    bool cond_sorted = true;
-    {
-        unsigned seen = 1u << s_cond[0];
-        for (int g = 1; g < G; ++g) {
-            if (s_cond[g] != s_cond[g - 1]) {
-                cond_sorted = cond_sorted && !((seen >> s_cond[g]) & 1u);
-                seen |= 1u << s_cond[g];
-            }
-        }
-    }
+    // u16 batches whose group slots are blocked by condition (every condition's slots are adjacent - all batch
+    // builders emit the runs condition by condition) are xp_prefilter_u16_kernel's, launched in front of this one
+    if (U16X && pf_cond_sorted(s_cond, G)) return;
     const int tile = blockIdx.x * WARPS + warp;
     const int p0 = tile * 32;
     if (p0 >= a.P) return;
@@ -235,21 +238,12 @@ __global__ void __launch_bounds__(WARPS * 32, XP_PF_MINB) xp_prefilter_kernel(Pr
                 // Integer sums are exact, so their order is free: a lane sums the reads of its current run inside one
                 // group (one add and one 64-bit multiply-add per read) and moves the run's sums to the group's side
                 // when it crosses into another group.  Counts come from the group lengths.
-                unsigned run1 = 0u, tot1 = 0u;  // cond_sorted: run = the prefix condition's sums, tot = the sums of all reads
-                unsigned long long run2 = 0ull, tot2 = 0ull;
-                // cond_sorted: the first `split` reads belong to the condition of the first present slot (side a or b)
-                int split = 0, n_a = 0;
-                bool prefix_a = true;
-                if (U16X) {
-                    int cfirst = -1;
-                    for (int gg = 0; gg < G; ++gg) {
-                        const int len = glen[gg];
-                        if (len > 0 && cfirst < 0) cfirst = s_cond[gg];
-                        if (s_cond[gg] == cfirst) split += len;
-                        if (s_cond[gg] == ca) n_a += len;
-                    }
-                    prefix_a = (cfirst == ca);
-                }
+                unsigned run1 = 0u;
+                unsigned long long run2 = 0ull;
+                int n_a = 0;
+                if (U16X)
+                    for (int gg = 0; gg < G; ++gg)
+                        if (s_cond[gg] == ca) n_a += glen[gg];
                 auto flush = [&]() {
                     if (side_a) {
                         mi.s1a += run1;
@@ -307,25 +301,7 @@ __global__ void __launch_bounds__(WARPS * 32, XP_PF_MINB) xp_prefilter_kernel(Pr
                         const unsigned x[4] = {__funnelshift_r(w0, w1, hs), __funnelshift_r(w1, w2, hs),
                                                __funnelshift_r(w2, w3, hs), __funnelshift_r(w3, w4, hs)};
                         const int ibase = bq << 3;
-                        if (U16X && cond_sorted) {
-                            // branch free: the block's valid reads (k < n - ibase) and those of the prefix condition
-                            // (k < split - ibase) are selected by masks on the packed words; integer sums of all
-                            // valid reads and of the prefix's reads, the other side follows by subtraction.
-                            const int b16 = max(min(n - ibase, 8), 0) * 16, a16 = max(min(split - ibase, 8), 0) * 16;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const unsigned mv = __funnelshift_rc(0xffffffffu, 0u, max(32 * (j + 1) - b16, 0));
-                                const unsigned ma = __funnelshift_rc(0xffffffffu, 0u, max(32 * (j + 1) - a16, 0));
-                                const unsigned xv = x[j] & mv, xa = x[j] & ma;
-                                const unsigned vl = xv & 0xffffu, vh = xv >> 16, al = xa & 0xffffu, ah = xa >> 16;
-                                tot1 += vl + vh;
-                                tot2 += (unsigned long long)vl * vl;
-                                tot2 += (unsigned long long)vh * vh;
-                                run1 += al + ah;
-                                run2 += (unsigned long long)al * al;
-                                run2 += (unsigned long long)ah * ah;
-                            }
-                        } else if (U16X) {
+                        if (U16X) {
                             if (ibase < n) advance(ibase);
                             if (ibase + 8 <= n && ibase + 8 <= gend) {  // a full block inside one group: no per-read checks
 #pragma unroll
@@ -350,12 +326,7 @@ __global__ void __launch_bounds__(WARPS * 32, XP_PF_MINB) xp_prefilter_kernel(Pr
                         nxt = nn;
                     }
                     if (U16X) {
-                        if (cond_sorted) {  // run = the prefix condition's sums, tot = all reads
-                            mi.s1a = prefix_a ? run1 : tot1 - run1;
-                            mi.s2a = prefix_a ? run2 : tot2 - run2;
-                            mi.s1b = prefix_a ? tot1 - run1 : run1;
-                            mi.s2b = prefix_a ? tot2 - run2 : run2;
-                        } else flush();
+                        flush();
                         if (sl == 0) mi.na = n_a;  // the quad reduction below sums the lanes: lane 0 carries the count
                     }
                 } else {
@@ -430,6 +401,203 @@ __global__ void __launch_bounds__(WARPS * 32, XP_PF_MINB) xp_prefilter_kernel(Pr
         // a p-value this close to the threshold could fall on the other side of it under another (equally accurate)
         // evaluation of the incomplete beta function: flagged for the host (bit-exact selection)
         if (fabs(pv - a.threshold) <= 1e-9 * a.threshold) st |= STATUS_NEAR_THRESHOLD;
+        a.pval[p] = pv;
+        a.status[p] = st;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 for u16 batches whose group slots are blocked by condition (what every batch builder emits): exact integer
+// sums over ALIGNED 16-byte chunks, no masks and no shuffles in the streaming loop.
+// ------------------------------------------------------------------------------------------
+// Integer sums do not care about order or grouping, so a quad of lanes simply strides over the aligned 16-byte
+// chunks [c0, cE] that cover its position - lane sl takes c0 + sl, c0 + sl + 4, ... - and adds all eight codes of
+// every chunk: per pair of codes two extracts, one three-input add and two 32 x 32 + 64-bit multiply-adds.  The
+// reads of the condition whose block of slots comes first are a prefix of the position (`split` reads), so a lane
+// keeps, besides its running total, a copy of the total as it stood after its last chunk in front of the chunk
+// that holds the first read of the other condition (cS): the quad's sum of those copies is the prefix side, the
+// other side follows by subtraction.  What the whole chunks added too much - the neighbours' codes in the first
+// and the last chunk, and the prefix part of chunk cS that went to the wrong side - is computed once per position
+// by three lanes of the quad (one masked chunk each) and taken out again: the arithmetic is exact, so the result
+// equals the sums of the position's own reads bit for bit, and the p-values those of xp_prefilter_kernel<W, true>.
+// The per-position bookkeeping (offsets, split, conditions present) is done once per tile by the lane that also
+// evaluates the position's p-value, and handed to the quads by shuffles.
+// The kernel returns at once when the slots are not blocked by condition; xp_prefilter_kernel<W, true> is
+// launched behind it and returns at once when they are (both read the same grp_cond): the host-side entry points
+// take device pointers and never synchronise, so the choice is made on the device.
+__device__ __forceinline__ unsigned long long mad_wide_u32(unsigned a, unsigned b, unsigned long long c) {
+    unsigned long long d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+// Sums of a chunk's eight codes q = 256 h + l: s1 += sum q, ql += sum q l, qh += sum q h (sum q^2 = ql + 256 qh).
+// One byte permute per pair of codes gathers {l0, l1, h0, h1}; three two-way 16 x 8-bit dot products (IDP.2A) do
+// the rest.  32-bit accumulators: a term is < 2^24, so 256 codes (32 chunks) fit before they are folded into 64 bits.
+__device__ __forceinline__ void pf_add_chunk(const uint4& w, unsigned& s1, unsigned& ql, unsigned& qh) {
+    const unsigned x[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned b = __byte_perm(x[j], 0u, 0x3120);
+        s1 = __dp2a_lo(x[j], 0x0101u, s1);
+        ql = __dp2a_lo(x[j], b, ql);
+        qh = __dp2a_hi(x[j], b, qh);
+    }
+}
+constexpr int kPfFoldTrips = 32;
+// codes k in [lo, hi) of a chunk
+__device__ __forceinline__ void pf_add_chunk_range(const uint4& w, int lo, int hi, unsigned& s1, unsigned long long& s2) {
+    const unsigned x[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const unsigned q = (k >= lo && k < hi) ? ((x[k >> 1] >> ((k & 1) * 16)) & 0xffffu) : 0u;
+        s1 += q;
+        s2 = mad_wide_u32(q, q, s2);
+    }
+}
+
+#ifndef XP_PF16_MINB
+#define XP_PF16_MINB 8
+#endif
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, XP_PF16_MINB) xp_prefilter_u16_kernel(PrefilterArgs a) {
+    __shared__ int s_cond[kMaxGroups];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = a.G;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) s_cond[g] = a.grp_cond[g];
+    __syncthreads();
+    if (!pf_cond_sorted(s_cond, G)) return;  // xp_prefilter_kernel<W, true> takes the batch
+    const int p0 = (blockIdx.x * WARPS + warp) * 32;
+    if (p0 >= a.P) return;
+
+    // ---- once per tile: lane j looks at position p0 + j ---------------------------------------------------
+    const int p = p0 + lane;
+    int64_t off = 0;
+    int n = 0, split = 0;
+    bool valid = false, prefix_a = true;
+    if (p < a.P) {
+        off = a.read_off[p];
+        n = (int)(a.read_off[p + 1] - off);
+        const int32_t* glen = a.grp_len + (size_t)p * G;
+        unsigned cmask = 0;
+        int cfirst = -1;
+        for (int g = 0; g < G; ++g) {
+            const int len = glen[g], c = s_cond[g];
+            if (len > 0) {
+                cmask |= 1u << c;
+                if (cfirst < 0) cfirst = c;
+            }
+            if (c == cfirst) split += len;  // reads of the condition whose slots come first: a prefix of the position
+        }
+        valid = a.enabled && (__popc(cmask) == 2);
+        prefix_a = (cfirst == __ffs(cmask) - 1);  // the lower-numbered condition is side a (as in xp_prefilter_kernel)
+    }
+    // offsets relative to the aligned chunk that holds the tile's first read (a tile has < 2^20 reads)
+    const int64_t off0 = __shfl_sync(kFull, off, 0);
+    const int64_t e0 = off0 & ~(int64_t)7;
+    const int rel = (int)(off - e0);
+    const int n_eff = valid ? n : 0;
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(a.y) + e0);
+
+    const int sub = lane >> 2, sl = lane & 3;
+    unsigned k_t1 = 0u, k_a1 = 0u;
+    unsigned long long k_t2 = 0ull, k_a2 = 0ull;
+#pragma unroll 1
+    for (int round = 0; round < 4; ++round) {
+        const int from = round * 8 + sub;
+        const int r0 = __shfl_sync(kFull, rel, from), np = __shfl_sync(kFull, n_eff, from);
+        const int sp = __shfl_sync(kFull, split, from);
+        const int c0 = r0 >> 3, cS = (r0 + sp) >> 3;
+        const int cE = np > 0 ? (r0 + np - 1) >> 3 : c0 - 1;
+        unsigned t1 = 0u, a1 = 0u;
+        unsigned long long t2 = 0ull, a2 = 0ull;
+        const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+        int c = c0 + sl;
+        uint4 cur = (c <= cE) ? __ldg(src + c) : zero4;
+        uint4 nxt = (c + 4 <= cE) ? __ldg(src + c + 4) : zero4;
+        while (c <= cE) {  // blocks of kPfFoldTrips chunks (one block unless the position has > 1024 reads)
+            unsigned s1 = 0u, ql = 0u, qh = 0u, p1 = 0u, pl = 0u, ph = 0u;
+            const bool in_prefix = c < cS;
+            const int cend = min(cE, c + 4 * (kPfFoldTrips - 1));
+#pragma unroll 3
+            for (; c <= cend; c += 4) {
+                const uint4 nn = (c + 8 <= cE) ? __ldg(src + c + 8) : zero4;
+                pf_add_chunk(cur, s1, ql, qh);
+                if (c < cS) {  // still in front of the other condition's first read: the prefix follows the total
+                    p1 = s1;
+                    pl = ql;
+                    ph = qh;
+                }
+                cur = nxt;
+                nxt = nn;
+            }
+            if (in_prefix) {
+                a1 = t1 + p1;
+                a2 = t2 + pl + ((unsigned long long)ph << 8);
+            }
+            t1 += s1;
+            t2 += ql + ((unsigned long long)qh << 8);
+        }
+        // ---- what the whole chunks added too much: lane 0 the codes in front of the position in chunk c0, lane 1
+        // those behind it in chunk cE, lane 2 the prefix part of chunk cS (counted for the other side above) ----
+        {
+            const int first = r0 & 7, last = (r0 + np - 1) & 7;  // of the position's reads inside c0 / cE
+            const int cc = sl == 0 ? c0 : (sl == 1 ? cE : cS);
+            int lo = 0, hi = 0;
+            if (np > 0) {
+                if (sl == 0) hi = first;
+                else if (sl == 1) { lo = last + 1; hi = 8; }
+                else if (sl == 2) { lo = cS == c0 ? first : 0; hi = (r0 + sp) & 7; }
+            }
+            unsigned x1 = 0u;
+            unsigned long long x2 = 0ull;
+            if (hi > lo) {
+                const uint4 w = __ldg(src + cc);
+                pf_add_chunk_range(w, lo, hi, x1, x2);
+            }
+            if (sl < 2) {
+                t1 -= x1;
+                t2 -= x2;
+                if (sl == 0 && c0 < cS) {
+                    a1 -= x1;
+                    a2 -= x2;
+                }
+            } else {
+                a1 += x1;
+                a2 += x2;
+            }
+        }
+#pragma unroll
+        for (int d = 1; d < 4; d <<= 1) {
+            t1 += __shfl_xor_sync(kFull, t1, d);
+            a1 += __shfl_xor_sync(kFull, a1, d);
+            t2 += __shfl_xor_sync(kFull, t2, d);
+            a2 += __shfl_xor_sync(kFull, a2, d);
+        }
+        // position round * 8 + j goes to lane round * 8 + j
+        const int own = (lane & 7) * 4;
+        const unsigned g_t1 = __shfl_sync(kFull, t1, own), g_a1 = __shfl_sync(kFull, a1, own);
+        const unsigned long long g_t2 = __shfl_sync(kFull, t2, own), g_a2 = __shfl_sync(kFull, a2, own);
+        if ((lane >> 3) == round) {
+            k_t1 = g_t1; k_a1 = g_a1; k_t2 = g_t2; k_a2 = g_a2;
+        }
+    }
+    if (p < a.P) {
+        double pv = NAN;
+        uint32_t st = 0;
+        if (valid) {
+            const unsigned s1a = prefix_a ? k_a1 : k_t1 - k_a1, s1b = prefix_a ? k_t1 - k_a1 : k_a1;
+            const unsigned long long s2a = prefix_a ? k_a2 : k_t2 - k_a2, s2b = prefix_a ? k_t2 - k_a2 : k_a2;
+            const int na = prefix_a ? split : n - split, nb = n - na;
+            // n S2 - S1^2 is exact in 64 bits (< 2^62): the t statistic takes the exact numerators
+            const double nssa = (double)((unsigned long long)na * s2a - (unsigned long long)s1a * s1a);
+            const double nssb = (double)((unsigned long long)nb * s2b - (unsigned long long)s1b * s1b);
+            double t, df;
+            ttest_from_exact_sums((double)na, (double)s1a, nssa, (double)nb, (double)s1b, nssb, t, df);
+            pv = student_t_two_sided(t, df);
+            st |= STATUS_TTEST_VALID;
+        }
+        if (pv != pv || pv < a.threshold) st |= STATUS_SELECTED;  // diffmod.py:54
+        if (fabs(pv - a.threshold) <= 1e-9 * a.threshold) st |= STATUS_NEAR_THRESHOLD;  // see xp_prefilter_kernel
         a.pval[p] = pv;
         a.status[p] = st;
     }
