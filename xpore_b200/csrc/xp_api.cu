@@ -116,7 +116,11 @@ int prepare_kernel(Geometry* g) {
     return prepare_kernel_fn(xpk::xp_fit_kernel<TW, MAXT, STREAM>, g);
 }
 // the tensor-memory flavour of the single-warp class (u16 batches), by positions per warp and thread limit
-using FitKernelFn = void (*)(xpk::FitArgs);
+using FitKernelFn = void (*)(xpk::FitArgs, xpk::FitChain);
+const xpk::FitChain& no_chain() {
+    static const xpk::FitChain z{};
+    return z;
+}
 template <int NPW, int GT>
 FitKernelFn tm_kernel_g(int maxt) {
     switch (maxt) {
@@ -142,6 +146,25 @@ FitKernelFn tm_kernel(int npw, int maxt, int G) {
         if (G == 4 && maxt == 640) return xpk::xp_fit_tm_kernel<1, 640, 4>;
     }
     return tm_kernel_g<1, 0>(maxt);
+}
+
+// The same kernels following the chain of chunk worklists of the host pipeline (xpk::FitChain); null where no such
+// instantiation exists (the pipeline then launches chunk by chunk).
+FitKernelFn tm_chain_kernel(int npw, int maxt, int G) {
+    if (npw == 2) {
+        if (maxt != 896) return nullptr;
+        if (G == 2) return xpk::xp_fit_tm_kernel<2, 896, 2, true>;
+        if (G == 4) return xpk::xp_fit_tm_kernel<2, 896, 4, true>;
+        if (G == 6) return xpk::xp_fit_tm_kernel<2, 896, 6, true>;
+        return xpk::xp_fit_tm_kernel<2, 896, 0, true>;
+    }
+    if (G == 18 && maxt == 640) return xpk::xp_fit_tm_kernel<1, 640, 18, true>;
+    switch (maxt) {
+        case 640: return xpk::xp_fit_tm_kernel<1, 640, 0, true>;
+        case 768: return xpk::xp_fit_tm_kernel<1, 768, 0, true>;
+        case 896: return xpk::xp_fit_tm_kernel<1, 896, 0, true>;
+        default: return xpk::xp_fit_tm_kernel<1, 1024, 0, true>;
+    }
 }
 
 constexpr int kFitWarpsDefault = 28;
@@ -285,13 +308,18 @@ int deep_class_split(int G) {
     return best;  // > kSplitReads for every G <= kMaxGroups
 }
 
+// Chained form of the host pipeline: the class launches of a chunk run beside the chained launch, which holds all but a
+// few SMs until the end of the batch - a grid larger than those few SMs would keep its stream busy until then, and with
+// it the select phases of later chunks the chained launch is waiting for.
+thread_local int g_fit_grid_cap = 0;
 int launch_fit(const Geometry& g, const xpk::FitArgs& fa_in, int max_teams_needed, cudaStream_t st) {
     xpk::FitArgs fa = fa_in;
     if (g.np > 0) xpk::fit_tm_fill_layout(fa, g.np);
     else xpk::fit_fill_layout(fa, g.tw, g.stream);
     const int need = (max_teams_needed + g.teams - 1) / g.teams;
-    const int grid = std::max(1, std::min(g.sms * g.ctas_per_sm, need));
-    if (g.np > 0) tm_kernel(g.np, g.maxt, fa.G)<<<grid, g.threads, g.smem, st>>>(fa);
+    int grid = std::max(1, std::min(g.sms * g.ctas_per_sm, need));
+    if (g_fit_grid_cap > 0) grid = std::min(grid, g_fit_grid_cap);
+    if (g.np > 0) tm_kernel(g.np, g.maxt, fa.G)<<<grid, g.threads, g.smem, st>>>(fa, no_chain());
     else if (g.stream) xpk::xp_fit_kernel<kStreamWarps, kStreamWarps * 32, true><<<grid, g.threads, g.smem, st>>>(fa);
     else if (g.tw == 1) {
         switch (g.maxt) {
@@ -413,8 +441,23 @@ int32_t xpb200_stats_device(const xpb200_batch* b, const xpb200_method* m, const
     return launch_stats(b, m, r, worklist, n_work, (cudaStream_t)stream);
 }
 
+namespace {
+enum { kPhaseSelect = 1, kPhaseFit = 2, kPhaseStats = 4, kPhaseAll = 7, kPhaseFitLarge = 8 };  // FitLarge: the team / streaming class launches only
+int fit_device_phases(const xpb200_batch* b, const xpb200_method* m, const xpb200_result* r, void* workspace,
+                      size_t workspace_bytes, uint32_t* n_fitted_dev, void* stream, int phases);
+}  // namespace
+
 int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const xpb200_result* r, void* workspace,
                           size_t workspace_bytes, uint32_t* n_fitted_dev, void* stream) {
+    return fit_device_phases(b, m, r, workspace, workspace_bytes, n_fitted_dev, stream, kPhaseAll);
+}
+
+namespace {
+// The phases of one fit: select (prefilter + worklist), fit (the class launches), stats.  The chunked host call, when
+// ONE chained launch fits all chunks (fit_host_impl), enqueues a chunk's select phase when its reads have arrived and its
+// stats phase when the chained launch is done.
+int fit_device_phases(const xpb200_batch* b, const xpb200_method* m, const xpb200_result* r, void* workspace,
+                      size_t workspace_bytes, uint32_t* n_fitted_dev, void* stream, int phases) {
     if (int rc = check_batch(b, m)) return rc;
     if (!r || !r->status || !r->n_iter || !r->pval || !r->fit || !r->stats)
         return fail(XPB200_EINVAL, "null result array");
@@ -426,15 +469,18 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
     }
     if (!workspace || workspace_bytes < xpb200_workspace_bytes(P)) return fail(XPB200_ENOMEM, "workspace too small");
     Workspace ws = carve(workspace);
-    CK(cudaMemsetAsync(workspace, 0, ws_header_bytes(), st));
+    const bool do_select = (phases & kPhaseSelect) != 0, do_fit = (phases & (kPhaseFit | kPhaseFitLarge)) != 0;
+    const bool do_fit_small = (phases & kPhaseFit) != 0;
+    if (do_select) CK(cudaMemsetAsync(workspace, 0, ws_header_bytes(), st));
     stage_mark(0, st);
 
     // K1 prefilter (or: everything selected, p-value NaN)
     const uint32_t* sel = nullptr;
     if (m->prefilter) {
-        if (int rc = launch_prefilter(b, m, r->status, r->pval, st)) return rc;
+        if (do_select)
+            if (int rc = launch_prefilter(b, m, r->status, r->pval, st)) return rc;
         sel = r->status;
-    } else {
+    } else if (do_select) {
         CK(cudaMemsetAsync(r->status, 0, (size_t)P * 4, st));
         CK(cudaMemsetAsync(r->pval, 0xFF, (size_t)P * 8, st));  // all-ones = NaN
     }
@@ -462,15 +508,18 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
     if (use_tm) {
         if (int rc = fit_tm_geometry(b->n_groups, tw1_reads, npw, &g)) return rc;
     } else if (int rc = fit_geometry(b->n_groups, tw1_reads, 1, &g)) return rc;
-    const int wthreads = 256;
-    const int wblocks = std::min((P + wthreads - 1) / wthreads, 1184);
-    xpk::xp_worklist_count<<<wblocks, wthreads, 0, st>>>(wa);
-    xpk::xp_worklist_scan<<<1, xpk::kBuckets, 0, st>>>(wa);
-    xpk::xp_worklist_scatter<<<wblocks, wthreads, 0, st>>>(wa);
-    g_launches += 3;
-    CK(cudaGetLastError());
+    if (do_select) {
+        const int wthreads = 256;
+        const int wblocks = std::min((P + wthreads - 1) / wthreads, 1184);
+        xpk::xp_worklist_count<<<wblocks, wthreads, 0, st>>>(wa);
+        xpk::xp_worklist_scan<<<1, xpk::kBuckets, 0, st>>>(wa);
+        xpk::xp_worklist_scatter<<<wblocks, wthreads, 0, st>>>(wa);
+        g_launches += 3;
+        CK(cudaGetLastError());
+    }
 
     stage_mark(2, st);
+    if (do_fit) {
     // K3 fit: persistent CTAs; the deepest positions first
     xpk::FitArgs fa;
     fa.y = b->y; fa.y_format = b->y_format; fa.y_scale = b->y_scale;
@@ -518,20 +567,25 @@ int32_t xpb200_fit_device(const xpb200_batch* b, const xpb200_method* m, const x
         if (int rc = end_class(k)) return rc;
         ++k;
     }
-    fa.cap = g.cap; fa.w_begin = two_class ? ws.n_large : nullptr; fa.w_end = ws.n_work; fa.ticket = ws.ticket;
-    if (int rc = begin_class(k)) return rc;
-    if (int rc = launch_fit(g, fa, P, class_stream(k))) return rc;
-    if (int rc = end_class(k)) return rc;
-    ++k;
+    if (do_fit_small) {
+        fa.cap = g.cap; fa.w_begin = two_class ? ws.n_large : nullptr; fa.w_end = ws.n_work; fa.ticket = ws.ticket;
+        if (int rc = begin_class(k)) return rc;
+        if (int rc = launch_fit(g, fa, P, class_stream(k))) return rc;
+        if (int rc = end_class(k)) return rc;
+        ++k;
+    }
+    }  // do_fit
 
     stage_mark(3, st);
     // K4 statistics
-    if (int rc = launch_stats(b, m, r, ws.worklist, ws.n_work, st)) return rc;
+    if (phases & kPhaseStats)
+        if (int rc = launch_stats(b, m, r, ws.worklist, ws.n_work, st)) return rc;
     stage_mark(4, st);
-    g_timer.valid = g_timer.on;
-    if (n_fitted_dev) CK(cudaMemcpyAsync(n_fitted_dev, ws.n_work, 4, cudaMemcpyDeviceToDevice, st));
+    g_timer.valid = g_timer.on && phases == kPhaseAll;
+    if (n_fitted_dev && do_select) CK(cudaMemcpyAsync(n_fitted_dev, ws.n_work, 4, cudaMemcpyDeviceToDevice, st));
     return 0;
 }
+}  // namespace
 
 // ---- host-buffer entry points -------------------------------------------------------------
 // The batch is cut into chunks of positions (~kChunkBytes of reads each).  Chunk c's reads go up
@@ -548,14 +602,17 @@ struct DevCache {
     int device = -1;
     cudaStream_t s_in = nullptr, s_c[kComputeStreams] = {nullptr, nullptr, nullptr}, s_out = nullptr;
     cudaEvent_t e_in[kMaxChunks], e_done[kMaxChunks];
+    cudaStream_t s_fit = nullptr;                    // the chained launch (see fit_host_impl)
+    cudaEvent_t e_zero = nullptr, e_fit = nullptr;   // its flags are cleared / it is done
     cudaEvent_t e_call = nullptr;  // end of the previous call's device work (the arena is reused by the next one)
     cudaEvent_t e_user = nullptr;  // the caller's stream at entry of an asynchronous call
     cudaEvent_t t_0 = nullptr, t_in[kMaxChunks], t_start[kMaxChunks], t_done[kMaxChunks];  // XPB200_TRACE=1 only
+    cudaEvent_t t_fit = nullptr, t_post = nullptr;
     void* buf = nullptr;
     size_t cap = 0;
     long calls = 0;
 };
-std::mutex g_cache_mu;
+std::recursive_mutex g_cache_mu;  // recursive: a chained call whose max_reads was understated starts over chunk by chunk
 std::vector<DevCache*> g_cache;
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -591,7 +648,7 @@ int launch_pack_rows(const xpb200_result& dr, int pc, int FW, int SW, long long 
     return 0;
 }
 
-int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m, const HostOut& ho);
+int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m, const HostOut& ho, bool allow_chain = true);
 }  // namespace
 
 int32_t xpb200_fit_host(int32_t device, const xpb200_batch* b, const xpb200_method* m, const xpb200_result* r,
@@ -631,13 +688,23 @@ int32_t xpb200_fit_host_rows_async(int32_t device, const xpb200_batch* b, const 
 }
 
 namespace {
-int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m, const HostOut& ho) {
+// The chained form of the pipeline (rows out, synchronous call, u16 batch whose deepest position is below the team
+// split, so that the whole batch is the tensor-memory kernel's single-warp class): ONE persistent fit launch on all but
+// kChainFreeSms SMs walks the chunks' worklists in order (xpk::FitChain) while the chunks' reads arrive and their prefilter
+// and worklist launches run on the SMs left free; statistics and the row compaction follow when it is done.  Chunk by
+// chunk launches (the other form) end each chunk with a tail of half-empty CTAs and leave most SMs idle through the
+// first, small chunks: c2 took 18.3 ms end to end against 14.1 ms resident, the copy alone 14.2 ms.
+constexpr int kChainFreeSms = 6;
+constexpr size_t kChainChunkBytes = 32u << 20;
+constexpr unsigned kChainSpinLimit = 1500000u;  // polls of a warp waiting for a chunk (4 us each: >= 6 s) before it gives up
+
+int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m, const HostOut& ho, bool allow_chain) {
     const xpb200_result* r = ho.dense;
     double* rows = ho.rows;
     const bool want_rows = ho.rows != nullptr || ho.rows_dev != nullptr;
     const bool async = ho.rows_dev != nullptr;
     CK(cudaSetDevice(device));
-    std::lock_guard<std::mutex> lk(g_cache_mu);
+    std::lock_guard<std::recursive_mutex> lk(g_cache_mu);
     DevCache* dc = nullptr;
     for (auto* c : g_cache)
         if (c->device == device) dc = c;
@@ -653,6 +720,9 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         }
         CK(cudaEventCreateWithFlags(&dc->e_call, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&dc->e_user, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&dc->s_fit, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&dc->e_zero, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&dc->e_fit, cudaEventDisableTiming));
         g_cache.push_back(dc);
     }
     const int P = b->n_positions, G = b->n_groups, C = b->n_conditions;
@@ -668,20 +738,66 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     // chunk boundaries (positions), cut where the read offsets cross the chunk targets.  The first chunks are
     // small so the SMs start early; a remainder of less than a quarter chunk joins the last one.
     const int64_t* roff = b->read_off;
-    const size_t chunk_bytes = (size_t)std::max(1, exp_int("XPB200_CHUNK_MB", (int)(kChunkBytes >> 20))) << 20;
     const size_t total_bytes = (size_t)b->n_reads * eb;
+    // chained form?  decided on the caller's max_reads (checked chunk by chunk below: an understated one aborts the
+    // chained launch and the call starts over chunk by chunk)
+    Geometry gch;
+    FitKernelFn chain_fn = nullptr;
+    int chain_npw = 0;
+    if (allow_chain && want_rows && !async && b->y_format == XPB200_Y_U16 && b->max_reads > 0 &&
+        exp_int("XPB200_TM", 1) != 0 && exp_int("XPB200_CHAIN", 1) != 0 && total_bytes >= (8u << 20)) {
+        chain_npw = tm_positions_per_warp(G, b->max_reads);
+        // the chained launch is the single-warp class's; the chunks' team / streaming classes keep their own launches,
+        // on the few SMs left free - so only where they are a sliver of the batch (a sample of the positions decides:
+        // a wrong guess costs time, not results)
+        const int split1 = tm_class_split(chain_npw);
+        int64_t seen = 0, large = 0;
+        for (int p = 0; p < P; p += 61) {
+            const int64_t n = roff[p + 1] - roff[p];
+            seen += n;
+            if (n >= split1) large += n;
+        }
+        if (large * 200 <= seen) {
+            if (int rc = fit_tm_geometry(G, std::min(b->max_reads, split1 - 1), chain_npw, &gch)) return rc;
+            chain_fn = tm_chain_kernel(chain_npw, gch.maxt, G);
+            if (chain_fn)
+                if (int rc = prepare_kernel_fn(chain_fn, &gch)) return rc;
+            if (gch.ctas_per_sm < 1 || gch.sms <= 2 * kChainFreeSms) chain_fn = nullptr;
+        }
+    }
+    const bool chain = chain_fn != nullptr;
+    const int chain_free_sms = std::max(1, exp_int("XPB200_CHAIN_FREE_SMS", kChainFreeSms));
+    const size_t chunk_cap = chain ? std::max(kChainChunkBytes, total_bytes / (size_t)(kMaxChunks - 16)) : kChunkBytes;
+    const size_t chunk_bytes = (size_t)std::max(1, exp_int(chain ? "XPB200_CHAIN_CHUNK_MB" : "XPB200_CHUNK_MB", (int)(chunk_cap >> 20))) << 20;
     std::vector<int> cut(1, 0);
     {
         std::vector<size_t> ends;  // byte targets of the chunk ends
         size_t pos = 0;
         // sizes grow by kChunkGrowth from an eighth of a full chunk: the copy is only ~1.2x faster than the fit, so
         // a chunk that is much larger than its predecessor would leave the SMs waiting for it to arrive
-        size_t sz = std::max<size_t>(chunk_bytes / 8, 1u << 20);
-        const double growth = std::max(1.0, exp_int("XPB200_CHUNK_GROWTH_PCT", kChunkGrowthPct) / 100.0);
-        while (pos + sz + sz / 4 < total_bytes && (int)ends.size() < kMaxChunks - 2) {
+        // (chained form: tails and small launches cost nothing there, so the chunks are small - they only set the
+        // latency between the arrival of a read and its fit - and double from a quarter chunk)
+        size_t sz = std::max<size_t>(chunk_bytes / (chain ? (size_t)std::max(1, exp_int("XPB200_CHAIN_FIRST_DIV", 16)) : 8), 1u << 20);
+        const double growth = chain ? 2.0 : std::max(1.0, exp_int("XPB200_CHUNK_GROWTH_PCT", kChunkGrowthPct) / 100.0);
+        // chained form: the last chunks halve again (down to 1 / kChainLastDiv of a chunk).  What is left to do when the
+        // last read has arrived is the last chunk plus the longest position of the late chunks (300 sweeps take over a
+        // millisecond), and a chunk of an eighth holds fewer of both
+        const int last_div = chain ? std::max(1, exp_int("XPB200_CHAIN_LAST_DIV", 8)) : 1;
+        size_t tail_bytes = 0;
+        for (int dv = 2; dv <= last_div; dv *= 2) tail_bytes += chunk_bytes / dv;
+        if (tail_bytes * 3 > total_bytes) tail_bytes = 0;
+        const size_t body_bytes = total_bytes - tail_bytes;
+        while (pos + sz + sz / 4 < body_bytes && (int)ends.size() < kMaxChunks - 8) {
             pos += sz;
             ends.push_back(pos);
             sz = std::min(chunk_bytes, (size_t)((double)sz * growth));
+        }
+        if (tail_bytes) {
+            pos = body_bytes;
+            for (int dv = 2; dv <= last_div; dv *= 2) {
+                ends.push_back(pos);
+                pos += chunk_bytes / dv;
+            }
         }
         for (size_t e : ends) {
             const int64_t target = (int64_t)(e / eb);
@@ -718,6 +834,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     const size_t o_pval = o; o += align_up((size_t)P * 8);
     const size_t o_fit = o; o += align_up((size_t)P * FW * 8);
     const size_t o_stats = o; o += align_up((size_t)P * SW * 8);
+    const size_t o_flags = o; o += align_up((size_t)(2 * kMaxChunks + 1) * 4);  // chained form: ready[c], the abort flag, polls spent waiting (experiment builds)
     const size_t o_nf = o; o += align_up((size_t)kMaxChunks * 4);
     const size_t o_nr = o; o += align_up((size_t)kMaxChunks * 4);
     const size_t o_cnt = o; o += want_rows ? align_up((size_t)kMaxChunks * kPackWarps * 4) : 0;
@@ -751,6 +868,8 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     double* d_pval = (double*)(d + o_pval);
     double* d_fit = (double*)(d + o_fit);
     double* d_stats = (double*)(d + o_stats);
+    uint32_t* d_ready = (uint32_t*)(d + o_flags);
+    uint32_t* d_abort = d_ready + kMaxChunks;
     uint32_t* d_nf = (uint32_t*)(d + o_nf);
     uint32_t* d_nr = (uint32_t*)(d + o_nr);
     uint32_t* d_cnt = (uint32_t*)(d + o_cnt);
@@ -761,6 +880,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     if (dc->calls > 1) {
         CK(cudaStreamWaitEvent(dc->s_in, dc->e_call, 0));
         for (int i = 0; i < kComputeStreams; ++i) CK(cudaStreamWaitEvent(dc->s_c[i], dc->e_call, 0));
+        CK(cudaStreamWaitEvent(dc->s_fit, dc->e_call, 0));
     }
     if (async) {
         CK(cudaEventRecord(dc->e_user, ho.user_stream));
@@ -770,6 +890,175 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     CK(cudaMemcpyAsync(d + o_gc, b->grp_cond, (size_t)G * 4, cudaMemcpyDefault, dc->s_in));
     CK(cudaMemsetAsync(d_nf, 0, (size_t)kMaxChunks * 4, dc->s_in));
     CK(cudaMemsetAsync(d_nr, 0, (size_t)kMaxChunks * 4, dc->s_in));
+    bool chain_launched = false, chain_understated = false;
+    // An error return after the chained launch must not leave it polling for chunks that will never come
+    auto chain_bail = [&](int rc) -> int {
+        if (chain_launched) {
+            cudaMemsetAsync(d_abort, 0xFF, 4, dc->s_out);
+            cudaStreamSynchronize(dc->s_out);
+            cudaStreamSynchronize(dc->s_fit);
+            for (int i = 0; i < kComputeStreams; ++i) cudaStreamSynchronize(dc->s_c[i]);
+            cudaStreamSynchronize(dc->s_in);
+        }
+        return rc;
+    };
+#define CKB(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return chain_bail(fail(XPB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); \
+    } while (0)
+    if (chain) {
+        CK(cudaMemsetAsync(d_ready, 0, (size_t)(2 * kMaxChunks + 1) * 4, dc->s_in));
+        CK(cudaEventRecord(dc->e_zero, dc->s_in));
+        CK(cudaStreamWaitEvent(dc->s_fit, dc->e_zero, 0));
+    }
+    for (int c = 0; chain && c < nchunks; ++c) {
+        const int p0 = cut[c], p1 = cut[c + 1], pc = p1 - p0;
+        const int64_t r0 = roff[p0], r1 = roff[p1];
+        CKB(cudaMemcpyAsync(d_y + (size_t)r0 * eb, (const char*)b->y + (size_t)r0 * eb, (size_t)(r1 - r0) * eb,
+                            cudaMemcpyDefault, dc->s_in));
+        CKB(cudaMemcpyAsync(d_off + p0, roff + p0, (size_t)(pc + 1) * 8, cudaMemcpyDefault, dc->s_in));
+        CKB(cudaMemcpyAsync(d_glen + (size_t)p0 * G, b->grp_len + (size_t)p0 * G, (size_t)pc * G * 4, cudaMemcpyDefault, dc->s_in));
+        CKB(cudaMemcpyAsync(d_km + p0, b->kmer_mean + p0, (size_t)pc * 8, cudaMemcpyDefault, dc->s_in));
+        CKB(cudaMemcpyAsync(d_ks + p0, b->kmer_std + p0, (size_t)pc * 8, cudaMemcpyDefault, dc->s_in));
+        CKB(cudaEventRecord(dc->e_in[c], dc->s_in));
+        if (trace) CKB(cudaEventRecord(dc->t_in[c], dc->s_in));
+        // the chunk's select phase (prefilter, worklist) on the SMs the chained launch leaves free, then its ready flag
+        cudaStream_t sc = dc->s_c[c % n_streams];
+        CKB(cudaStreamWaitEvent(sc, dc->e_in[c], 0));
+        if (trace) CKB(cudaEventRecord(dc->t_start[c], sc));
+        int64_t deepest = 0;
+        for (int p = p0; p < p1; ++p) deepest = std::max(deepest, roff[p + 1] - roff[p]);
+        if (deepest > (int64_t)b->max_reads) {  // the caller understated max_reads: start over, chunk by chunk
+            chain_understated = true;
+            break;
+        }
+        xpb200_batch db = *b;
+        db.n_positions = pc;
+        db.n_reads = r1 - r0;
+        db.y = d_y; db.read_off = d_off + p0; db.grp_len = d_glen + (size_t)p0 * G;
+        db.kmer_mean = d_km + p0; db.kmer_std = d_ks + p0; db.grp_cond = (const int32_t*)(d + o_gc);
+        xpb200_result dr;
+        dr.status = d_status + p0; dr.n_iter = d_niter + p0; dr.pval = d_pval + p0;
+        dr.fit = d_fit + (size_t)p0 * FW; dr.stats = d_stats + (size_t)p0 * SW;
+        dr.coef = nullptr;
+        CKB(cudaMemsetAsync(dr.n_iter, 0, (size_t)pc * 4, sc));
+        g_fit_grid_cap = chain_free_sms;
+        const int rc_sel = fit_device_phases(&db, m, &dr, d + o_ws[c], xpb200_workspace_bytes(pc), d_nf + c, sc, kPhaseSelect | kPhaseFitLarge);
+        g_fit_grid_cap = 0;
+        if (rc_sel) return chain_bail(rc_sel);
+        CKB(cudaMemsetAsync(d_ready + c, 0x01, 4, sc));
+        if (trace) CKB(cudaEventRecord(dc->t_done[c], sc));
+        if (c == 0) {  // the chained launch, as soon as the first chunk is on its way
+            xpk::FitArgs fa;
+            memset(&fa, 0, sizeof(fa));
+            fa.y = d_y; fa.y_format = b->y_format; fa.y_scale = b->y_scale;
+            fa.read_off = d_off; fa.grp_len = d_glen; fa.kmer_mean = d_km; fa.kmer_std = d_ks;
+            fa.G = G; fa.max_iters = m->max_iters; fa.stopping = m->stopping_criteria; fa.conc0 = m->dirichlet_conc;
+            fa.lg_prior_w = xpm::xlgamma(2.0 * m->dirichlet_conc) - 2.0 * xpm::xlgamma(m->dirichlet_conc);
+            fa.fit = d_fit; fa.n_iter = d_niter; fa.status = d_status; fa.coef = nullptr;
+            fa.cap = gch.cap;
+            xpk::fit_tm_fill_layout(fa, gch.np);
+            xpk::FitChain ch;
+            memset(&ch, 0, sizeof(ch));
+            ch.n = nchunks;
+            ch.spin_limit = kChainSpinLimit;
+            ch.ready = d_ready;
+            ch.abort = d_abort;
+            ch.wait_polls = d_abort + 1;
+            for (int k = 0; k < nchunks; ++k) {
+                const Workspace wk = carve(d + o_ws[k]);
+                ch.c[k].worklist = wk.worklist; ch.c[k].ticket = wk.ticket; ch.c[k].n_work = wk.n_work; ch.c[k].p0 = cut[k];
+                ch.c[k].w_begin = b->max_reads >= tm_class_split(chain_npw) ? wk.n_large : nullptr;
+            }
+            const int need = (P + gch.teams - 1) / gch.teams;
+            const int grid = std::max(1, std::min(gch.sms * gch.ctas_per_sm - chain_free_sms, need));
+            chain_fn<<<grid, gch.threads, gch.smem, dc->s_fit>>>(fa, ch);
+            ++g_launches;
+            CKB(cudaGetLastError());
+            chain_launched = true;
+        }
+    }
+    if (chain && chain_understated) {
+        chain_bail(0);
+        return fit_host_impl(device, b, m, ho, false);
+    }
+    if (chain) {
+        // statistics of every chunk once the chained launch is done, then the rows of the whole batch in position order
+        CKB(cudaEventRecord(dc->e_fit, dc->s_fit));
+        if (trace) {
+            if (!dc->t_fit) {
+                CKB(cudaEventCreate(&dc->t_fit));
+                CKB(cudaEventCreate(&dc->t_post));
+            }
+            CKB(cudaEventRecord(dc->t_fit, dc->s_fit));
+        }
+        for (int c = 0; c < nchunks; ++c) {
+            const int p0 = cut[c], pc = cut[c + 1] - cut[c];
+            cudaStream_t sc = dc->s_c[c % n_streams];
+            CKB(cudaStreamWaitEvent(sc, dc->e_fit, 0));
+            xpb200_batch db = *b;
+            db.n_positions = pc;
+            db.y = d_y; db.read_off = d_off + p0; db.grp_len = d_glen + (size_t)p0 * G;
+            db.kmer_mean = d_km + p0; db.kmer_std = d_ks + p0; db.grp_cond = (const int32_t*)(d + o_gc);
+            xpb200_result dr;
+            dr.status = d_status + p0; dr.n_iter = d_niter + p0; dr.pval = d_pval + p0;
+            dr.fit = d_fit + (size_t)p0 * FW; dr.stats = d_stats + (size_t)p0 * SW;
+            dr.coef = nullptr;
+            const Workspace wk = carve(d + o_ws[c]);
+            if (int rc = launch_stats(&db, m, &dr, wk.worklist, wk.n_work, sc)) return chain_bail(rc);
+            CKB(cudaEventRecord(dc->e_done[c], sc));
+            CKB(cudaStreamWaitEvent(dc->s_out, dc->e_done[c], 0));
+        }
+        xpb200_result dr;
+        dr.status = d_status; dr.n_iter = d_niter; dr.pval = d_pval; dr.fit = d_fit; dr.stats = d_stats; dr.coef = nullptr;
+        if (int rc = launch_pack_rows(dr, P, FW, SW, ho.index_offset, P, d_cnt, d_nr, d_rows, dc->s_out)) return chain_bail(rc);
+        if (trace) CKB(cudaEventRecord(dc->t_post, dc->s_out));
+        uint32_t tail[2] = {0u, 0u};  // rows, abort flag
+        CKB(cudaMemcpyAsync(&tail[0], d_nr, 4, cudaMemcpyDefault, dc->s_out));
+        CKB(cudaMemcpyAsync(&tail[1], d_abort, 4, cudaMemcpyDefault, dc->s_out));
+        uint32_t nf[kMaxChunks];
+        CKB(cudaMemcpyAsync(nf, d_nf, sizeof(nf), cudaMemcpyDefault, dc->s_out));
+        CKB(cudaStreamSynchronize(dc->s_out));
+        for (int i = 0; i < kComputeStreams; ++i) CK(cudaStreamSynchronize(dc->s_c[i]));
+        CK(cudaStreamSynchronize(dc->s_in));
+        CK(cudaStreamSynchronize(dc->s_fit));
+        if (tail[1] != 0u) {  // a warp gave up waiting for a chunk (the free SMs were not free?): chunk by chunk, then
+            CK(cudaEventRecord(dc->e_call, dc->s_out));
+            return fit_host_impl(device, b, m, ho, false);
+        }
+        const int64_t total_rows = tail[0];
+        *ho.n_rows = total_rows;
+        uint32_t total = 0;
+        for (int c = 0; c < nchunks; ++c) total += nf[c];
+        if (ho.n_fitted) *ho.n_fitted = total;
+        if (total_rows > ho.rows_capacity) {
+            CK(cudaEventRecord(dc->e_call, dc->s_out));
+            return fail(XPB200_ENOMEM, "rows buffer too small: " + std::to_string(total_rows) + " rows needed");
+        }
+        if (total_rows) CK(cudaMemcpyAsync(rows, d_rows, (size_t)total_rows * RW * 8, cudaMemcpyDefault, dc->s_out));
+        CK(cudaStreamSynchronize(dc->s_out));
+        CK(cudaEventRecord(dc->e_call, dc->s_out));
+        if (trace) {
+            const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+            float tf = 0, tp = 0;
+            cudaEventElapsedTime(&tf, dc->t_0, dc->t_fit);
+            cudaEventElapsedTime(&tp, dc->t_0, dc->t_post);
+            fprintf(stderr, "[xpb200 trace] chained: %d chunks, host %.3f ms, chained launch done %.3f, rows packed %.3f ms\n", nchunks, host_ms, tf, tp);
+            uint32_t polls[kMaxChunks];
+            cudaMemcpy(polls, d_abort + 1, sizeof(polls), cudaMemcpyDefault);
+            for (int c = 0; c < nchunks; ++c) {
+                float a = 0, s2 = 0, e = 0;
+                cudaEventElapsedTime(&a, dc->t_0, dc->t_in[c]);
+                cudaEventElapsedTime(&s2, dc->t_0, dc->t_start[c]);
+                cudaEventElapsedTime(&e, dc->t_0, dc->t_done[c]);
+                fprintf(stderr, "[xpb200 trace] chunk %2d: %8d positions %7.1f MB  copied %7.3f  select %7.3f .. %7.3f ms  fitted %u  polls waiting %u\n", c,
+                        cut[c + 1] - cut[c], (double)(roff[cut[c + 1]] - roff[cut[c]]) * eb / 1048576.0, a, s2, e, nf[c], polls[c]);
+            }
+        }
+        return 0;
+    }
+#undef CKB
     for (int c = 0; c < nchunks; ++c) {
         const int p0 = cut[c], p1 = cut[c + 1], pc = p1 - p0;
         if (pc == 0) continue;
@@ -892,13 +1181,15 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
 }  // namespace
 
 void xpb200_release(void) {
-    std::lock_guard<std::mutex> lk(g_cache_mu);
+    std::lock_guard<std::recursive_mutex> lk(g_cache_mu);
     for (auto* c : g_cache) {
         cudaSetDevice(c->device);
         cudaDeviceSynchronize();  // an asynchronous call may still be using the arena
         if (c->buf) cudaFree(c->buf);
-        for (cudaStream_t st : {c->s_in, c->s_c[0], c->s_c[1], c->s_c[2], c->s_out})
+        for (cudaStream_t st : {c->s_in, c->s_c[0], c->s_c[1], c->s_c[2], c->s_out, c->s_fit})
             if (st) cudaStreamDestroy(st);
+        if (c->e_zero) cudaEventDestroy(c->e_zero);
+        if (c->e_fit) cudaEventDestroy(c->e_fit);
         for (int i = 0; i < kMaxChunks; ++i) {
             cudaEventDestroy(c->e_in[i]);
             cudaEventDestroy(c->e_done[i]);

@@ -82,6 +82,29 @@ struct FitArgs {
     int hdr_bytes, off_scratch, tm_cols;
 };
 
+// The chunked host call's chain of worklists (xp_fit_tm_kernel only; n = 0: a plain launch over FitArgs' worklist).
+// ONE persistent launch serves the whole batch: a warp that finds chunk c's worklist exhausted goes on with chunk c + 1,
+// waiting (nanosleep polling) until that chunk's reads have arrived and its prefilter and worklist launches - which run
+// beside this kernel on the SMs its grid leaves free - have set ready[c + 1].  No chunk ends with a tail of idle warps,
+// and the early, small chunks no longer leave most of the machine empty.  FitArgs' position arrays are the batch's
+// (chunk c's worklist entries are relative to position p0 of the batch).
+constexpr int kMaxChainChunks = 64;
+struct FitChainChunk {
+    const int32_t* worklist;
+    unsigned int* ticket;
+    const uint32_t* n_work;
+    const uint32_t* w_begin;  // entries in front of the single-warp class (the chunk's team / streaming classes, which get launches of their own); null: none
+    int p0, pad;
+};
+struct FitChain {
+    int n;
+    unsigned int spin_limit;  // polls (about a microsecond each) before a warp gives up and raises `abort`
+    const uint32_t* ready;    // [n] device flags
+    unsigned int* abort;      // device flag: set by the host on an error path or by a warp whose wait timed out
+    unsigned int* wait_polls; // experiment builds: [n] polls spent waiting for each chunk, summed over the warps
+    FitChainChunk c[kMaxChainChunks];
+};
+
 constexpr int kTabExpDoubles = 256;
 constexpr int kTabLogDoubles = 130 * 2;
 constexpr size_t kFitTableBytes = (size_t)(kTabExpDoubles + kTabLogDoubles) * 8;

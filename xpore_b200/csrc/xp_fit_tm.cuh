@@ -81,6 +81,11 @@ __device__ __forceinline__ void tm_alloc_all(uint32_t* smem_dst) {  // one warp;
 __device__ __forceinline__ void tm_free_all(uint32_t base) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(kTmColumns) : "memory");
 }
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // one double of this thread's lane (two columns); the data are in the register when the statement is done
@@ -114,8 +119,9 @@ __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sy
 
 // GT: the number of group slots as a compile-time constant (0 = read it from the arguments): the common designs get
 // their G-sized loops unrolled and the variants of the column sums chosen at compile time.
-template <int NPW, int MAXT, int GT = 0>
-__global__ void __launch_bounds__(MAXT, 1) xp_fit_tm_kernel(FitArgs a) {
+// CHAIN: the launch of the chunked host call that follows the chain of chunk worklists (FitChain, xp_fit.cuh).
+template <int NPW, int MAXT, int GT = 0, bool CHAIN = false>
+__global__ void __launch_bounds__(MAXT, 1) xp_fit_tm_kernel(FitArgs a, FitChain ch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int LP = 32 / NPW;  // lanes per position in the scalar phase
     constexpr int CS = 33;        // doubles between scratch columns
@@ -171,13 +177,15 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_tm_kernel(FitArgs a) {
     const uint32_t tm_warp = __reduce_max_sync(kFull, tm_base + ((uint32_t)(warp & 3) << 21) + (uint32_t)(warp >> 2) * (uint32_t)(NPW * a.tm_cols));
 
     uint32_t parity = 0;
-    const unsigned w_begin = a.w_begin ? *a.w_begin : 0u;
-    const unsigned w_end = *a.w_end;
+    const unsigned w_begin = (!CHAIN && a.w_begin) ? *a.w_begin : 0u;
+    const unsigned w_end = CHAIN ? 0xffffffffu : *a.w_end;  // CHAIN: unused
     const double conc0 = a.conc0;
     const double rscale = 1.0 / a.y_scale;
     const int kpar = lane & 1;  // component owned by this lane in the scalar phase (LP is even)
 
     unsigned alive = (1u << NPW) - 1u, need = alive;  // per position slot of this warp (warp-uniform)
+    int* wcur = reinterpret_cast<int*>(mbar) + 2;  // CHAIN: the chunk this warp takes its positions from (second half of the barrier's 16 bytes)
+    if (CHAIN && lane == 0) *wcur = 0;
     int it = 0;  // sweeps of position `sub` so far: all the scalar phase carries from sweep to sweep in registers
 
     for (;;) {
@@ -195,10 +203,43 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_tm_kernel(FitArgs a) {
             bool got = false;
             for (;;) {
                 unsigned w = 0;
-                if (lane == 0) w = atomicAdd(a.ticket, 1u);
-                w = __shfl_sync(kFull, w, 0) + w_begin;
-                if (w >= w_end) break;
-                p = a.worklist ? a.worklist[w] : (int)w;
+                if (CHAIN) {
+                    // lane 0 walks the chain of chunk worklists from the warp's current chunk (kept in shared memory)
+                    int cc = 0;
+                    if (lane == 0) {
+                        cc = *wcur;
+                        while (cc < ch.n) {
+                            unsigned spins = 0, ns = 250;
+                            while (ld_acquire_u32(ch.ready + cc) == 0u) {  // the chunk's reads / prefilter / worklist are still on their way
+                                if (*reinterpret_cast<volatile unsigned int*>(ch.abort) != 0u || ++spins > ch.spin_limit) {
+                                    atomicExch(ch.abort, 1u);
+                                    cc = ch.n;
+                                    break;
+                                }
+                                __nanosleep(ns);
+                                ns = min(ns * 2u, 4000u);
+                            }
+                            if (cc >= ch.n) break;
+#ifdef XPB200_EXPERIMENTS
+                            if (spins) atomicAdd(ch.wait_polls + cc, spins);
+#endif
+                            w = atomicAdd(ch.c[cc].ticket, 1u);
+                            if (ch.c[cc].w_begin) w += *reinterpret_cast<const volatile uint32_t*>(ch.c[cc].w_begin);
+                            if (w < *reinterpret_cast<const volatile uint32_t*>(ch.c[cc].n_work)) break;
+                            ++cc;
+                        }
+                        *wcur = cc;
+                    }
+                    cc = __shfl_sync(kFull, cc, 0);
+                    if (cc >= ch.n) break;
+                    w = __shfl_sync(kFull, w, 0);
+                    p = ch.c[cc].worklist[w] + ch.c[cc].p0;
+                } else {
+                    if (lane == 0) w = atomicAdd(a.ticket, 1u);
+                    w = __shfl_sync(kFull, w, 0) + w_begin;
+                    if (w >= w_end) break;
+                    p = a.worklist ? a.worklist[w] : (int)w;
+                }
                 off = a.read_off[p];
                 n = (int)(a.read_off[p + 1] - off);
                 if (n > a.cap || n <= 0) {  // only when the caller understated batch.max_reads
