@@ -535,6 +535,36 @@ def test_fit_host_rows_equals_dense_records(torch_cuda):
     np.testing.assert_array_equal(rows2, rows)
 
 
+def test_chained_host_pipeline(torch_cuda):
+    """xpb200_fit_host_rows on a u16 batch runs its chained form (one persistent fit launch walking the chunks' worklists
+    while the reads arrive, xp_api.cu:fit_host_impl): the rows must be those of the dense, chunk-by-chunk call record for
+    record - also when a few positions belong to the 4-warp teams' class (launches of their own beside the chained one),
+    and when the caller understates max_reads (the chained launch is abandoned and the call starts over)."""
+    from xpore_b200.dist import unpack_records
+    spec = Spec({"KO": 3, "WT": 3}, reads_lo=20, reads_hi=112, f_mod=0.3, seed=23,
+                method={"prefiltering": {"method": "t-test", "threshold": 0.1}})
+    batch = make_batch(spec, KmerModel.load(), n_positions=90000)
+    assert batch.encode_reads() == 2
+    n = np.diff(batch.read_off)
+    method = xf.Method.from_dict(spec.method)
+    dense = xf.fit_batch(batch, method)  # dense results: chunk-by-chunk launches
+    team = (n >= 576) & dense.selected  # class split of two positions per warp (xp_api.cu:tm_class_split)
+    assert 5 < team.sum() < 0.01 * batch.n_positions and n.max() < 1024
+    keep = np.nonzero(dense.keep_row)[0]
+    assert team[keep].any()
+    for claim in (None, 560, 300):  # the truth; below the class split; far below
+        rows, n_fitted = xf.fit_rows(batch, method, max_reads=claim)
+        assert n_fitted == dense.n_fitted
+        idx, status, n_iter, pval, fit, stats = unpack_records(rows, xf.fit_width(6), xf.stats_width(6, 2))
+        np.testing.assert_array_equal(idx, keep)
+        np.testing.assert_array_equal(status, dense.status[keep])
+        np.testing.assert_array_equal(n_iter, dense.n_iter[keep])
+        np.testing.assert_array_equal(pval, dense.pval[keep])
+        np.testing.assert_array_equal(fit, dense.fit[keep])
+        np.testing.assert_array_equal(stats, dense.stats[keep])
+    assert not (dense.status & xf.NOT_FITTED).any()
+
+
 @pytest.mark.parametrize("grouping", ["pooled", "runs"])
 def test_deep_positions_vs_oracle(torch_cuda, grouping):
     """Positions deeper than one CTA's shared memory (the reference has no cap on n, gmm.py:93-127; pooled mode keeps

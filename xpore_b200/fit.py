@@ -155,12 +155,14 @@ def fit_batch(batch: Batch, method: Method, device: int = 0) -> FitResult:
     return res
 
 
-def fit_rows(batch: Batch, method: Method, device: int = 0, capacity_rows: int | None = None, staging=None):
+def fit_rows(batch: Batch, method: Method, device: int = 0, capacity_rows: int | None = None, staging=None,
+             max_reads: int | None = None):
     """Rows of ``diffmod.table`` only (``xpb200_fit_host_rows``): ``(records, n_fitted)`` with ``records`` the
     ``[n_rows, 4+FW+SW]`` matrix ``[position, status, n_iter, pval, fit, stats]`` of the positions that were
     fitted and pass the reference's row filter, ascending by position (``dist.unpack_records`` splits it).
     ``staging`` (:class:`xpore_b200.ingest.Staging`): take the record buffer from its page-locked memory - the
-    returned matrix is then a view that the next call with the same staging overwrites."""
+    returned matrix is then a view that the next call with the same staging overwrites.  ``max_reads`` overrides the
+    batch's own deepest position as the caller's claim (tests: the library checks it against the offsets)."""
     L = _lib.lib()
     P, G, Cn = batch.n_positions, batch.layout.n_groups, batch.layout.n_conditions
     y, yfmt, yscale = _y_buffer(batch)
@@ -174,8 +176,8 @@ def fit_rows(batch: Batch, method: Method, device: int = 0, capacity_rows: int |
     rows = staging.array("rows", np.float64, (max(cap, 1), W)) if staging is not None else \
         np.empty((max(cap, 1), W), dtype=np.float64)
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
-    b = _lib.XpBatch(P, G, Cn, _max_reads(batch), batch.n_reads, ptr(y), ptr(read_off), ptr(grp_len), ptr(km),
-                     ptr(ks), ptr(gc), yfmt, 0, yscale)
+    b = _lib.XpBatch(P, G, Cn, _max_reads(batch) if max_reads is None else int(max_reads), batch.n_reads, ptr(y),
+                     ptr(read_off), ptr(grp_len), ptr(km), ptr(ks), ptr(gc), yfmt, 0, yscale)
     m = method.c_struct()
     nr, nf = C.c_int64(0), C.c_uint32(0)
     _lib.check(L.xpb200_fit_host_rows(int(device), C.byref(b), C.byref(m), ptr(rows), cap, C.byref(nr), C.byref(nf)))
