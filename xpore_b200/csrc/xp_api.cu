@@ -602,7 +602,8 @@ struct DevCache {
     int device = -1;
     cudaStream_t s_in = nullptr, s_c[kComputeStreams] = {nullptr, nullptr, nullptr}, s_out = nullptr;
     cudaEvent_t e_in[kMaxChunks], e_done[kMaxChunks];
-    cudaStream_t s_fit = nullptr;                    // the chained launch (see fit_host_impl)
+    cudaStream_t s_fit = nullptr, s_help = nullptr;  // the chained launch and its late helper (see fit_host_impl)
+    cudaEvent_t e_sel[kComputeStreams] = {nullptr, nullptr, nullptr}, e_help = nullptr;
     cudaEvent_t e_zero = nullptr, e_fit = nullptr;   // its flags are cleared / it is done
     cudaEvent_t e_call = nullptr;  // end of the previous call's device work (the arena is reused by the next one)
     cudaEvent_t e_user = nullptr;  // the caller's stream at entry of an asynchronous call
@@ -721,6 +722,9 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         CK(cudaEventCreateWithFlags(&dc->e_call, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&dc->e_user, cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&dc->s_fit, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&dc->s_help, cudaStreamNonBlocking));
+        for (int i = 0; i < kComputeStreams; ++i) CK(cudaEventCreateWithFlags(&dc->e_sel[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&dc->e_help, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&dc->e_zero, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&dc->e_fit, cudaEventDisableTiming));
         g_cache.push_back(dc);
@@ -881,6 +885,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         CK(cudaStreamWaitEvent(dc->s_in, dc->e_call, 0));
         for (int i = 0; i < kComputeStreams; ++i) CK(cudaStreamWaitEvent(dc->s_c[i], dc->e_call, 0));
         CK(cudaStreamWaitEvent(dc->s_fit, dc->e_call, 0));
+        CK(cudaStreamWaitEvent(dc->s_help, dc->e_call, 0));
     }
     if (async) {
         CK(cudaEventRecord(dc->e_user, ho.user_stream));
@@ -890,13 +895,16 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     CK(cudaMemcpyAsync(d + o_gc, b->grp_cond, (size_t)G * 4, cudaMemcpyDefault, dc->s_in));
     CK(cudaMemsetAsync(d_nf, 0, (size_t)kMaxChunks * 4, dc->s_in));
     CK(cudaMemsetAsync(d_nr, 0, (size_t)kMaxChunks * 4, dc->s_in));
-    bool chain_launched = false, chain_understated = false;
+    bool chain_launched = false, chain_understated = false, chain_helper = false;
+    xpk::FitArgs chain_fa;
+    xpk::FitChain chain_ch;
     // An error return after the chained launch must not leave it polling for chunks that will never come
     auto chain_bail = [&](int rc) -> int {
         if (chain_launched) {
             cudaMemsetAsync(d_abort, 0xFF, 4, dc->s_out);
             cudaStreamSynchronize(dc->s_out);
             cudaStreamSynchronize(dc->s_fit);
+            cudaStreamSynchronize(dc->s_help);
             for (int i = 0; i < kComputeStreams; ++i) cudaStreamSynchronize(dc->s_c[i]);
             cudaStreamSynchronize(dc->s_in);
         }
@@ -950,7 +958,8 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         CKB(cudaMemsetAsync(d_ready + c, 0x01, 4, sc));
         if (trace) CKB(cudaEventRecord(dc->t_done[c], sc));
         if (c == 0) {  // the chained launch, as soon as the first chunk is on its way
-            xpk::FitArgs fa;
+            xpk::FitArgs& fa = chain_fa;
+            xpk::FitChain& ch = chain_ch;
             memset(&fa, 0, sizeof(fa));
             fa.y = d_y; fa.y_format = b->y_format; fa.y_scale = b->y_scale;
             fa.read_off = d_off; fa.grp_len = d_glen; fa.kmer_mean = d_km; fa.kmer_std = d_ks;
@@ -959,7 +968,6 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
             fa.fit = d_fit; fa.n_iter = d_niter; fa.status = d_status; fa.coef = nullptr;
             fa.cap = gch.cap;
             xpk::fit_tm_fill_layout(fa, gch.np);
-            xpk::FitChain ch;
             memset(&ch, 0, sizeof(ch));
             ch.n = nchunks;
             ch.spin_limit = kChainSpinLimit;
@@ -973,6 +981,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
             }
             const int need = (P + gch.teams - 1) / gch.teams;
             const int grid = std::max(1, std::min(gch.sms * gch.ctas_per_sm - chain_free_sms, need));
+            chain_helper = need > grid;
             chain_fn<<<grid, gch.threads, gch.smem, dc->s_fit>>>(fa, ch);
             ++g_launches;
             CKB(cudaGetLastError());
@@ -982,6 +991,20 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     if (chain && chain_understated) {
         chain_bail(0);
         return fit_host_impl(device, b, m, ho, false);
+    }
+    if (chain && chain_helper && exp_int("XPB200_CHAIN_HELPER", 1)) {
+        // Once every chunk's select phase is through, the SMs kept free have nothing left to do: a second launch of the
+        // same kernel on them walks the same chain (a batch whose fit outlasts its copy - c3, c5 - would otherwise run
+        // its whole second half on 142 of 148 SMs)
+        for (int i = 0; i < n_streams; ++i) {
+            CKB(cudaEventRecord(dc->e_sel[i], dc->s_c[i]));
+            CKB(cudaStreamWaitEvent(dc->s_help, dc->e_sel[i], 0));
+        }
+        chain_fn<<<chain_free_sms, gch.threads, gch.smem, dc->s_help>>>(chain_fa, chain_ch);
+        ++g_launches;
+        CKB(cudaGetLastError());
+        CKB(cudaEventRecord(dc->e_help, dc->s_help));
+        CKB(cudaStreamWaitEvent(dc->s_fit, dc->e_help, 0));
     }
     if (chain) {
         // statistics of every chunk once the chained launch is done, then the rows of the whole batch in position order
@@ -1186,8 +1209,11 @@ void xpb200_release(void) {
         cudaSetDevice(c->device);
         cudaDeviceSynchronize();  // an asynchronous call may still be using the arena
         if (c->buf) cudaFree(c->buf);
-        for (cudaStream_t st : {c->s_in, c->s_c[0], c->s_c[1], c->s_c[2], c->s_out, c->s_fit})
+        for (cudaStream_t st : {c->s_in, c->s_c[0], c->s_c[1], c->s_c[2], c->s_out, c->s_fit, c->s_help})
             if (st) cudaStreamDestroy(st);
+        for (int i = 0; i < kComputeStreams; ++i)
+            if (c->e_sel[i]) cudaEventDestroy(c->e_sel[i]);
+        if (c->e_help) cudaEventDestroy(c->e_help);
         if (c->e_zero) cudaEventDestroy(c->e_zero);
         if (c->e_fit) cudaEventDestroy(c->e_fit);
         for (int i = 0; i < kMaxChunks; ++i) {
