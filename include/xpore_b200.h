@@ -134,7 +134,10 @@ int32_t xpb200_fit_host(int32_t device, const xpb200_batch* batch, const xpb200_
  * rows[n_rows][4+FW+SW] f64 = [position, status, n_iter, pval, fit[FW], stats[SW]] (the record of
  * xpb200_pack_records), ascending by position.  This is what `execute()` (scripts/diffmod.py:15-77) hands to
  * the table writer.  `rows` holds `capacity_rows` rows (XPB200_ENOMEM and *n_rows = rows needed if more);
- * copies the batch up in chunks like xpb200_fit_host, synchronises. */
+ * copies the batch up in chunks like xpb200_fit_host, synchronises.
+ * A u16 batch is fitted by ONE persistent launch that follows the chunks as they arrive ("chained
+ * form"); it is sized by batch->max_reads, so an understated max_reads costs a restart (never a wrong result), and it
+ * keeps all but six SMs of the device busy for the duration of the call. */
 int32_t xpb200_fit_host_rows(int32_t device, const xpb200_batch* batch, const xpb200_method* method, double* rows,
                              int64_t capacity_rows, int64_t* n_rows, uint32_t* n_fitted);
 

@@ -33,10 +33,10 @@ cap() { # config positions count
     python tools/ncu_summary.py $D/step_$cfg.ncu-rep > $D/step_$cfg.ncu_summary.txt 2>&1
     rm -f $D/step_$cfg.ncu-rep
 }
-cap c2 0 7
-cap c3 0 7
-cap c4 0 8
-cap c5 1000000 8
+cap c2 0 9
+cap c3 0 9
+cap c4 0 10
+cap c5 1000000 9
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:"xp_(pack|count|concat)" -c 4 -f -o $D/pack_c2 \
   python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-cli > $D/ncu_pack_c2.log 2>&1; echo "ncu pack rc=$?"
 python tools/ncu_summary.py $D/pack_c2.ncu-rep > $D/pack_c2.ncu_summary.txt 2>&1

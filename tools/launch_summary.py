@@ -27,6 +27,8 @@ idx = [j for j, r in enumerate(ours) if "xp_stats_kernel" in r[1]]
 if idx:
     end = idx[-1]
     start = max(j for j in range(end) if "xp_prefilter_kernel" in ours[j][1])
+    if start > 0 and "xp_prefilter_u16_kernel" in ours[start - 1][1]:  # u16 batches: the pair of prefilter launches
+        start -= 1
     step = ours[start:end + 1]
     tot = sum(r[4] for r in step)
     print("# the last complete step in this list is launches %d-%d:" % (step[0][0], step[-1][0]))

@@ -920,15 +920,25 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         CK(cudaEventRecord(dc->e_zero, dc->s_in));
         CK(cudaStreamWaitEvent(dc->s_fit, dc->e_zero, 0));
     }
+    int meta_next = 0;
+    const size_t chain_meta_bytes = (size_t)std::max(1, exp_int("XPB200_CHAIN_META_MB", 128)) << 20;  // reads per group of small-array copies
     for (int c = 0; chain && c < nchunks; ++c) {
         const int p0 = cut[c], p1 = cut[c + 1], pc = p1 - p0;
         const int64_t r0 = roff[p0], r1 = roff[p1];
+        if (c == meta_next) {
+            // the small arrays (offsets, group lengths, priors: 6 % of the bytes) go up for several chunks at once, in front
+            // of the first one's reads: four more copies per chunk cost the copy engine ~25 us of gaps each time
+            int ce = c;
+            while (ce < nchunks && (ce == c || (size_t)(roff[cut[ce + 1]] - roff[cut[c]]) * eb <= chain_meta_bytes)) ++ce;
+            const int q0 = cut[c], qc = cut[ce] - cut[c];
+            CKB(cudaMemcpyAsync(d_off + q0, roff + q0, (size_t)(qc + 1) * 8, cudaMemcpyDefault, dc->s_in));
+            CKB(cudaMemcpyAsync(d_glen + (size_t)q0 * G, b->grp_len + (size_t)q0 * G, (size_t)qc * G * 4, cudaMemcpyDefault, dc->s_in));
+            CKB(cudaMemcpyAsync(d_km + q0, b->kmer_mean + q0, (size_t)qc * 8, cudaMemcpyDefault, dc->s_in));
+            CKB(cudaMemcpyAsync(d_ks + q0, b->kmer_std + q0, (size_t)qc * 8, cudaMemcpyDefault, dc->s_in));
+            meta_next = ce;
+        }
         CKB(cudaMemcpyAsync(d_y + (size_t)r0 * eb, (const char*)b->y + (size_t)r0 * eb, (size_t)(r1 - r0) * eb,
                             cudaMemcpyDefault, dc->s_in));
-        CKB(cudaMemcpyAsync(d_off + p0, roff + p0, (size_t)(pc + 1) * 8, cudaMemcpyDefault, dc->s_in));
-        CKB(cudaMemcpyAsync(d_glen + (size_t)p0 * G, b->grp_len + (size_t)p0 * G, (size_t)pc * G * 4, cudaMemcpyDefault, dc->s_in));
-        CKB(cudaMemcpyAsync(d_km + p0, b->kmer_mean + p0, (size_t)pc * 8, cudaMemcpyDefault, dc->s_in));
-        CKB(cudaMemcpyAsync(d_ks + p0, b->kmer_std + p0, (size_t)pc * 8, cudaMemcpyDefault, dc->s_in));
         CKB(cudaEventRecord(dc->e_in[c], dc->s_in));
         if (trace) CKB(cudaEventRecord(dc->t_in[c], dc->s_in));
         // the chunk's select phase (prefilter, worklist) on the SMs the chained launch leaves free, then its ready flag
