@@ -9,6 +9,7 @@
 #include <chrono>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -603,6 +604,9 @@ struct DevCache {
     cudaStream_t s_in = nullptr, s_c[kComputeStreams] = {nullptr, nullptr, nullptr}, s_out = nullptr;
     cudaEvent_t e_in[kMaxChunks], e_done[kMaxChunks];
     cudaStream_t s_fit = nullptr, s_help = nullptr;  // the chained launch and its late helper (see fit_host_impl)
+    cudaStream_t s_post[kComputeStreams] = {nullptr, nullptr, nullptr}, s_poll = nullptr;  // chained form: statistics / rows of finished chunks, progress polls
+    cudaEvent_t e_cls[kMaxChunks];                   // a chunk's select phase and class launches are enqueued / done
+    uint32_t* h_poll = nullptr;                      // page-locked: the flag words, then n_fitted and the row count of every chunk
     cudaEvent_t e_sel[kComputeStreams] = {nullptr, nullptr, nullptr}, e_help = nullptr;
     cudaEvent_t e_zero = nullptr, e_fit = nullptr;   // its flags are cleared / it is done
     cudaEvent_t e_call = nullptr;  // end of the previous call's device work (the arena is reused by the next one)
@@ -723,6 +727,10 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         CK(cudaEventCreateWithFlags(&dc->e_user, cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&dc->s_fit, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&dc->s_help, cudaStreamNonBlocking));
+        for (int i = 0; i < kComputeStreams; ++i) CK(cudaStreamCreateWithFlags(&dc->s_post[i], cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&dc->s_poll, cudaStreamNonBlocking));
+        for (int i = 0; i < kMaxChunks; ++i) CK(cudaEventCreateWithFlags(&dc->e_cls[i], cudaEventDisableTiming));
+        CK(cudaHostAlloc((void**)&dc->h_poll, (size_t)(6 * kMaxChunks + 8) * 4, cudaHostAllocPortable));
         for (int i = 0; i < kComputeStreams; ++i) CK(cudaEventCreateWithFlags(&dc->e_sel[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&dc->e_help, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&dc->e_zero, cudaEventDisableTiming));
@@ -770,6 +778,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         }
     }
     const bool chain = chain_fn != nullptr;
+    const bool chain_two_class = chain && b->max_reads >= tm_class_split(chain_npw);  // chunks have a team class of their own
     const int chain_free_sms = std::max(1, exp_int("XPB200_CHAIN_FREE_SMS", kChainFreeSms));
     const size_t chunk_cap = chain ? std::max(kChainChunkBytes, total_bytes / (size_t)(kMaxChunks - 16)) : kChunkBytes;
     const size_t chunk_bytes = (size_t)std::max(1, exp_int(chain ? "XPB200_CHAIN_CHUNK_MB" : "XPB200_CHUNK_MB", (int)(chunk_cap >> 20))) << 20;
@@ -838,7 +847,9 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     const size_t o_pval = o; o += align_up((size_t)P * 8);
     const size_t o_fit = o; o += align_up((size_t)P * FW * 8);
     const size_t o_stats = o; o += align_up((size_t)P * SW * 8);
-    const size_t o_flags = o; o += align_up((size_t)(2 * kMaxChunks + 1) * 4);  // chained form: ready[c], the abort flag, polls spent waiting (experiment builds)
+    // chained form: ready[c], the abort flag, polls spent waiting (experiment builds), positions done, size of the team / streaming classes
+    constexpr int kFlagWords = 4 * kMaxChunks + 1;
+    const size_t o_flags = o; o += align_up((size_t)kFlagWords * 4);
     const size_t o_nf = o; o += align_up((size_t)kMaxChunks * 4);
     const size_t o_nr = o; o += align_up((size_t)kMaxChunks * 4);
     const size_t o_cnt = o; o += want_rows ? align_up((size_t)kMaxChunks * kPackWarps * 4) : 0;
@@ -874,6 +885,8 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     double* d_stats = (double*)(d + o_stats);
     uint32_t* d_ready = (uint32_t*)(d + o_flags);
     uint32_t* d_abort = d_ready + kMaxChunks;
+    uint32_t* d_done = d_abort + 1 + kMaxChunks;
+    uint32_t* d_nl = d_done + kMaxChunks;
     uint32_t* d_nf = (uint32_t*)(d + o_nf);
     uint32_t* d_nr = (uint32_t*)(d + o_nr);
     uint32_t* d_cnt = (uint32_t*)(d + o_cnt);
@@ -886,6 +899,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         for (int i = 0; i < kComputeStreams; ++i) CK(cudaStreamWaitEvent(dc->s_c[i], dc->e_call, 0));
         CK(cudaStreamWaitEvent(dc->s_fit, dc->e_call, 0));
         CK(cudaStreamWaitEvent(dc->s_help, dc->e_call, 0));
+        for (int i = 0; i < kComputeStreams; ++i) CK(cudaStreamWaitEvent(dc->s_post[i], dc->e_call, 0));
     }
     if (async) {
         CK(cudaEventRecord(dc->e_user, ho.user_stream));
@@ -906,6 +920,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
             cudaStreamSynchronize(dc->s_fit);
             cudaStreamSynchronize(dc->s_help);
             for (int i = 0; i < kComputeStreams; ++i) cudaStreamSynchronize(dc->s_c[i]);
+            for (int i = 0; i < kComputeStreams; ++i) cudaStreamSynchronize(dc->s_post[i]);
             cudaStreamSynchronize(dc->s_in);
         }
         return rc;
@@ -916,7 +931,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         if (e_ != cudaSuccess) return chain_bail(fail(XPB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); \
     } while (0)
     if (chain) {
-        CK(cudaMemsetAsync(d_ready, 0, (size_t)(2 * kMaxChunks + 1) * 4, dc->s_in));
+        CK(cudaMemsetAsync(d_ready, 0, (size_t)kFlagWords * 4, dc->s_in));
         CK(cudaEventRecord(dc->e_zero, dc->s_in));
         CK(cudaStreamWaitEvent(dc->s_fit, dc->e_zero, 0));
     }
@@ -965,7 +980,9 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         const int rc_sel = fit_device_phases(&db, m, &dr, d + o_ws[c], xpb200_workspace_bytes(pc), d_nf + c, sc, kPhaseSelect | kPhaseFitLarge);
         g_fit_grid_cap = 0;
         if (rc_sel) return chain_bail(rc_sel);
+        if (chain_two_class) CKB(cudaMemcpyAsync(d_nl + c, carve(d + o_ws[c]).n_large, 4, cudaMemcpyDeviceToDevice, sc));
         CKB(cudaMemsetAsync(d_ready + c, 0x01, 4, sc));
+        CKB(cudaEventRecord(dc->e_cls[c], sc));
         if (trace) CKB(cudaEventRecord(dc->t_done[c], sc));
         if (c == 0) {  // the chained launch, as soon as the first chunk is on its way
             xpk::FitArgs& fa = chain_fa;
@@ -984,10 +1001,11 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
             ch.ready = d_ready;
             ch.abort = d_abort;
             ch.wait_polls = d_abort + 1;
+            ch.done = d_done;
             for (int k = 0; k < nchunks; ++k) {
                 const Workspace wk = carve(d + o_ws[k]);
                 ch.c[k].worklist = wk.worklist; ch.c[k].ticket = wk.ticket; ch.c[k].n_work = wk.n_work; ch.c[k].p0 = cut[k];
-                ch.c[k].w_begin = b->max_reads >= tm_class_split(chain_npw) ? wk.n_large : nullptr;
+                ch.c[k].w_begin = chain_two_class ? wk.n_large : nullptr;
             }
             const int need = (P + gch.teams - 1) / gch.teams;
             const int grid = std::max(1, std::min(gch.sms * gch.ctas_per_sm - chain_free_sms, need));
@@ -1025,6 +1043,94 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
                 CKB(cudaEventCreate(&dc->t_post));
             }
             CKB(cudaEventRecord(dc->t_fit, dc->s_fit));
+        }
+        if (exp_int("XPB200_CHAIN_POST", 1)) {
+            // A chunk's statistics, row compaction and copy-out as soon as all its positions are fitted, while the chained
+            // launch works on later chunks: the host polls the per-chunk counts of finished positions the kernel keeps.
+            uint32_t* h_flags = dc->h_poll;                  // [kFlagWords]
+            uint32_t* h_nf = dc->h_poll + kFlagWords + 3;    // [kMaxChunks]
+            uint32_t* h_cnt = h_nf + kMaxChunks;             // [kMaxChunks] rows of each chunk
+            const uint32_t *h_ready = h_flags, *h_abort = h_flags + kMaxChunks, *h_done = h_abort + 1 + kMaxChunks, *h_nl = h_done + kMaxChunks;
+            int next_post = 0, next_copy = 0;
+            int64_t total_rows = 0;
+            bool overflow = false, failed = false;
+            while (next_copy < nchunks) {
+                bool progressed = false;
+                if (next_post < nchunks) {
+                    const bool fit_over = cudaEventQuery(dc->e_fit) == cudaSuccess;  // read BEFORE the counts
+                    CKB(cudaMemcpyAsync(h_flags, d_ready, (size_t)kFlagWords * 4, cudaMemcpyDefault, dc->s_poll));
+                    CKB(cudaMemcpyAsync(h_nf, d_nf, (size_t)kMaxChunks * 4, cudaMemcpyDefault, dc->s_poll));
+                    CKB(cudaStreamSynchronize(dc->s_poll));
+                    if (*h_abort != 0u) {
+                        failed = true;
+                        break;
+                    }
+                    while (next_post < nchunks && h_ready[next_post] != 0u &&
+                           h_done[next_post] == h_nf[next_post] - h_nl[next_post]) {
+                        const int c = next_post, p0 = cut[c], pc = cut[c + 1] - cut[c];
+                        cudaStream_t sp = dc->s_post[c % kComputeStreams];
+                        CKB(cudaStreamWaitEvent(sp, dc->e_cls[c], 0));
+                        xpb200_batch db = *b;
+                        db.n_positions = pc;
+                        db.y = d_y; db.read_off = d_off + p0; db.grp_len = d_glen + (size_t)p0 * G;
+                        db.kmer_mean = d_km + p0; db.kmer_std = d_ks + p0; db.grp_cond = (const int32_t*)(d + o_gc);
+                        xpb200_result dr;
+                        dr.status = d_status + p0; dr.n_iter = d_niter + p0; dr.pval = d_pval + p0;
+                        dr.fit = d_fit + (size_t)p0 * FW; dr.stats = d_stats + (size_t)p0 * SW;
+                        dr.coef = nullptr;
+                        const Workspace wk = carve(d + o_ws[c]);
+                        if (int rc = launch_stats(&db, m, &dr, wk.worklist, wk.n_work, sp)) return chain_bail(rc);
+                        if (int rc = launch_pack_rows(dr, pc, FW, SW, ho.index_offset + p0, pc, d_cnt + (size_t)c * kPackWarps, d_nr + c,
+                                                      d_rows + (size_t)p0 * RW, sp))
+                            return chain_bail(rc);
+                        CKB(cudaMemcpyAsync(h_cnt + c, d_nr + c, 4, cudaMemcpyDefault, sp));
+                        CKB(cudaEventRecord(dc->e_done[c], sp));
+                        ++next_post;
+                        progressed = true;
+                    }
+                    if (!progressed && fit_over && next_post < nchunks) {  // the launch is over, yet a chunk is incomplete
+                        failed = true;
+                        break;
+                    }
+                }
+                while (next_copy < next_post && cudaEventQuery(dc->e_done[next_copy]) == cudaSuccess) {
+                    const int c = next_copy;
+                    const int64_t cnt = h_cnt[c];
+                    if (total_rows + cnt > ho.rows_capacity) overflow = true;
+                    else if (cnt)
+                        CKB(cudaMemcpyAsync(rows + (size_t)total_rows * RW, d_rows + (size_t)cut[c] * RW, (size_t)cnt * RW * 8,
+                                            cudaMemcpyDefault, dc->s_out));
+                    total_rows += cnt;
+                    ++next_copy;
+                    progressed = true;
+                }
+                if (!progressed) std::this_thread::sleep_for(std::chrono::microseconds(20));
+            }
+            if (failed) {  // a warp gave up waiting for a chunk (the free SMs were not free?): chunk by chunk, then
+                chain_bail(0);
+                CK(cudaEventRecord(dc->e_call, dc->s_out));
+                return fit_host_impl(device, b, m, ho, false);
+            }
+            if (trace) CKB(cudaEventRecord(dc->t_post, dc->s_out));
+            CK(cudaStreamSynchronize(dc->s_out));
+            for (int i = 0; i < kComputeStreams; ++i) CK(cudaStreamSynchronize(dc->s_c[i]));
+            for (int i = 0; i < kComputeStreams; ++i) CK(cudaStreamSynchronize(dc->s_post[i]));
+            CK(cudaStreamSynchronize(dc->s_in));
+            CK(cudaStreamSynchronize(dc->s_fit));
+            CK(cudaEventRecord(dc->e_call, dc->s_out));
+            *ho.n_rows = total_rows;
+            uint32_t total = 0;
+            for (int c = 0; c < nchunks; ++c) total += h_nf[c];
+            if (ho.n_fitted) *ho.n_fitted = total;
+            if (overflow) return fail(XPB200_ENOMEM, "rows buffer too small: " + std::to_string(total_rows) + " rows needed");
+            if (trace) {
+                const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+                float tf = 0, tp = 0;
+                cudaEventElapsedTime(&tf, dc->t_0, dc->t_fit);
+                cudaEventElapsedTime(&tp, dc->t_0, dc->t_post);
+                fprintf(stderr, "[xpb200 trace] chained: %d chunks, host %.3f ms, chained launch done %.3f, last rows on their way %.3f ms\n", nchunks, host_ms, tf, tp);
+            }
+            return 0;
         }
         for (int c = 0; c < nchunks; ++c) {
             const int p0 = cut[c], pc = cut[c + 1] - cut[c];
@@ -1221,8 +1327,13 @@ void xpb200_release(void) {
         if (c->buf) cudaFree(c->buf);
         for (cudaStream_t st : {c->s_in, c->s_c[0], c->s_c[1], c->s_c[2], c->s_out, c->s_fit, c->s_help})
             if (st) cudaStreamDestroy(st);
-        for (int i = 0; i < kComputeStreams; ++i)
+        for (int i = 0; i < kComputeStreams; ++i) {
             if (c->e_sel[i]) cudaEventDestroy(c->e_sel[i]);
+            if (c->s_post[i]) cudaStreamDestroy(c->s_post[i]);
+        }
+        if (c->s_poll) cudaStreamDestroy(c->s_poll);
+        for (int i = 0; i < kMaxChunks; ++i) cudaEventDestroy(c->e_cls[i]);
+        if (c->h_poll) cudaFreeHost(c->h_poll);
         if (c->e_help) cudaEventDestroy(c->e_help);
         if (c->e_zero) cudaEventDestroy(c->e_zero);
         if (c->e_fit) cudaEventDestroy(c->e_fit);

@@ -102,6 +102,8 @@ struct FitChain {
     const uint32_t* ready;    // [n] device flags
     unsigned int* abort;      // device flag: set by the host on an error path or by a warp whose wait timed out
     unsigned int* wait_polls; // experiment builds: [n] polls spent waiting for each chunk, summed over the warps
+    unsigned int* done;       // [n] positions of each chunk fitted so far (their records are visible device-wide): the host
+                              // polls these and runs a chunk's statistics / row compaction / copy-out while later chunks are fitted
     FitChainChunk c[kMaxChainChunks];
 };
 

@@ -33,7 +33,8 @@
 // warp region:       [ mbar (16 B) | header of position 0 | (header of position 1) | staging (u16 codes, TMA
 //                      destination) | scratch columns (G + 3) x 33 doubles, >= 2 KB: select histograms before the first sweep ]
 // position header:   sc[8] bc[8] pc[8] | tot[G + 4] | Asm[G] | dps[G] | goff[G + 1] (int) | gid[cap] (u8)
-//   bc: 0 B, 1 C, 2 go flag, 3 state (int: 0 out of work, 1 swept, 2 new), 4 {p, n} (ints), 5 second start location
+//   bc: 0 B, 1 C, 2 go flag, 3 state (int: 0 out of work, 1 swept, 2 new), 4 {p, n} (ints), 5 second start location,
+//       6 chunk of the position (int; chained launch)
 //   pc: m0, a0, b0, ELBO constant, prior_gamma, sum y', sum y'^2, previous ELBO;  tot[G + 3] = N_0
 #pragma once
 #include "xp_fit.cuh"
@@ -198,14 +199,13 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_tm_kernel(FitArgs a, FitChain 
             double* tot = reinterpret_cast<double*>(hb + a.off_tot);
             int* goff = reinterpret_cast<int*>(hb + a.off_goff);
             unsigned char* gid = hb + a.off_gid;
-            int p = 0, n = 0;
+            int p = 0, n = 0, cc = 0;
             int64_t off = 0;
             bool got = false;
             for (;;) {
                 unsigned w = 0;
                 if (CHAIN) {
                     // lane 0 walks the chain of chunk worklists from the warp's current chunk (kept in shared memory)
-                    int cc = 0;
                     if (lane == 0) {
                         cc = *wcur;
                         while (cc < ch.n) {
@@ -246,6 +246,10 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_tm_kernel(FitArgs a, FitChain 
                     if (lane == 0) {
                         a.status[p] = (a.status[p] & (STATUS_TTEST_VALID | STATUS_NEAR_THRESHOLD)) | STATUS_SELECTED | STATUS_NOT_FITTED;
                         a.n_iter[p] = -1;
+                        if (CHAIN) {
+                            __threadfence();
+                            atomicAdd(ch.done + cc, 1u);
+                        }
                     }
                     continue;
                 }
@@ -368,6 +372,7 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_tm_kernel(FitArgs a, FitChain 
                 reinterpret_cast<int*>(bc + 3)[0] = 2;
                 reinterpret_cast<int*>(bc + 4)[0] = p;
                 reinterpret_cast<int*>(bc + 4)[1] = n;
+                if (CHAIN) reinterpret_cast<int*>(bc + 6)[0] = cc;
                 bc[5] = loc1;
             }
         }
@@ -520,6 +525,11 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_tm_kernel(FitArgs a, FitChain 
                     const double v = Ltot[g];
                     out[FIT_N + s] = (it == 0) ? 0.0 : (kpar ? (double)(Lgoff[g + 1] - Lgoff[g]) - v : v);
                 }
+                if (CHAIN) __threadfence();  // the record before the chunk's count of finished positions
+            }
+            if (CHAIN) {
+                __syncwarp();
+                if (live && !go && sl == 0) atomicAdd(ch.done + reinterpret_cast<const int*>(Lbc + 6)[0], 1u);
             }
         }
         __syncwarp();
