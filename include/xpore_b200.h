@@ -146,7 +146,8 @@ int32_t xpb200_fit_host_rows(int32_t device, const xpb200_batch* batch, const xp
  * scripts/diffmod.py:68-69).  Host buffers in (pinned: the copies are asynchronous; they must stay valid until the
  * work completes); rows_dev[capacity_rows][4+FW+SW] and counts_dev[2] = {rows needed, positions fitted} are device
  * memory.  Record column 0 is index_offset + position.  Rows beyond capacity_rows are dropped (counts_dev[0] still
- * reports the number needed).  Everything is ordered after the work already enqueued on `cuda_stream`, and later work on
+ * reports the number needed; 0xffffffff there: the persistent launch of the chained form gave up waiting for a chunk -
+ * the device was not this call's alone - and the rows are incomplete).  Everything is ordered after the work already enqueued on `cuda_stream`, and later work on
  * `cuda_stream` is ordered after it; the call returns as soon as the work is enqueued. */
 int32_t xpb200_fit_host_rows_async(int32_t device, const xpb200_batch* batch, const xpb200_method* method,
                                    double* rows_dev, int64_t capacity_rows, int64_t index_offset, uint32_t* counts_dev,

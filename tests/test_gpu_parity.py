@@ -563,6 +563,36 @@ def test_chained_host_pipeline(torch_cuda):
         np.testing.assert_array_equal(fit, dense.fit[keep])
         np.testing.assert_array_equal(stats, dense.stats[keep])
     assert not (dense.status & xf.NOT_FITTED).any()
+    # the asynchronous entry point of the multi-GPU path (rows and counts stay on the device, nothing waits on the host):
+    # the same rows, with an index offset, behind work already enqueued on the caller's stream; too small a buffer
+    # drops rows but reports the number needed
+    import ctypes as C
+    from xpore_b200 import _lib
+    torch = torch_cuda
+    L = _lib.lib()
+    W = 4 + xf.fit_width(6) + xf.stats_width(6, 2)
+    y, yfmt, yscale = xf._y_buffer(batch)
+    arrs = [y, np.ascontiguousarray(batch.read_off, dtype=np.int64), np.ascontiguousarray(batch.grp_len, dtype=np.int32),
+            np.ascontiguousarray(batch.kmer_mean), np.ascontiguousarray(batch.kmer_std),
+            np.ascontiguousarray(batch.layout.grp_cond, dtype=np.int32)]
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    cb = _lib.XpBatch(batch.n_positions, 6, 2, int(n.max()), batch.n_reads, *[ptr(a) for a in arrs], yfmt, 0, yscale)
+    cm = method.c_struct()
+    for cap in (len(keep) + 10, len(keep) - 7):
+        rows_dev = torch.full((cap, W), -1.0, dtype=torch.float64, device="cuda:0")
+        counts = torch.zeros(2, dtype=torch.int32, device="cuda:0")
+        busy = torch.ones(1 << 24, device="cuda:0")
+        for _ in range(8):
+            busy = busy * 1.0001  # work in front of the call on the caller's stream
+        _lib.check(L.xpb200_fit_host_rows_async(0, C.byref(cb), C.byref(cm), rows_dev.data_ptr(), cap, 1000, counts.data_ptr(),
+                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        got = rows_dev.clone()  # ordered after the call on the same stream
+        torch.cuda.synchronize()
+        assert counts.tolist() == [len(keep), dense.n_fitted]
+        m_ = min(cap, len(keep))
+        exp_rows = rows.copy()
+        exp_rows[:, 0] += 1000
+        np.testing.assert_array_equal(got.cpu().numpy()[:m_], exp_rows[:m_])
 
 
 @pytest.mark.parametrize("grouping", ["pooled", "runs"])

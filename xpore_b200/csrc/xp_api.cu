@@ -756,7 +756,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     Geometry gch;
     FitKernelFn chain_fn = nullptr;
     int chain_npw = 0;
-    if (allow_chain && want_rows && !async && b->y_format == XPB200_Y_U16 && b->max_reads > 0 &&
+    if (allow_chain && want_rows && b->y_format == XPB200_Y_U16 && b->max_reads > 0 &&
         exp_int("XPB200_TM", 1) != 0 && exp_int("XPB200_CHAIN", 1) != 0 && total_bytes >= (8u << 20)) {
         chain_npw = tm_positions_per_warp(G, b->max_reads);
         // the chained launch is the single-warp class's; the chunks' team / streaming classes keep their own launches,
@@ -1044,7 +1044,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
             }
             CKB(cudaEventRecord(dc->t_fit, dc->s_fit));
         }
-        if (exp_int("XPB200_CHAIN_POST", 1)) {
+        if (!async && exp_int("XPB200_CHAIN_POST", 1)) {
             // A chunk's statistics, row compaction and copy-out as soon as all its positions are fitted, while the chained
             // launch works on later chunks: the host polls the per-chunk counts of finished positions the kernel keeps.
             uint32_t* h_flags = dc->h_poll;                  // [kFlagWords]
@@ -1151,6 +1151,17 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         }
         xpb200_result dr;
         dr.status = d_status; dr.n_iter = d_niter; dr.pval = d_pval; dr.fit = d_fit; dr.stats = d_stats; dr.coef = nullptr;
+        if (async) {
+            // the rows straight into the caller's device buffer, the counts beside them; nothing waits on the host
+            if (int rc = launch_pack_rows(dr, P, FW, SW, ho.index_offset, ho.rows_capacity, d_cnt, d_nr, ho.rows_dev, dc->s_out))
+                return chain_bail(rc);
+            xpk::xp_chain_counts_kernel<<<1, 32, 0, dc->s_out>>>(d_nr, d_nf, nchunks, d_abort, ho.counts_dev);
+            ++g_launches;
+            CKB(cudaGetLastError());
+            CKB(cudaEventRecord(dc->e_call, dc->s_out));
+            CKB(cudaStreamWaitEvent(ho.user_stream, dc->e_call, 0));
+            return 0;
+        }
         if (int rc = launch_pack_rows(dr, P, FW, SW, ho.index_offset, P, d_cnt, d_nr, d_rows, dc->s_out)) return chain_bail(rc);
         if (trace) CKB(cudaEventRecord(dc->t_post, dc->s_out));
         uint32_t tail[2] = {0u, 0u};  // rows, abort flag

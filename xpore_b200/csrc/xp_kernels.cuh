@@ -838,6 +838,18 @@ __global__ void xp_pack_rows_kernel(PackRowsArgs a) {
     }
 }
 
+// Counts of an asynchronous call in the chained form of the host pipeline: {rows needed, positions fitted}; all ones
+// in the first when the chained launch gave up waiting for a chunk (the caller cannot be told any other way).
+__global__ void xp_chain_counts_kernel(const unsigned int* n_rows, const unsigned int* n_fitted, int n_chunks,
+                                       const unsigned int* abort_flag, unsigned int* out_counts) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned int fitted = 0;
+        for (int c = 0; c < n_chunks; ++c) fitted += n_fitted[c];
+        out_counts[0] = *abort_flag ? 0xffffffffu : n_rows[0];
+        out_counts[1] = fitted;
+    }
+}
+
 // Rows of several chunks (xpb200_fit_host_rows_async: chunk c's rows sit at row chunk_start[c] of `rows`, n_rows[c] of
 // them) concatenated in chunk order into `out`; one warp per row.  out_counts = {rows needed, positions fitted}.
 constexpr int kMaxRowChunks = 64;
