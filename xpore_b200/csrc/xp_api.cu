@@ -789,7 +789,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         // sizes grow by kChunkGrowth from an eighth of a full chunk: the copy is only ~1.2x faster than the fit, so
         // a chunk that is much larger than its predecessor would leave the SMs waiting for it to arrive
         // (chained form: tails and small launches cost nothing there, so the chunks are small - they only set the
-        // latency between the arrival of a read and its fit - and double from a quarter chunk)
+        // latency between the arrival of a read and its fit - and double from a sixteenth of a chunk)
         size_t sz = std::max<size_t>(chunk_bytes / (chain ? (size_t)std::max(1, exp_int("XPB200_CHAIN_FIRST_DIV", 16)) : 8), 1u << 20);
         const double growth = chain ? 2.0 : std::max(1.0, exp_int("XPB200_CHUNK_GROWTH_PCT", kChunkGrowthPct) / 100.0);
         // chained form: the last chunks halve again (down to 1 / kChainLastDiv of a chunk).  What is left to do when the
