@@ -103,13 +103,47 @@ constexpr int kStreamWarps = 16;  // warps of a streaming team (one CTA, one pos
 
 int exp_int(const char* name, int dflt);
 
+// Shared-memory opt-in, occupancy and register count of a kernel at a launch shape, remembered per device: the chunked
+// host calls ask for the same few shapes once per chunk, and the three runtime calls cost the enqueueing thread tens of
+// microseconds each time - at the start of a call that is time the SMs spend waiting for their first launches.  (The
+// opt-in is set to the full 227 KB once per kernel, so a later, larger shape of the same kernel needs no second call.)
+struct PrepKey {
+    int dev;
+    const void* fn;
+    int threads;
+    size_t smem;
+    bool operator<(const PrepKey& o) const {
+        if (dev != o.dev) return dev < o.dev;
+        if (fn != o.fn) return fn < o.fn;
+        if (threads != o.threads) return threads < o.threads;
+        return smem < o.smem;
+    }
+};
+std::mutex g_prep_mu;
+std::map<PrepKey, std::pair<int, int>> g_prep;      // -> {CTAs per SM, registers per thread}
+std::map<std::pair<int, const void*>, bool> g_optin;  // kernels whose dynamic shared memory limit is raised
 template <class K>
 int prepare_kernel_fn(K* k, Geometry* g) {
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem));
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    const PrepKey key{dev, reinterpret_cast<const void*>(k), g->threads, g->smem};
+    std::lock_guard<std::mutex> lk(g_prep_mu);
+    auto it = g_prep.find(key);
+    if (it != g_prep.end()) {
+        g->ctas_per_sm = it->second.first;
+        g->regs = it->second.second;
+        return 0;
+    }
+    bool& opted = g_optin[std::make_pair(dev, key.fn)];
+    if (!opted) {
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemPerCta));
+        opted = true;
+    }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g->ctas_per_sm, k, g->threads, g->smem));
     cudaFuncAttributes fa;
     CK(cudaFuncGetAttributes(&fa, k));
     g->regs = fa.numRegs;
+    g_prep[key] = std::make_pair(g->ctas_per_sm, g->regs);
     return 0;
 }
 template <int TW, int MAXT, bool STREAM = false>
@@ -935,6 +969,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         CK(cudaEventRecord(dc->e_zero, dc->s_in));
         CK(cudaStreamWaitEvent(dc->s_fit, dc->e_zero, 0));
     }
+    double host_enq[kMaxChunks] = {0.0};  // XPB200_TRACE: when the host had enqueued the chunk (ms since entry)
     int meta_next = 0;
     const size_t chain_meta_bytes = (size_t)std::max(1, exp_int("XPB200_CHAIN_META_MB", 128)) << 20;  // reads per group of small-array copies
     for (int c = 0; chain && c < nchunks; ++c) {
@@ -944,7 +979,8 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
             // the small arrays (offsets, group lengths, priors: 6 % of the bytes) go up for several chunks at once, in front
             // of the first one's reads: four more copies per chunk cost the copy engine ~25 us of gaps each time
             int ce = c;
-            while (ce < nchunks && (ce == c || (size_t)(roff[cut[ce + 1]] - roff[cut[c]]) * eb <= chain_meta_bytes)) ++ce;
+            const size_t group_bytes = c == 0 ? chain_meta_bytes / 8 : chain_meta_bytes;  // the first group small: it is in front of the first reads
+            while (ce < nchunks && (ce == c || (size_t)(roff[cut[ce + 1]] - roff[cut[c]]) * eb <= group_bytes)) ++ce;
             const int q0 = cut[c], qc = cut[ce] - cut[c];
             CKB(cudaMemcpyAsync(d_off + q0, roff + q0, (size_t)(qc + 1) * 8, cudaMemcpyDefault, dc->s_in));
             CKB(cudaMemcpyAsync(d_glen + (size_t)q0 * G, b->grp_len + (size_t)q0 * G, (size_t)qc * G * 4, cudaMemcpyDefault, dc->s_in));
@@ -983,6 +1019,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         if (chain_two_class) CKB(cudaMemcpyAsync(d_nl + c, carve(d + o_ws[c]).n_large, 4, cudaMemcpyDeviceToDevice, sc));
         CKB(cudaMemsetAsync(d_ready + c, 0x01, 4, sc));
         CKB(cudaEventRecord(dc->e_cls[c], sc));
+        if (trace) host_enq[c] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
         if (trace) CKB(cudaEventRecord(dc->t_done[c], sc));
         if (c == 0) {  // the chained launch, as soon as the first chunk is on its way
             xpk::FitArgs& fa = chain_fa;
@@ -1202,8 +1239,8 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
                 cudaEventElapsedTime(&a, dc->t_0, dc->t_in[c]);
                 cudaEventElapsedTime(&s2, dc->t_0, dc->t_start[c]);
                 cudaEventElapsedTime(&e, dc->t_0, dc->t_done[c]);
-                fprintf(stderr, "[xpb200 trace] chunk %2d: %8d positions %7.1f MB  copied %7.3f  select %7.3f .. %7.3f ms  fitted %u  polls waiting %u\n", c,
-                        cut[c + 1] - cut[c], (double)(roff[cut[c + 1]] - roff[cut[c]]) * eb / 1048576.0, a, s2, e, nf[c], polls[c]);
+                fprintf(stderr, "[xpb200 trace] chunk %2d: %8d positions %7.1f MB  copied %7.3f  select %7.3f .. %7.3f ms  fitted %u  polls waiting %u  host enqueued %.3f\n", c,
+                        cut[c + 1] - cut[c], (double)(roff[cut[c + 1]] - roff[cut[c]]) * eb / 1048576.0, a, s2, e, nf[c], polls[c], host_enq[c]);
             }
         }
         return 0;
