@@ -552,7 +552,12 @@ def test_chained_host_pipeline(torch_cuda):
     assert 5 < team.sum() < 0.01 * batch.n_positions and n.max() < 1024
     keep = np.nonzero(dense.keep_row)[0]
     assert team[keep].any()
+    # the device arena of the host calls is reused from call to call: leave another batch of the same shape in it, so that
+    # anything the persistent launch read too early (a chunk's offsets or status before they had arrived) would differ
+    other = batch.subset(np.random.default_rng(5).permutation(batch.n_positions))
+    assert other.encode_reads() == 2
     for claim in (None, 560, 300):  # the truth; below the class split; far below
+        xf.fit_rows(other, method)
         rows, n_fitted = xf.fit_rows(batch, method, max_reads=claim)
         assert n_fitted == dense.n_fitted
         idx, status, n_iter, pval, fit, stats = unpack_records(rows, xf.fit_width(6), xf.stats_width(6, 2))

@@ -87,6 +87,14 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Load of an input array in the chained launch: the launch lives through the arrival of later chunks, whose offsets, group
+// lengths, priors and prefilter status land in the same arrays - and in the same 32-byte sectors as the last positions of
+// the chunk before, which this SM may have read (and its L1 kept) before they arrived.  L1 is coherent only at launch
+// boundaries, so these loads go to L2 (ld.global.cg).  A plain launch reads arrays that were complete before it started.
+template <bool CG, class T>
+__device__ __forceinline__ T ld_in(const T* p) {
+    return CG ? __ldcg(p) : *p;
+}
 __device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // one double of this thread's lane (two columns); the data are in the register when the statement is done
@@ -233,18 +241,18 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_tm_kernel(FitArgs a, FitChain 
                     cc = __shfl_sync(kFull, cc, 0);
                     if (cc >= ch.n) break;
                     w = __shfl_sync(kFull, w, 0);
-                    p = ch.c[cc].worklist[w] + ch.c[cc].p0;
+                    p = __ldcg(ch.c[cc].worklist + w) + ch.c[cc].p0;
                 } else {
                     if (lane == 0) w = atomicAdd(a.ticket, 1u);
                     w = __shfl_sync(kFull, w, 0) + w_begin;
                     if (w >= w_end) break;
                     p = a.worklist ? a.worklist[w] : (int)w;
                 }
-                off = a.read_off[p];
-                n = (int)(a.read_off[p + 1] - off);
+                off = ld_in<CHAIN>(reinterpret_cast<const long long*>(a.read_off) + p);
+                n = (int)(ld_in<CHAIN>(reinterpret_cast<const long long*>(a.read_off) + p + 1) - off);
                 if (n > a.cap || n <= 0) {  // only when the caller understated batch.max_reads
                     if (lane == 0) {
-                        a.status[p] = (a.status[p] & (STATUS_TTEST_VALID | STATUS_NEAR_THRESHOLD)) | STATUS_SELECTED | STATUS_NOT_FITTED;
+                        a.status[p] = (ld_in<CHAIN>(a.status + p) & (STATUS_TTEST_VALID | STATUS_NEAR_THRESHOLD)) | STATUS_SELECTED | STATUS_NOT_FITTED;
                         a.n_iter[p] = -1;
                         if (CHAIN) {
                             __threadfence();
@@ -270,12 +278,12 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_tm_kernel(FitArgs a, FitChain 
                 mbar_expect_tx(mbar, bytes);
                 tma_bulk_g2s(stage, reinterpret_cast<const char*>(a.y) + (off - sh) * 2, bytes, mbar);
             }
-            const double m0 = a.kmer_mean[p];
-            const double sd = a.kmer_std[p];
+            const double m0 = ld_in<CHAIN>(a.kmer_mean + p);
+            const double sd = ld_in<CHAIN>(a.kmer_std + p);
             const double tau = 1.0 / (sd * sd);   // diffmod.py:24
             const double a0 = tau;                // diffmod.py:40
             const double b0 = 0.5 * (1.0 / tau);  // diffmod.py:41
-            for (int g = lane; g < G; g += 32) goff[g + 1] = a.grp_len[(size_t)p * G + g];
+            for (int g = lane; g < G; g += 32) goff[g + 1] = ld_in<CHAIN>(a.grp_len + (size_t)p * G + g);
             __syncwarp();
             if (lane == 0) {
                 int acc = 0;
@@ -518,7 +526,7 @@ __global__ void __launch_bounds__(MAXT, 1) xp_fit_tm_kernel(FitArgs a, FitChain 
                 if (sl == 0) {
                     out[FIT_ELBO] = elbo;
                     a.n_iter[p_s] = it;
-                    a.status[p_s] = (a.status[p_s] & (STATUS_TTEST_VALID | STATUS_NEAR_THRESHOLD)) | st;
+                    a.status[p_s] = (ld_in<CHAIN>(a.status + p_s) & (STATUS_TTEST_VALID | STATUS_NEAR_THRESHOLD)) | st;
                 }
                 for (int s = sl; s < 2 * G; s += LP) {
                     const int g = s >> 1;
