@@ -641,6 +641,8 @@ struct DevCache {
     cudaStream_t s_post[kComputeStreams] = {nullptr, nullptr, nullptr}, s_poll = nullptr;  // chained form: statistics / rows of finished chunks, progress polls
     cudaEvent_t e_cls[kMaxChunks];                   // a chunk's select phase and class launches are enqueued / done
     uint32_t* h_poll = nullptr;                      // page-locked: the flag words, then n_fitted and the row count of every chunk
+    bool chain_off = false;  // a chained launch timed out waiting for a chunk (kernels serialised by a profiler, SMs held by
+                             // somebody else): this process stays with chunk-by-chunk launches on this device
     cudaEvent_t e_sel[kComputeStreams] = {nullptr, nullptr, nullptr}, e_help = nullptr;
     cudaEvent_t e_zero = nullptr, e_fit = nullptr;   // its flags are cleared / it is done
     cudaEvent_t e_call = nullptr;  // end of the previous call's device work (the arena is reused by the next one)
@@ -735,7 +737,7 @@ namespace {
 // first, small chunks: c2 took 18.3 ms end to end against 14.1 ms resident, the copy alone 14.2 ms.
 constexpr int kChainFreeSms = 6;
 constexpr size_t kChainChunkBytes = 32u << 20;
-constexpr unsigned kChainSpinLimit = 1500000u;  // polls of a warp waiting for a chunk (4 us each: >= 6 s) before it gives up
+constexpr unsigned kChainSpinLimit = 500000u;  // polls of a warp waiting for a chunk (4 us each: >= 2 s) before it gives up
 
 int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m, const HostOut& ho, bool allow_chain) {
     const xpb200_result* r = ho.dense;
@@ -790,7 +792,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     Geometry gch;
     FitKernelFn chain_fn = nullptr;
     int chain_npw = 0;
-    if (allow_chain && want_rows && b->y_format == XPB200_Y_U16 && b->max_reads > 0 &&
+    if (allow_chain && !dc->chain_off && want_rows && b->y_format == XPB200_Y_U16 && b->max_reads > 0 &&
         exp_int("XPB200_TM", 1) != 0 && exp_int("XPB200_CHAIN", 1) != 0 && total_bytes >= (8u << 20)) {
         chain_npw = tm_positions_per_warp(G, b->max_reads);
         // the chained launch is the single-warp class's; the chunks' team / streaming classes keep their own launches,
@@ -1144,6 +1146,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
                 if (!progressed) std::this_thread::sleep_for(std::chrono::microseconds(20));
             }
             if (failed) {  // a warp gave up waiting for a chunk (the free SMs were not free?): chunk by chunk, then
+                dc->chain_off = true;
                 chain_bail(0);
                 CK(cudaEventRecord(dc->e_call, dc->s_out));
                 return fit_host_impl(device, b, m, ho, false);
@@ -1211,6 +1214,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         CK(cudaStreamSynchronize(dc->s_in));
         CK(cudaStreamSynchronize(dc->s_fit));
         if (tail[1] != 0u) {  // a warp gave up waiting for a chunk (the free SMs were not free?): chunk by chunk, then
+            dc->chain_off = true;
             CK(cudaEventRecord(dc->e_call, dc->s_out));
             return fit_host_impl(device, b, m, ho, false);
         }
