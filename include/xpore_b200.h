@@ -207,6 +207,12 @@ int32_t xpb200_fit_launch_info(int32_t device, int32_t n_groups, int32_t max_rea
  * every sweep) instead of being held in shared memory; depends on the number of group slots only. */
 int32_t xpb200_deep_split(int32_t n_groups);
 
+/* How the host entry points cut a batch into chunks of positions (no GPU needed): cuts[0] = 0 < cuts[1] < ... <
+ * cuts[n] = n_positions, n returned (XPB200_EINVAL when `capacity` < n + 1 entries).  elem_bytes = 8 / 4 / 2 for the f64 /
+ * i32 / u16 read formats; chained != 0: the plan of the chained form. */
+int32_t xpb200_host_chunk_plan(const int64_t* read_off, int32_t n_positions, int32_t elem_bytes, int32_t chained,
+                               int32_t* cuts, int32_t capacity);
+
 /* Kernel launches issued by this library in the calling thread since load (bench.py's gpu_launches). */
 uint64_t xpb200_launch_count(void);
 

@@ -56,6 +56,43 @@ def test_argument_validation_without_gpu(library):
     assert rc == -1 and b"n_groups" in library.xpb200_last_error()
 
 
+def test_host_chunk_plan(library):
+    """Chunk plans of the host entry points (xp_api.cu:plan_chunks): boundaries strictly ascending from 0 to P, at most 64
+    chunks whatever the batch size, chunk-by-chunk sizes growing to 112 MB, chained sizes doubling from 2 MB to 32 MB and
+    halving again at the end; small batches are one chunk."""
+    import numpy as np
+    L = library
+    L.xpb200_host_chunk_plan.restype = C.c_int32
+    L.xpb200_host_chunk_plan.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
+
+    def plan(n_reads_per_pos, eb, chained):
+        off = np.zeros(len(n_reads_per_pos) + 1, dtype=np.int64)
+        np.cumsum(n_reads_per_pos, out=off[1:])
+        cuts = np.zeros(80, dtype=np.int32)
+        n = L.xpb200_host_chunk_plan(off.ctypes.data, len(n_reads_per_pos), eb, chained, cuts.ctypes.data, len(cuts))
+        assert n >= 1, L.xpb200_last_error()
+        c = cuts[:n + 1]
+        assert c[0] == 0 and c[-1] == len(n_reads_per_pos) and (np.diff(c) > 0).all() and n <= 64
+        return off[c[1:]] * eb - off[c[:-1]] * eb  # bytes of reads per chunk
+
+    rng = np.random.default_rng(0)
+    c2 = rng.integers(120, 601, size=1_000_000)  # c2 shape: 0.72 GB of u16 reads
+    by = plan(c2, 2, 0)
+    assert 8 <= len(by) <= 12 and by.max() <= (112 << 20) + 4096 and by[0] < 16 << 20 and (np.diff(by[:-1]) >= -4096).all()
+    ch = plan(c2, 2, 1)
+    mb = ch / 2**20
+    assert 24 <= len(ch) <= 32 and mb[0] < 2.1 and mb.max() < 32.1
+    assert (np.diff(mb[:5]) > 0).all() and (np.diff(mb[-3:]) < 0).all() and mb[-1] < 4.1
+    assert len(plan(rng.integers(120, 601, size=2000), 2, 1)) == 1  # 1.4 MB: one chunk
+    assert len(plan(rng.integers(120, 601, size=2000), 8, 0)) == 1
+    big = plan(np.full(3_000_000, 1500), 2, 1)  # 9 GB of reads: still inside the chain table
+    assert len(big) <= 64 and big.max() < 9e9 / 40
+    off = np.arange(0, 2_000_001 * 360, 360, dtype=np.int64)  # too few entries for the boundaries: an error, not an overrun
+    cuts = np.zeros(3, dtype=np.int32)
+    assert L.xpb200_host_chunk_plan(off.ctypes.data, 2_000_000, 2, 1, cuts.ctypes.data, 3) == -1
+    assert b"cuts holds fewer" in L.xpb200_last_error()
+
+
 def test_no_cpu_fallback_in_product():
     """The product package must not import the oracle or the emulator."""
     pkg = os.path.join(REPO, "xpore_b200")

@@ -44,7 +44,7 @@ class XpLaunchInfo(C.Structure):
 
 EXPORTS = ["xpb200_fit_width", "xpb200_stats_width", "xpb200_workspace_bytes", "xpb200_fit_device",
            "xpb200_fit_host", "xpb200_fit_host_rows", "xpb200_fit_host_rows_async", "xpb200_pack_rows", "xpb200_release", "xpb200_prefilter_device", "xpb200_stats_device",
-           "xpb200_posterior_device", "xpb200_fit_launch_info", "xpb200_deep_split", "xpb200_launch_count", "xpb200_measure_fp64_peak", "xpb200_eval_special",
+           "xpb200_posterior_device", "xpb200_fit_launch_info", "xpb200_deep_split", "xpb200_host_chunk_plan", "xpb200_launch_count", "xpb200_measure_fp64_peak", "xpb200_eval_special",
            "xpb200_set_stage_timing", "xpb200_get_stage_ms", "xpb200_pack_records",
            "xpb200_debug_fill_smem", "xpb200_last_error", "xpb200_version",
            "xpb200_ingest_open", "xpb200_ingest_genes", "xpb200_ingest_copy", "xpb200_ingest_close",

@@ -739,6 +739,50 @@ constexpr int kChainFreeSms = 6;
 constexpr size_t kChainChunkBytes = 32u << 20;
 constexpr unsigned kChainSpinLimit = 500000u;  // polls of a warp waiting for a chunk (4 us each: >= 2 s) before it gives up
 
+// Chunk boundaries (positions) of a host call, cut where the read offsets cross the byte targets.
+//   chunk by chunk: sizes grow by kChunkGrowthPct from an eighth of a full chunk (112 MB) - the copy is only ~1.2x faster
+//     than the fit, so a chunk much larger than its predecessor would leave the SMs waiting for it to arrive; a remainder
+//     of less than a quarter chunk joins the last one;
+//   chained form: tails and small launches cost nothing there, so the chunks are small (32 MB; more for batches beyond
+//     ~1.5 GB, the chain table holds kMaxChunks) - they only set the latency between the arrival of a read and its fit -
+//     and double from a sixteenth of a chunk; the last ones halve again down to an eighth: what is left to do when the last
+//     read has arrived is the last chunk plus the long positions of the late chunks, and a small chunk holds fewer of both.
+std::vector<int> plan_chunks(const int64_t* roff, int P, size_t eb, bool chain) {
+    const size_t total_bytes = (size_t)roff[P] * eb;
+    const size_t chunk_cap = chain ? std::max(kChainChunkBytes, total_bytes / (size_t)(kMaxChunks - 16)) : kChunkBytes;
+    const size_t chunk_bytes = (size_t)std::max(1, exp_int(chain ? "XPB200_CHAIN_CHUNK_MB" : "XPB200_CHUNK_MB", (int)(chunk_cap >> 20))) << 20;
+    std::vector<int> cut(1, 0);
+    std::vector<size_t> ends;  // byte targets of the chunk ends
+    size_t pos = 0;
+    size_t sz = std::max<size_t>(chunk_bytes / (chain ? (size_t)std::max(1, exp_int("XPB200_CHAIN_FIRST_DIV", 16)) : 8), 1u << 20);
+    const double growth = chain ? 2.0 : std::max(1.0, exp_int("XPB200_CHUNK_GROWTH_PCT", kChunkGrowthPct) / 100.0);
+    const int last_div = chain ? std::max(1, exp_int("XPB200_CHAIN_LAST_DIV", 8)) : 1;
+    size_t tail_bytes = 0;
+    for (int dv = 2; dv <= last_div; dv *= 2) tail_bytes += chunk_bytes / dv;
+    if (tail_bytes * 3 > total_bytes) tail_bytes = 0;
+    const size_t body_bytes = total_bytes - tail_bytes;
+    while (pos + sz + sz / 4 < body_bytes && (int)ends.size() < kMaxChunks - 8) {
+        pos += sz;
+        ends.push_back(pos);
+        sz = std::min(chunk_bytes, (size_t)((double)sz * growth));
+    }
+    if (tail_bytes) {
+        pos = body_bytes;
+        for (int dv = 2; dv <= last_div; dv *= 2) {
+            ends.push_back(pos);
+            pos += chunk_bytes / dv;
+        }
+    }
+    for (size_t e : ends) {
+        const int64_t target = (int64_t)(e / eb);
+        int p = (int)(std::lower_bound(roff, roff + P + 1, target) - roff);
+        p = std::min(std::max(p, cut.back()), P);
+        if (p > cut.back() && p < P) cut.push_back(p);
+    }
+    cut.push_back(P);
+    return cut;
+}
+
 int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m, const HostOut& ho, bool allow_chain) {
     const xpb200_result* r = ho.dense;
     double* rows = ho.rows;
@@ -816,46 +860,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     const bool chain = chain_fn != nullptr;
     const bool chain_two_class = chain && b->max_reads >= tm_class_split(chain_npw);  // chunks have a team class of their own
     const int chain_free_sms = std::max(1, exp_int("XPB200_CHAIN_FREE_SMS", kChainFreeSms));
-    const size_t chunk_cap = chain ? std::max(kChainChunkBytes, total_bytes / (size_t)(kMaxChunks - 16)) : kChunkBytes;
-    const size_t chunk_bytes = (size_t)std::max(1, exp_int(chain ? "XPB200_CHAIN_CHUNK_MB" : "XPB200_CHUNK_MB", (int)(chunk_cap >> 20))) << 20;
-    std::vector<int> cut(1, 0);
-    {
-        std::vector<size_t> ends;  // byte targets of the chunk ends
-        size_t pos = 0;
-        // sizes grow by kChunkGrowth from an eighth of a full chunk: the copy is only ~1.2x faster than the fit, so
-        // a chunk that is much larger than its predecessor would leave the SMs waiting for it to arrive
-        // (chained form: tails and small launches cost nothing there, so the chunks are small - they only set the
-        // latency between the arrival of a read and its fit - and double from a sixteenth of a chunk)
-        size_t sz = std::max<size_t>(chunk_bytes / (chain ? (size_t)std::max(1, exp_int("XPB200_CHAIN_FIRST_DIV", 16)) : 8), 1u << 20);
-        const double growth = chain ? 2.0 : std::max(1.0, exp_int("XPB200_CHUNK_GROWTH_PCT", kChunkGrowthPct) / 100.0);
-        // chained form: the last chunks halve again (down to 1 / kChainLastDiv of a chunk).  What is left to do when the
-        // last read has arrived is the last chunk plus the longest position of the late chunks (300 sweeps take over a
-        // millisecond), and a chunk of an eighth holds fewer of both
-        const int last_div = chain ? std::max(1, exp_int("XPB200_CHAIN_LAST_DIV", 8)) : 1;
-        size_t tail_bytes = 0;
-        for (int dv = 2; dv <= last_div; dv *= 2) tail_bytes += chunk_bytes / dv;
-        if (tail_bytes * 3 > total_bytes) tail_bytes = 0;
-        const size_t body_bytes = total_bytes - tail_bytes;
-        while (pos + sz + sz / 4 < body_bytes && (int)ends.size() < kMaxChunks - 8) {
-            pos += sz;
-            ends.push_back(pos);
-            sz = std::min(chunk_bytes, (size_t)((double)sz * growth));
-        }
-        if (tail_bytes) {
-            pos = body_bytes;
-            for (int dv = 2; dv <= last_div; dv *= 2) {
-                ends.push_back(pos);
-                pos += chunk_bytes / dv;
-            }
-        }
-        for (size_t e : ends) {
-            const int64_t target = (int64_t)(e / eb);
-            int p = (int)(std::lower_bound(roff, roff + P + 1, target) - roff);
-            p = std::min(std::max(p, cut.back()), P);
-            if (p > cut.back() && p < P) cut.push_back(p);
-        }
-        cut.push_back(P);
-    }
+    const std::vector<int> cut = plan_chunks(roff, P, eb, chain);
     const int nchunks = (int)cut.size() - 1;
     ++dc->calls;
     const bool trace = exp_int("XPB200_TRACE", 0) != 0 && !async;  // experiment builds: timed events per chunk, printed to stderr
@@ -1370,6 +1375,16 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     return 0;
 }
 }  // namespace
+
+int32_t xpb200_host_chunk_plan(const int64_t* read_off, int32_t n_positions, int32_t elem_bytes, int32_t chained,
+                               int32_t* cuts, int32_t capacity) {
+    if (!read_off || !cuts || n_positions < 0 || (elem_bytes != 2 && elem_bytes != 4 && elem_bytes != 8))
+        return fail(XPB200_EINVAL, "bad arguments");
+    const std::vector<int> cut = plan_chunks(read_off, n_positions, (size_t)elem_bytes, chained != 0);
+    if ((int)cut.size() > capacity) return fail(XPB200_EINVAL, "cuts holds fewer than " + std::to_string(cut.size()) + " entries");
+    for (size_t i = 0; i < cut.size(); ++i) cuts[i] = cut[i];
+    return (int32_t)cut.size() - 1;
+}
 
 void xpb200_release(void) {
     std::lock_guard<std::recursive_mutex> lk(g_cache_mu);
