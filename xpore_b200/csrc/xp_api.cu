@@ -783,14 +783,62 @@ std::vector<int> plan_chunks(const int64_t* roff, int P, size_t eb, bool chain) 
     return cut;
 }
 
-int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m, const HostOut& ho, bool allow_chain) {
-    const xpb200_result* r = ho.dense;
-    double* rows = ho.rows;
-    const bool want_rows = ho.rows != nullptr || ho.rows_dev != nullptr;
-    const bool async = ho.rows_dev != nullptr;
-    CK(cudaSetDevice(device));
-    std::lock_guard<std::recursive_mutex> lk(g_cache_mu);
+// One call of a host entry point: what its two forms - chained and chunk by chunk - share (the chunks, the device arena).
+struct HostCall {
+    // chained form: ready[c], the abort flag, polls spent waiting (experiment builds), positions done, size of the team / streaming classes
+    static constexpr int kFlagWords = 4 * kMaxChunks + 1;
+    const int32_t device;
+    const xpb200_batch* const b;
+    const xpb200_method* const m;
+    const HostOut& ho;
     DevCache* dc = nullptr;
+    const xpb200_result* const r;  // dense results wanted (host or device memory), else null
+    double* const rows;            // rows wanted in host memory, else null
+    const bool want_rows, async;
+    const int P, G, C, FW, SW;
+    int RW = 0;
+    const size_t eb;
+    const int64_t* const roff;
+    const size_t total_bytes;
+    // the chained form, when it applies
+    Geometry gch;
+    FitKernelFn chain_fn = nullptr;
+    int chain_npw = 0;
+    bool chain = false, chain_two_class = false;
+    int chain_free_sms = kChainFreeSms;
+    // chunks, streams, tracing
+    std::vector<int> cut;
+    int nchunks = 0, n_streams = kComputeStreams;
+    bool trace = false;
+    std::chrono::steady_clock::time_point host_t0;
+    // device arena: offsets and pointers
+    size_t o_y = 0, o_off = 0, o_glen = 0, o_km = 0, o_ks = 0, o_gc = 0, o_status = 0, o_niter = 0, o_pval = 0, o_fit = 0, o_stats = 0,
+           o_flags = 0, o_nf = 0, o_nr = 0, o_cnt = 0, o_rows = 0;
+    std::vector<size_t> o_ws;
+    char *d = nullptr, *d_y = nullptr;
+    int64_t* d_off = nullptr;
+    int32_t *d_glen = nullptr, *d_niter = nullptr;
+    double *d_km = nullptr, *d_ks = nullptr, *d_pval = nullptr, *d_fit = nullptr, *d_stats = nullptr, *d_rows = nullptr;
+    uint32_t *d_status = nullptr, *d_ready = nullptr, *d_abort = nullptr, *d_done = nullptr, *d_nl = nullptr, *d_nf = nullptr, *d_nr = nullptr,
+             *d_cnt = nullptr;
+
+    HostCall(int32_t device_, const xpb200_batch* b_, const xpb200_method* m_, const HostOut& ho_)
+        : device(device_), b(b_), m(m_), ho(ho_), r(ho_.dense), rows(ho_.rows),
+          want_rows(ho_.rows != nullptr || ho_.rows_dev != nullptr), async(ho_.rows_dev != nullptr),
+          P(b_->n_positions), G(b_->n_groups), C(b_->n_conditions), FW(xpc::fit_width(b_->n_groups)),
+          SW(xpc::stats_width(b_->n_groups, b_->n_conditions)),
+          eb(b_->y_format == XPB200_Y_F64 ? 8 : (b_->y_format == XPB200_Y_I32 ? 4 : 2)), roff(b_->read_off),
+          total_bytes((size_t)b_->n_reads * (b_->y_format == XPB200_Y_F64 ? 8 : (b_->y_format == XPB200_Y_I32 ? 4 : 2))) {}
+
+    int open_cache();                    // the device's streams, events and arena (created at the first call)
+    int decide_chain(bool allow_chain);  // chained form?
+    int lay_out();                       // arena offsets, (re)allocation, pointers
+    int begin();                         // ordering against the previous call / the caller's stream, the first copies
+    int chained();
+    int chunked();
+};
+
+int HostCall::open_cache() {
     for (auto* c : g_cache)
         if (c->device == device) dc = c;
     if (!dc) {
@@ -817,25 +865,14 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         CK(cudaEventCreateWithFlags(&dc->e_fit, cudaEventDisableTiming));
         g_cache.push_back(dc);
     }
-    const int P = b->n_positions, G = b->n_groups, C = b->n_conditions;
-    if (ho.n_fitted) *ho.n_fitted = 0;
-    if (ho.n_rows) *ho.n_rows = 0;
-    if (P == 0) {
-        if (async) CK(cudaMemsetAsync(ho.counts_dev, 0, 8, ho.user_stream));
-        return 0;
-    }
-    const size_t eb = b->y_format == XPB200_Y_F64 ? 8 : (b->y_format == XPB200_Y_I32 ? 4 : 2);
-    const int FW = xpc::fit_width(G), SW = xpc::stats_width(G, C);
+    return 0;
+}
 
-    // chunk boundaries (positions), cut where the read offsets cross the chunk targets.  The first chunks are
-    // small so the SMs start early; a remainder of less than a quarter chunk joins the last one.
-    const int64_t* roff = b->read_off;
-    const size_t total_bytes = (size_t)b->n_reads * eb;
+// Chained form?  Decided on the caller's max_reads (checked chunk by chunk: an understated one aborts the chained launch
+// and the call starts over chunk by chunk).
+int HostCall::decide_chain(bool allow_chain) {
     // chained form?  decided on the caller's max_reads (checked chunk by chunk below: an understated one aborts the
     // chained launch and the call starts over chunk by chunk)
-    Geometry gch;
-    FitKernelFn chain_fn = nullptr;
-    int chain_npw = 0;
     if (allow_chain && !dc->chain_off && want_rows && b->y_format == XPB200_Y_U16 && b->max_reads > 0 &&
         exp_int("XPB200_TM", 1) != 0 && exp_int("XPB200_CHAIN", 1) != 0 && total_bytes >= (8u << 20)) {
         chain_npw = tm_positions_per_warp(G, b->max_reads);
@@ -857,46 +894,32 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
             if (gch.ctas_per_sm < 1 || gch.sms <= 2 * kChainFreeSms) chain_fn = nullptr;
         }
     }
-    const bool chain = chain_fn != nullptr;
-    const bool chain_two_class = chain && b->max_reads >= tm_class_split(chain_npw);  // chunks have a team class of their own
-    const int chain_free_sms = std::max(1, exp_int("XPB200_CHAIN_FREE_SMS", kChainFreeSms));
-    const std::vector<int> cut = plan_chunks(roff, P, eb, chain);
-    const int nchunks = (int)cut.size() - 1;
-    ++dc->calls;
-    const bool trace = exp_int("XPB200_TRACE", 0) != 0 && !async;  // experiment builds: timed events per chunk, printed to stderr
-    if (trace && !dc->t_0) {
-        CK(cudaEventCreate(&dc->t_0));
-        for (int i = 0; i < kMaxChunks; ++i) {
-            CK(cudaEventCreate(&dc->t_in[i]));
-            CK(cudaEventCreate(&dc->t_start[i]));
-            CK(cudaEventCreate(&dc->t_done[i]));
-        }
-    }
-    const auto host_t0 = std::chrono::steady_clock::now();
-    const int n_streams = std::min(kComputeStreams, std::max(1, exp_int("XPB200_STREAMS", 3)));
+    chain = chain_fn != nullptr;
+    chain_two_class = chain && b->max_reads >= tm_class_split(chain_npw);  // chunks have a team class of their own
+    chain_free_sms = std::max(1, exp_int("XPB200_CHAIN_FREE_SMS", kChainFreeSms));
+    return 0;
+}
 
-    // device layout
+int HostCall::lay_out() {
     size_t o = 0;
-    const size_t o_y = o; o += align_up((size_t)b->n_reads * eb + 64);
-    const size_t o_off = o; o += align_up((size_t)(P + 1) * 8);
-    const size_t o_glen = o; o += align_up((size_t)P * G * 4);
-    const size_t o_km = o; o += align_up((size_t)P * 8);
-    const size_t o_ks = o; o += align_up((size_t)P * 8);
-    const size_t o_gc = o; o += align_up((size_t)G * 4);
-    const size_t o_status = o; o += align_up((size_t)P * 4);
-    const size_t o_niter = o; o += align_up((size_t)P * 4);
-    const size_t o_pval = o; o += align_up((size_t)P * 8);
-    const size_t o_fit = o; o += align_up((size_t)P * FW * 8);
-    const size_t o_stats = o; o += align_up((size_t)P * SW * 8);
-    // chained form: ready[c], the abort flag, polls spent waiting (experiment builds), positions done, size of the team / streaming classes
-    constexpr int kFlagWords = 4 * kMaxChunks + 1;
-    const size_t o_flags = o; o += align_up((size_t)kFlagWords * 4);
-    const size_t o_nf = o; o += align_up((size_t)kMaxChunks * 4);
-    const size_t o_nr = o; o += align_up((size_t)kMaxChunks * 4);
-    const size_t o_cnt = o; o += want_rows ? align_up((size_t)kMaxChunks * kPackWarps * 4) : 0;
-    const int RW = 4 + FW + SW;  // record width
-    const size_t o_rows = o; o += want_rows ? align_up((size_t)P * RW * 8) : 0;  // chunk c's rows start at row cut[c]
-    std::vector<size_t> o_ws(nchunks);
+    o_y = o; o += align_up((size_t)b->n_reads * eb + 64);
+    o_off = o; o += align_up((size_t)(P + 1) * 8);
+    o_glen = o; o += align_up((size_t)P * G * 4);
+    o_km = o; o += align_up((size_t)P * 8);
+    o_ks = o; o += align_up((size_t)P * 8);
+    o_gc = o; o += align_up((size_t)G * 4);
+    o_status = o; o += align_up((size_t)P * 4);
+    o_niter = o; o += align_up((size_t)P * 4);
+    o_pval = o; o += align_up((size_t)P * 8);
+    o_fit = o; o += align_up((size_t)P * FW * 8);
+    o_stats = o; o += align_up((size_t)P * SW * 8);
+    o_flags = o; o += align_up((size_t)kFlagWords * 4);
+    o_nf = o; o += align_up((size_t)kMaxChunks * 4);
+    o_nr = o; o += align_up((size_t)kMaxChunks * 4);
+    o_cnt = o; o += want_rows ? align_up((size_t)kMaxChunks * kPackWarps * 4) : 0;
+    RW = 4 + FW + SW;  // record width
+    o_rows = o; o += want_rows ? align_up((size_t)P * RW * 8) : 0;  // chunk c's rows start at row cut[c]
+    o_ws.assign(nchunks, 0);
     for (int c = 0; c < nchunks; ++c) {
         o_ws[c] = o;
         o += align_up(xpb200_workspace_bytes(cut[c + 1] - cut[c]));
@@ -913,26 +936,30 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         }
         dc->cap = want;
     }
-    char* d = reinterpret_cast<char*>(dc->buf);
-    char* d_y = d + o_y;
-    int64_t* d_off = (int64_t*)(d + o_off);
-    int32_t* d_glen = (int32_t*)(d + o_glen);
-    double* d_km = (double*)(d + o_km);
-    double* d_ks = (double*)(d + o_ks);
-    uint32_t* d_status = (uint32_t*)(d + o_status);
-    int32_t* d_niter = (int32_t*)(d + o_niter);
-    double* d_pval = (double*)(d + o_pval);
-    double* d_fit = (double*)(d + o_fit);
-    double* d_stats = (double*)(d + o_stats);
-    uint32_t* d_ready = (uint32_t*)(d + o_flags);
-    uint32_t* d_abort = d_ready + kMaxChunks;
-    uint32_t* d_done = d_abort + 1 + kMaxChunks;
-    uint32_t* d_nl = d_done + kMaxChunks;
-    uint32_t* d_nf = (uint32_t*)(d + o_nf);
-    uint32_t* d_nr = (uint32_t*)(d + o_nr);
-    uint32_t* d_cnt = (uint32_t*)(d + o_cnt);
-    double* d_rows = (double*)(d + o_rows);
+    d = reinterpret_cast<char*>(dc->buf);
+    d_y = d + o_y;
+    d_off = (int64_t*)(d + o_off);
+    d_glen = (int32_t*)(d + o_glen);
+    d_km = (double*)(d + o_km);
+    d_ks = (double*)(d + o_ks);
+    d_status = (uint32_t*)(d + o_status);
+    d_niter = (int32_t*)(d + o_niter);
+    d_pval = (double*)(d + o_pval);
+    d_fit = (double*)(d + o_fit);
+    d_stats = (double*)(d + o_stats);
+    d_ready = (uint32_t*)(d + o_flags);
+    d_abort = d_ready + kMaxChunks;
+    d_done = d_abort + 1 + kMaxChunks;
+    d_nl = d_done + kMaxChunks;
+    d_nf = (uint32_t*)(d + o_nf);
+    d_nr = (uint32_t*)(d + o_nr);
+    d_cnt = (uint32_t*)(d + o_cnt);
+    d_rows = (double*)(d + o_rows);
 
+    return 0;
+}
+
+int HostCall::begin() {
     // the arena is shared with the previous call, which an asynchronous caller may not have waited for; and an
     // asynchronous call starts after the work already enqueued on the caller's stream
     if (dc->calls > 1) {
@@ -950,6 +977,10 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     CK(cudaMemcpyAsync(d + o_gc, b->grp_cond, (size_t)G * 4, cudaMemcpyDefault, dc->s_in));
     CK(cudaMemsetAsync(d_nf, 0, (size_t)kMaxChunks * 4, dc->s_in));
     CK(cudaMemsetAsync(d_nr, 0, (size_t)kMaxChunks * 4, dc->s_in));
+    return 0;
+}
+
+int HostCall::chained() {
     bool chain_launched = false, chain_understated = false, chain_helper = false;
     xpk::FitArgs chain_fa;
     xpk::FitChain chain_ch;
@@ -979,7 +1010,7 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
     double host_enq[kMaxChunks] = {0.0};  // XPB200_TRACE: when the host had enqueued the chunk (ms since entry)
     int meta_next = 0;
     const size_t chain_meta_bytes = (size_t)std::max(1, exp_int("XPB200_CHAIN_META_MB", 128)) << 20;  // reads per group of small-array copies
-    for (int c = 0; chain && c < nchunks; ++c) {
+    for (int c = 0; c < nchunks; ++c) {
         const int p0 = cut[c], p1 = cut[c + 1], pc = p1 - p0;
         const int64_t r0 = roff[p0], r1 = roff[p1];
         if (c == meta_next) {
@@ -1060,11 +1091,11 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
             chain_launched = true;
         }
     }
-    if (chain && chain_understated) {
+    if (chain_understated) {
         chain_bail(0);
         return fit_host_impl(device, b, m, ho, false);
     }
-    if (chain && chain_helper && exp_int("XPB200_CHAIN_HELPER", 1)) {
+    if (chain_helper && exp_int("XPB200_CHAIN_HELPER", 1)) {
         // Once every chunk's select phase is through, the SMs kept free have nothing left to do: a second launch of the
         // same kernel on them walks the same chain (a batch whose fit outlasts its copy - c3, c5 - would otherwise run
         // its whole second half on 142 of 148 SMs)
@@ -1254,7 +1285,11 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         }
         return 0;
     }
+    return 0;
 #undef CKB
+}
+
+int HostCall::chunked() {
     for (int c = 0; c < nchunks; ++c) {
         const int p0 = cut[c], p1 = cut[c + 1], pc = p1 - p0;
         if (pc == 0) continue;
@@ -1373,6 +1408,38 @@ int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m,
         }
     }
     return 0;
+}
+
+int fit_host_impl(int32_t device, const xpb200_batch* b, const xpb200_method* m, const HostOut& ho, bool allow_chain) {
+    CK(cudaSetDevice(device));
+    std::lock_guard<std::recursive_mutex> lk(g_cache_mu);
+    HostCall hc(device, b, m, ho);
+    if (int rc = hc.open_cache()) return rc;
+    if (ho.n_fitted) *ho.n_fitted = 0;
+    if (ho.n_rows) *ho.n_rows = 0;
+    if (hc.P == 0) {
+        if (hc.async) CK(cudaMemsetAsync(ho.counts_dev, 0, 8, ho.user_stream));
+        return 0;
+    }
+    if (int rc = hc.decide_chain(allow_chain)) return rc;
+    hc.cut = plan_chunks(hc.roff, hc.P, hc.eb, hc.chain);
+    hc.nchunks = (int)hc.cut.size() - 1;
+    DevCache* dc = hc.dc;
+    ++dc->calls;
+    hc.trace = exp_int("XPB200_TRACE", 0) != 0 && !hc.async;  // experiment builds: timed events per chunk, printed to stderr
+    if (hc.trace && !dc->t_0) {
+        CK(cudaEventCreate(&dc->t_0));
+        for (int i = 0; i < kMaxChunks; ++i) {
+            CK(cudaEventCreate(&dc->t_in[i]));
+            CK(cudaEventCreate(&dc->t_start[i]));
+            CK(cudaEventCreate(&dc->t_done[i]));
+        }
+    }
+    hc.host_t0 = std::chrono::steady_clock::now();
+    hc.n_streams = std::min(kComputeStreams, std::max(1, exp_int("XPB200_STREAMS", 3)));
+    if (int rc = hc.lay_out()) return rc;
+    if (int rc = hc.begin()) return rc;
+    return hc.chain ? hc.chained() : hc.chunked();
 }
 }  // namespace
 
