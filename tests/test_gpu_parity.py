@@ -583,6 +583,19 @@ def test_chained_host_pipeline(torch_cuda):
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
     cb = _lib.XpBatch(batch.n_positions, 6, 2, int(n.max()), batch.n_reads, *[ptr(a) for a in arrs], yfmt, 0, yscale)
     cm = method.c_struct()
+    # ... and of an f64 batch, which takes the chunk-by-chunk form in both calls
+    plain = make_batch(spec, KmerModel.load(), n_positions=90000)
+    rows_f64, _ = xf.fit_rows(plain, method)
+    yf, yfmt_f, yscale_f = xf._y_buffer(plain)
+    assert yfmt_f == 0 and len(rows_f64) == len(keep)
+    cb_f = _lib.XpBatch(batch.n_positions, 6, 2, int(n.max()), batch.n_reads, ptr(yf), *[ptr(a) for a in arrs[1:]], yfmt_f, 0, yscale_f)
+    rows_dev = torch.full((len(keep) + 3, W), -1.0, dtype=torch.float64, device="cuda:0")
+    counts = torch.zeros(2, dtype=torch.int32, device="cuda:0")
+    _lib.check(L.xpb200_fit_host_rows_async(0, C.byref(cb_f), C.byref(cm), rows_dev.data_ptr(), len(keep) + 3, 0, counts.data_ptr(),
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert counts.tolist() == [len(keep), dense.n_fitted]
+    np.testing.assert_array_equal(rows_dev.cpu().numpy()[:len(keep)], rows_f64)
     for cap in (len(keep) + 10, len(keep) - 7):
         rows_dev = torch.full((cap, W), -1.0, dtype=torch.float64, device="cuda:0")
         counts = torch.zeros(2, dtype=torch.int32, device="cuda:0")
