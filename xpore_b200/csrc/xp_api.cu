@@ -987,8 +987,8 @@ int HostCall::chained() {
     // An error return after the chained launch must not leave it polling for chunks that will never come
     auto chain_bail = [&](int rc) -> int {
         if (chain_launched) {
-            cudaMemsetAsync(d_abort, 0xFF, 4, dc->s_out);
-            cudaStreamSynchronize(dc->s_out);
+            cudaMemsetAsync(d_abort, 0xFF, 4, dc->s_poll);  // a stream nothing is ever queued on behind the launch
+            cudaStreamSynchronize(dc->s_poll);
             cudaStreamSynchronize(dc->s_fit);
             cudaStreamSynchronize(dc->s_help);
             for (int i = 0; i < kComputeStreams; ++i) cudaStreamSynchronize(dc->s_c[i]);
